@@ -1,0 +1,201 @@
+/* lvo.h — C ABI of liblvo.so: the B200 (sm_100a) drop-in for the per-frame hot path of the reference
+ * A-LOAM fork (ucmmesa/Lidar-Visual-Odometry).
+ *
+ * The reference exposes this path only as three ROS callback / loop bodies.  Each entry point below replaces
+ * exactly one of them (citations are into the reference tree):
+ *
+ *   lvo_extract_features  <-  laserCloudHandler body            src/scanRegistration.cpp:127-411
+ *   lvo_scan_to_scan      <-  odometry frame body               src/laserOdometry.cpp:353-641
+ *   lvo_scan_to_map       <-  mapping process() body            src/laserMapping.cpp:307-848
+ *
+ * Payload type is the reference's PointType = pcl::PointXYZI (include/aloam_velodyne/common.h:43); a
+ * lvo_cloud_view describes its memory without naming PCL (stride 32, xyz at 0, intensity at 16), or a packed
+ * float4 (stride 16, xyz at 0, intensity at 12).  Poses are (quaternion x,y,z,w ; translation) in double, the
+ * layout of the reference's `para_q/para_t` (laserOdometry.cpp:131-137) and `parameters[7]`
+ * (laserMapping.cpp:110-112).
+ *
+ * No exceptions cross this boundary; no torch / PCL / Eigen / ROS types appear in it.  All arithmetic runs in
+ * hand-written CUDA kernels; there is no CPU fallback: lvo_create fails with LVO_E_CUDA when no sm_100 device
+ * (or no CUDA device at all) is usable.
+ */
+#ifndef LVO_H_
+#define LVO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ---------------------------------------------------------------------------------------- */
+#define LVO_OK 0
+#define LVO_E_BADARG (-1)   /* null pointer, bad stride, unsupported n_scans (reference: ROS_BREAK, scanRegistration.cpp:203) */
+#define LVO_E_CAPACITY (-2) /* an input exceeds the context's capacities, or an output buffer is too small          */
+#define LVO_E_CUDA (-3)     /* CUDA error (sticky); text through lvo_last_error                                    */
+#define LVO_E_STATE (-4)    /* call order violated (e.g. lane out of range)                                        */
+/* positive = the reference's soft conditions; outputs are still valid */
+#define LVO_W_FIRST_FRAME 1   /* laserOdometry.cpp:355-358: first frame only initialises                           */
+#define LVO_W_FEW_CORR 2      /* laserOdometry.cpp:566-568: < 10 correspondences in some outer iteration           */
+#define LVO_W_MAP_TOO_SMALL 3 /* laserMapping.cpp:554,730-733: map too small, pose = initial guess, map updated    */
+
+/* ---- plain data ------------------------------------------------------------------------------------------ */
+typedef struct lvo_point { float x, y, z, intensity; } lvo_point; /* device + output layout: packed float4 */
+
+typedef struct lvo_cloud_view { /* borrowed for the duration of the call */
+  const void* data;
+  size_t n;             /* number of points */
+  size_t stride;        /* bytes between points: 32 for pcl::PointXYZI, 16 for lvo_point */
+  size_t off_xyz;       /* byte offset of x (y, z follow) */
+  size_t off_intensity; /* byte offset of intensity */
+} lvo_cloud_view;
+
+typedef struct lvo_cloud_out { /* caller-owned; n is written back; LVO_E_CAPACITY if cap < n */
+  lvo_point* data;
+  size_t cap;
+  size_t n;
+} lvo_cloud_out;
+
+typedef struct lvo_pose { double q[4]; /* x,y,z,w */ double t[3]; } lvo_pose;
+
+typedef struct lvo_config {
+  int n_scans;           /* 16 | 32 | 64                        scanRegistration.cpp:466                   */
+  double minimum_range;  /* m                                   scanRegistration.cpp:468                   */
+  double line_res;       /* corner voxel leaf, m                laserMapping.cpp:902                        */
+  double plane_res;      /* surf voxel leaf, m                  laserMapping.cpp:903                        */
+  int skip_frame;        /* mapping_skip_frame                  laserOdometry.cpp:274                       */
+  int outer_iters;       /* 10                                  laserOdometry.cpp:364, laserMapping.cpp:562 */
+  int lm_max_iters;      /* 4                                   laserOdometry.cpp:573, laserMapping.cpp:715 */
+  double huber;          /* 0.1                                 laserOdometry.cpp:369, laserMapping.cpp:565 */
+  int device;            /* CUDA ordinal                                                                    */
+  int lanes;             /* independent sequences advanced in lock-step by the *_batch entry points (>=1)  */
+  int max_points;        /* capacity per sweep (reference: 400000, scanRegistration.cpp:66); 0 = 262144    */
+  int max_map_corner;    /* capacity of the whole corner map per lane, points; 0 = 1<<20                   */
+  int max_map_surf;      /* capacity of the whole surf map per lane, points;   0 = 1<<21                   */
+} lvo_config;
+
+/* Per-call counters, also the parity probes (SURVEY §5 "Metrics / logging").  One record per lane. */
+typedef struct lvo_stats {
+  /* lvo_extract_features */
+  int n_in, n_kept, n_sharp, n_less_sharp, n_flat, n_less_flat;
+  /* lvo_scan_to_scan: per outer iteration */
+  int odo_corner_corr[16], odo_plane_corr[16], odo_lm_iters[16];
+  double odo_final_cost[16];
+  /* lvo_scan_to_map */
+  int map_corner_from_map, map_surf_from_map, map_corner_stack, map_surf_stack;
+  int map_corner_corr[16], map_surf_corr[16], map_lm_iters[16];
+  double map_final_cost[16];
+  int map_corner_total, map_surf_total; /* points in all 4851 cubes after insertion + re-filter */
+  int center_cube[3], cen[3];           /* centerCubeI/J/K and laserCloudCen{Width,Height,Depth} after shifting */
+} lvo_stats;
+
+typedef struct lvo_ctx lvo_ctx; /* one per (GPU, group of lanes); owns streams, device arenas, cross-frame state */
+
+/* ---- lifetime -------------------------------------------------------------------------------------------- */
+void lvo_default_config(lvo_config* cfg); /* HDL-64 launch values: 64, 5.0, 0.4, 0.8, 1, 10, 4, 0.1, dev 0, 1 lane */
+int lvo_create(const lvo_config* cfg, lvo_ctx** out);
+int lvo_destroy(lvo_ctx* ctx);
+const char* lvo_last_error(const lvo_ctx* ctx);
+int lvo_get_stats(const lvo_ctx* ctx, int lane, lvo_stats* out, size_t bytes);
+
+/* ---- the three drop-in entry points (lane 0; synchronous on return) --------------------------------------- */
+
+/* scanRegistration.cpp:127-411.  `sweep` = /velodyne_points; outputs = /velodyne_cloud_2, /laser_cloud_sharp,
+ * /laser_cloud_less_sharp, /laser_cloud_flat, /laser_cloud_less_flat (:413-441).  Any output may be NULL. */
+int lvo_extract_features(lvo_ctx* ctx, lvo_cloud_view sweep, lvo_cloud_out* full, lvo_cloud_out* sharp,
+                         lvo_cloud_out* less_sharp, lvo_cloud_out* flat, lvo_cloud_out* less_flat);
+
+/* laserOdometry.cpp:353-641.  Keeps para_q/para_t, q_w_curr/t_w_curr and the two "last" clouds in ctx.
+ * T_last_curr = (para_q, para_t) after the solve; T_w_curr = accumulated odometry pose (:581-582). */
+int lvo_scan_to_scan(lvo_ctx* ctx, lvo_cloud_view sharp, lvo_cloud_view less_sharp, lvo_cloud_view flat,
+                     lvo_cloud_view less_flat, lvo_pose* T_last_curr, lvo_pose* T_w_curr);
+
+/* laserMapping.cpp:307-848.  corner_last / surf_last are what laserOdometry publishes (:646-656), i.e. the
+ * current frame's less-sharp / less-flat clouds; full_or_null is /velodyne_cloud_3; T_wodom_curr is
+ * /laser_odom_to_init.  Writes /aft_mapped_to_init to T_wmap_curr and, if requested, /velodyne_cloud_registered. */
+int lvo_scan_to_map(lvo_ctx* ctx, lvo_cloud_view corner_last, lvo_cloud_view surf_last, lvo_cloud_view full_or_null,
+                    const lvo_pose* T_wodom_curr, lvo_pose* T_wmap_curr, lvo_cloud_out* registered_or_null);
+
+/* ---- device-resident, batched pipeline (no host hops between the three stages) --------- */
+
+/* One frame for every lane: extract -> scan-to-scan -> scan-to-map, all on device.  sweeps[l] is the sweep of
+ * lane l (host memory; copied through pinned staging).  Poses may be NULL.  Returns the max status over lanes;
+ * per-lane statuses through lvo_lane_status. */
+int lvo_step_batch(lvo_ctx* ctx, const lvo_cloud_view* sweeps, lvo_pose* T_wodom_curr, lvo_pose* T_wmap_curr);
+
+/* Same, with sweeps already resident in device memory as packed lvo_point arrays (d_sweeps[l] is a device
+ * pointer with n[l] points).  This is what bench.py's device-resident `value` times. */
+int lvo_step_batch_dev(lvo_ctx* ctx, const lvo_point* const* d_sweeps, const size_t* n, lvo_pose* T_wodom_curr,
+                       lvo_pose* T_wmap_curr);
+int lvo_lane_status(const lvo_ctx* ctx, int lane);
+
+/* ---- state export / import (SURVEY §5 "Checkpoint / resume"; needed to start from a pre-filled map) ------- */
+
+/* Replace the map of `lane` with the given cubes.  cube_ind[i] is the reference's array index
+ * i + 21*j + 441*k (laserMapping.cpp:522) of point i; points of one cube keep their relative order. */
+int lvo_map_import(lvo_ctx* ctx, int lane, const lvo_point* corner, const int* corner_cube, size_t n_corner,
+                   const lvo_point* surf, const int* surf_cube, size_t n_surf);
+/* which: 0 = corner, 1 = surf.  Points are returned cube-major in array-index order; cube_out may be NULL. */
+int lvo_map_export(lvo_ctx* ctx, int lane, int which, lvo_cloud_out* pts, int* cube_out);
+/* (q_wmap_wodom, t_wmap_wodom), laserMapping.cpp:116-117 */
+int lvo_get_map_correction(lvo_ctx* ctx, int lane, lvo_pose* T_wmap_wodom);
+int lvo_set_map_correction(lvo_ctx* ctx, int lane, const lvo_pose* T_wmap_wodom);
+/* (para_q, para_t) and (q_w_curr, t_w_curr) of the odometry stage */
+int lvo_set_odometry_state(lvo_ctx* ctx, int lane, const lvo_pose* T_last_curr, const lvo_pose* T_w_curr);
+
+/* ---- parity probes: copy an intermediate device array of `lane` to host ----------------------------------- */
+enum lvo_probe {
+  LVO_P_FULL = 0,          /* lvo_point[n_kept]  ring-ordered cloud                       scanRegistration.cpp:246-252 */
+  LVO_P_CURVATURE = 1,     /* float[n_kept]      cloudCurvature                           :262                        */
+  LVO_P_SORT_IND = 2,      /* int[n_kept]        cloudSortInd after all sector sorts      :288                        */
+  LVO_P_LABEL = 3,         /* int[n_kept]        cloudLabel                               :303,309,355                */
+  LVO_P_PICKED = 4,        /* int[n_kept]        cloudNeighborPicked                      :317-342                    */
+  LVO_P_SCAN_START = 5,    /* int[n_scans]       scanStartInd                             :249                        */
+  LVO_P_SCAN_END = 6,      /* int[n_scans]       scanEndInd                               :251                        */
+  LVO_P_SHARP = 7, LVO_P_LESS_SHARP = 8, LVO_P_FLAT = 9, LVO_P_LESS_FLAT = 10, /* lvo_point[]                          */
+  LVO_P_ODO_CORNER_CORR = 11, /* int[outer][n_sharp][2]  (closestPointInd, minPointInd2) or -1  laserOdometry.cpp:388-442 */
+  LVO_P_ODO_PLANE_CORR = 12,  /* int[outer][n_flat][3]   (closest, minPointInd2, minPointInd3)   :472-534             */
+  LVO_P_ODO_LM_TRACE = 13,    /* double[outer][lm_max_iters+1][10]: x(7), cost, radius, flags    ceres::Solve :576    */
+  LVO_P_MAP_CORNER_STACK = 14, LVO_P_MAP_SURF_STACK = 15, /* lvo_point[]                         laserMapping.cpp:542-550 */
+  LVO_P_MAP_CORNER_FROM_MAP = 16, LVO_P_MAP_SURF_FROM_MAP = 17, /* lvo_point[] in gather order    :531-537             */
+  LVO_P_MAP_CORNER_KNN = 18,  /* int[outer][n_corner_stack][5], -1 row if d5^2 >= 1.0             :582-584             */
+  LVO_P_MAP_SURF_KNN = 19,    /* int[outer][n_surf_stack][5]                                      :648-652             */
+  LVO_P_MAP_CORNER_VALID = 20,/* int[outer][n_corner_stack]  1 if an edge factor was added        :611                 */
+  LVO_P_MAP_SURF_VALID = 21,  /* int[outer][n_surf_stack]    1 if a plane factor was added        :681                 */
+  LVO_P_MAP_LM_TRACE = 22,    /* as LVO_P_ODO_LM_TRACE                                            ceres::Solve :720    */
+  LVO_P_REGISTERED = 23       /* lvo_point[n_kept]                                                :838-842             */
+};
+/* Copies up to cap_bytes; *n_bytes gets the full size (so a too-small buffer can be detected). */
+int lvo_probe_fetch(lvo_ctx* ctx, int lane, int what, void* out, size_t cap_bytes, size_t* n_bytes);
+
+/* Stand-alone operators (used by parity tests and by bench.py's per-kernel roofline; lane 0 scratch). */
+/* pcl::VoxelGrid::filter restated (scanRegistration.cpp:401-405, laserMapping.cpp:543-549,793-799). */
+int lvo_voxel_downsample(lvo_ctx* ctx, lvo_cloud_view in, float leaf, lvo_cloud_out* out);
+/* Exact K-NN (K<=5) of queries in cloud, squared-distance gate `max_sq`; ind/sq are [nq][K]; -1 when fewer
+ * than K points lie inside the gate.  Replaces pcl::KdTreeFLANN::nearestKSearch + the d^2 gate
+ * (laserMapping.cpp:582-584; laserOdometry.cpp:386-389). */
+int lvo_knn(lvo_ctx* ctx, lvo_cloud_view cloud, lvo_cloud_view queries, int K, float max_sq, int* ind, float* sq);
+
+/* Throughput-mode 5-NN benchmark entry: S independent (map, query) problems in ONE launch.
+ * d_maps / d_queries are device pointers to packed points, problems laid out back to back with the given
+ * per-problem counts.  Builds the cell grids (untimed part) on first call with build != 0, then runs the search
+ * kernel `reps` times; returns the average kernel milliseconds in *ms (CUDA events on the ctx stream). */
+int lvo_knn5_throughput(lvo_ctx* ctx, const lvo_point* d_maps, const int* map_counts, const lvo_point* d_queries,
+                        const int* query_counts, int S, int reps, int* d_ind_out, float* d_sq_out, float* ms);
+
+/* ---- timing: the reference's TicToc stage names, CUDA-event milliseconds of the last call ------ */
+typedef struct lvo_timings {
+  float extract_ms;       /* "scan registration time"   scanRegistration.cpp:456 */
+  float odometry_ms;      /* "whole laserOdometry time" laserOdometry.cpp:665    */
+  float mapping_ms;       /* "whole mapping time"       laserMapping.cpp:852     */
+  float knn_ms;           /* sum of the 5-NN kernels of the last scan-to-map call */
+  int knn_launches;
+  int kernel_launches;    /* kernels launched by the last call (for bench.py's gpu_launches) */
+  double knn_bytes;       /* algorithmic bytes of those 5-NN launches: 16 M + 56 Q each */
+} lvo_timings;
+int lvo_get_timings(const lvo_ctx* ctx, lvo_timings* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LVO_H_ */

@@ -1,0 +1,323 @@
+// oracle/ceres_lm.hpp — TEST INFRASTRUCTURE ONLY (see oracle/common.hpp).
+// Restates what `ceres::Solve` does for the reference's problems (Ceres 1.12.0, docker/Dockerfile:3; NOT in
+// /root/reference — restated from the published algorithm, parity unpinned):
+//   * residual blocks = the functors of src/lidarFactor.hpp:12-138 under ceres::HuberLoss(0.1)
+//     (laserOdometry.cpp:369, laserMapping.cpp:565) with Ceres' Corrector (rho'' <= 0 branch);
+//   * parameter blocks q (4, EigenQuaternionParameterization) and t (3)  (laserOdometry.cpp:370-376);
+//   * TrustRegionMinimizer + LevenbergMarquardtStrategy + DENSE_QR, max_num_iterations = 4, all other options at
+//     their 1.12 defaults (laserOdometry.cpp:571-576, laserMapping.cpp:713-720).  SURVEY §8a rows A17-A19.
+//
+// Two builds of this file exist:
+//   default                      : residuals/Jacobians analytic (the identity verified in SURVEY §8a A17),
+//                                  3x3 eigen / least squares by the small routines in linalg.hpp;
+//   -DLVO_ORACLE_USE_REFERENCE   : residuals/Jacobians by forward-mode autodiff of the reference's OWN functors
+//                                  (#include "lidarFactor.hpp" from /root/reference/src through oracle/shim), and
+//                                  Eigen 3.3.7's SelfAdjointEigenSolver / colPivHouseholderQr / householderQr.
+#pragma once
+#include "common.hpp"
+#include "linalg.hpp"
+#include <cfloat>
+
+#ifdef LVO_ORACLE_USE_REFERENCE
+#include "lidarFactor.hpp"  // the reference's file, found through -I/root/reference/src
+#endif
+
+namespace lvo_oracle {
+
+enum FactorType { F_EDGE = 0, F_PLANE = 1, F_PLANE_NORM = 2 };
+
+// Parameters of one residual block.
+//  F_EDGE       LidarEdgeFactor(curr_point=c, last_point_a=a, last_point_b=b, s=1)        lidarFactor.hpp:12-55
+//  F_PLANE      LidarPlaneFactor(curr_point=c, j=a, l=b, m=m, s=1)                         lidarFactor.hpp:57-104
+//  F_PLANE_NORM LidarPlaneNormFactor(curr_point=c, plane_unit_norm=a, negative_OA_dot_norm=d)  lidarFactor.hpp:106-138
+struct Factor {
+  int type;
+  Vec3 c, a, b, m;
+  double d;
+};
+
+struct LmTraceRow { double x[7]; double cost; double radius; int flags; };
+// flags: bit0 step valid, bit1 step accepted, bit2 terminated by parameter tolerance, bit3 function tolerance,
+//        bit4 gradient tolerance, bit5 this row is the initial evaluation
+
+struct LmOptions {
+  int max_num_iterations = 4;
+  double huber = 0.1;
+  double initial_trust_region_radius = 1e4, max_trust_region_radius = 1e16, min_trust_region_radius = 1e-32;
+  double min_relative_decrease = 1e-3;
+  double min_lm_diagonal = 1e-6, max_lm_diagonal = 1e32;
+  double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8;
+  int max_num_consecutive_invalid_steps = 5;
+};
+
+struct LmSummary { int iterations = 0; double initial_cost = 0, final_cost = 0; int num_successful = 0; };
+
+// EigenQuaternionParameterization::Plus (ceres/local_parameterization.cc): x_plus = q_delta * x,
+// q_delta = (cos|d|, sin|d|/|d| * d); translation block is plain addition.
+inline void plus7(const double* x, const double* delta, double* xp) {
+  const double nd = sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
+  if (nd > 0.0) {
+    const double s = sin(nd) / nd;
+    Quat dq{s * delta[0], s * delta[1], s * delta[2], cos(nd)};
+    Quat q{x[0], x[1], x[2], x[3]};
+    Quat r = qmul(dq, q);
+    xp[0] = r.x; xp[1] = r.y; xp[2] = r.z; xp[3] = r.w;
+  } else {
+    xp[0] = x[0]; xp[1] = x[1]; xp[2] = x[2]; xp[3] = x[3];
+  }
+  xp[4] = x[4] + delta[3]; xp[5] = x[5] + delta[4]; xp[6] = x[6] + delta[5];
+}
+
+// Residual (k = 3 or 1 rows) and local 6-column Jacobian of one block at x = (q xyzw, t), before the loss.
+inline int eval_factor(const Factor& f, const double* x, double* r, double* J /* k x 6 row-major, may be null */) {
+#ifdef LVO_ORACLE_USE_REFERENCE
+  typedef ceres::Jet<double, 7> JetT;
+  JetT q[4], t[3], res[3];
+  for (int i = 0; i < 4; ++i) q[i] = JetT(x[i], i);
+  for (int i = 0; i < 3; ++i) t[i] = JetT(x[4 + i], 4 + i);
+  int k;
+  Eigen::Vector3d c(f.c.x, f.c.y, f.c.z), a(f.a.x, f.a.y, f.a.z), b(f.b.x, f.b.y, f.b.z), m(f.m.x, f.m.y, f.m.z);
+  if (f.type == F_EDGE) { LidarEdgeFactor fn(c, a, b, 1.0); fn(q, t, res); k = 3; }
+  else if (f.type == F_PLANE) { LidarPlaneFactor fn(c, a, b, m, 1.0); fn(q, t, res); k = 1; }
+  else { LidarPlaneNormFactor fn(c, a, f.d); fn(q, t, res); k = 1; }
+  // EigenQuaternionParameterization::ComputeJacobian (4x3, xyzw storage)
+  const double P[4][3] = {{x[3], x[2], -x[1]}, {-x[2], x[3], x[0]}, {x[1], -x[0], x[3]}, {-x[0], -x[1], -x[2]}};
+  for (int i = 0; i < k; ++i) {
+    r[i] = res[i].a;
+    if (J) {
+      for (int cidx = 0; cidx < 3; ++cidx) {
+        double s = 0;
+        for (int g = 0; g < 4; ++g) s += res[i].v[g] * P[g][cidx];
+        J[i * 6 + cidx] = s;
+        J[i * 6 + 3 + cidx] = res[i].v[4 + cidx];
+      }
+    }
+  }
+  return k;
+#else
+  Quat q{x[0], x[1], x[2], x[3]};
+  Vec3 rc = rotate(q, f.c);
+  Vec3 lp{rc.x + x[4], rc.y + x[5], rc.z + x[6]};
+  // d lp / d delta = -2 [R c]_x  (x (+) delta = q_delta * x, delta = half rotation vector); d lp / d t = I
+  const double Jp[3][3] = {{0, 2 * rc.z, -2 * rc.y}, {-2 * rc.z, 0, 2 * rc.x}, {2 * rc.y, -2 * rc.x, 0}};
+  if (f.type == F_EDGE) {
+    Vec3 u{lp.x - f.a.x, lp.y - f.a.y, lp.z - f.a.z}, v{lp.x - f.b.x, lp.y - f.b.y, lp.z - f.b.z};
+    Vec3 nu = cross(u, v);
+    Vec3 de{f.a.x - f.b.x, f.a.y - f.b.y, f.a.z - f.b.z};
+    double den = sqrt(de.x * de.x + de.y * de.y + de.z * de.z);
+    r[0] = nu.x / den; r[1] = nu.y / den; r[2] = nu.z / den;
+    if (J) {
+      // d r / d lp = -[a-b]_x / |a-b|
+      const double D[3][3] = {{0, de.z / den, -de.y / den}, {-de.z / den, 0, de.x / den}, {de.y / den, -de.x / den, 0}};
+      for (int i = 0; i < 3; ++i)
+        for (int cidx = 0; cidx < 3; ++cidx) {
+          J[i * 6 + cidx] = D[i][0] * Jp[0][cidx] + D[i][1] * Jp[1][cidx] + D[i][2] * Jp[2][cidx];
+          J[i * 6 + 3 + cidx] = D[i][cidx];
+        }
+    }
+    return 3;
+  }
+  Vec3 n;
+  double r0;
+  if (f.type == F_PLANE) {
+    Vec3 jl{f.a.x - f.b.x, f.a.y - f.b.y, f.a.z - f.b.z}, jm{f.a.x - f.m.x, f.a.y - f.m.y, f.a.z - f.m.z};
+    n = cross(jl, jm);                                   // lidarFactor.hpp:64
+    double nn = sqrt(n.x * n.x + n.y * n.y + n.z * n.z);  // :65 normalize()
+    n.x /= nn; n.y /= nn; n.z /= nn;
+    r0 = (lp.x - f.a.x) * n.x + (lp.y - f.a.y) * n.y + (lp.z - f.a.z) * n.z;
+  } else {
+    n = f.a;
+    r0 = (n.x * lp.x + n.y * lp.y + n.z * lp.z) + f.d;
+  }
+  r[0] = r0;
+  if (J) {
+    const double nv[3] = {n.x, n.y, n.z};
+    for (int cidx = 0; cidx < 3; ++cidx) {
+      J[cidx] = nv[0] * Jp[0][cidx] + nv[1] * Jp[1][cidx] + nv[2] * Jp[2][cidx];
+      J[3 + cidx] = nv[cidx];
+    }
+  }
+  return 1;
+#endif
+}
+
+// Program evaluation as ceres::internal::ProgramEvaluator + ResidualBlock::Evaluate:
+//   cost = 1/2 sum rho(|r|^2); r and J rows scaled by sqrt(rho') (Corrector, rho'' <= 0 branch).
+struct Evaluation {
+  double cost = 0;
+  std::vector<double> r;   // corrected residuals
+  std::vector<double> J;   // corrected Jacobian, rows x 6 row-major
+  double g[6];             // J^T r
+};
+inline void evaluate(const std::vector<Factor>& F, const double* x, double huber, bool jac, Evaluation& e) {
+  e.cost = 0;
+  e.r.clear();
+  if (jac) e.J.clear();
+  const double b = huber * huber;
+  for (const Factor& f : F) {
+    double r[3], J[18];
+    int k = eval_factor(f, x, r, jac ? J : nullptr);
+    double s = 0;
+    for (int i = 0; i < k; ++i) s += r[i] * r[i];
+    double rho0, rho1;
+    if (s > b) { double rr = sqrt(s); rho0 = 2 * huber * rr - b; rho1 = std::max(DBL_MIN, huber / rr); }
+    else { rho0 = s; rho1 = 1.0; }
+    e.cost += 0.5 * rho0;
+    double sc = sqrt(rho1);
+    for (int i = 0; i < k; ++i) {
+      e.r.push_back(r[i] * sc);
+      if (jac) for (int c = 0; c < 6; ++c) e.J.push_back(J[i * 6 + c] * sc);
+    }
+  }
+  if (jac) {
+    for (int c = 0; c < 6; ++c) e.g[c] = 0;
+    size_t rows = e.r.size();
+    for (size_t i = 0; i < rows; ++i)
+      for (int c = 0; c < 6; ++c) e.g[c] += e.J[i * 6 + c] * e.r[i];
+  }
+}
+
+// ceres::Solve restated.  x (7) is updated in place; trace (optional) gets one row per iteration incl. row 0.
+inline LmSummary solve(const std::vector<Factor>& F, double* x, const LmOptions& opt, std::vector<LmTraceRow>* trace) {
+  LmSummary sum;
+  auto push_trace = [&](double cost, double radius, int flags) {
+    if (!trace) return;
+    LmTraceRow row;
+    for (int i = 0; i < 7; ++i) row.x[i] = x[i];
+    row.cost = cost; row.radius = radius; row.flags = flags;
+    trace->push_back(row);
+  };
+  if (F.empty()) {  // Ceres: "Terminating: Function tolerance reached. No non-constant parameter blocks found" / nothing to do
+    push_trace(0, opt.initial_trust_region_radius, 32);
+    return sum;
+  }
+  Evaluation e;
+  evaluate(F, x, opt.huber, true, e);
+  double cost = e.cost;
+  sum.initial_cost = sum.final_cost = cost;
+  size_t rows = e.r.size();
+  double x_norm = 0;
+  for (int i = 0; i < 7; ++i) x_norm += x[i] * x[i];
+  x_norm = sqrt(x_norm);
+
+  auto gradient_max_norm = [&](const Evaluation& ev) {
+    double ng[6], xp[7];
+    for (int c = 0; c < 6; ++c) ng[c] = -ev.g[c];
+    plus7(x, ng, xp);
+    double m = 0;
+    for (int i = 0; i < 7; ++i) m = std::max(m, fabs(x[i] - xp[i]));
+    return m;
+  };
+  // jacobi scaling, frozen at iteration 0: scale = 1 / (1 + ||J_col||)
+  double scale[6];
+  for (int c = 0; c < 6; ++c) {
+    double s = 0;
+    for (size_t i = 0; i < rows; ++i) s += e.J[i * 6 + c] * e.J[i * 6 + c];
+    scale[c] = 1.0 / (1.0 + sqrt(s));
+  }
+  auto scale_columns = [&](Evaluation& ev) {
+    for (size_t i = 0; i < rows; ++i)
+      for (int c = 0; c < 6; ++c) ev.J[i * 6 + c] *= scale[c];
+  };
+  double gmax = gradient_max_norm(e);
+  scale_columns(e);
+  double radius = opt.initial_trust_region_radius, decrease_factor = 2.0;
+  bool reuse_diagonal = false;
+  double diagonal[6];
+  push_trace(cost, radius, 32 | (gmax <= opt.gradient_tolerance ? 16 : 0));
+  if (gmax <= opt.gradient_tolerance) return sum;
+
+  int iteration = 0, invalid_run = 0;
+  std::vector<double> A, rhs, model;
+  while (true) {
+    if (iteration >= opt.max_num_iterations) break;  // NO_CONVERGENCE
+    ++iteration;
+    sum.iterations = iteration;
+    // LevenbergMarquardtStrategy::ComputeStep
+    if (!reuse_diagonal) {
+      for (int c = 0; c < 6; ++c) {
+        double s = 0;
+        for (size_t i = 0; i < rows; ++i) s += e.J[i * 6 + c] * e.J[i * 6 + c];
+        diagonal[c] = std::min(std::max(s, opt.min_lm_diagonal), opt.max_lm_diagonal);
+      }
+    }
+    double D[6];
+    for (int c = 0; c < 6; ++c) D[c] = sqrt(diagonal[c] / radius);
+    // DenseQRSolver: min || [J; diag(D)] y - [r; 0] ||, then step = -y
+    A.assign((rows + 6) * 6, 0.0);
+    rhs.assign(rows + 6, 0.0);
+    std::copy(e.J.begin(), e.J.end(), A.begin());
+    for (int c = 0; c < 6; ++c) A[(rows + c) * 6 + c] = D[c];
+    std::copy(e.r.begin(), e.r.end(), rhs.begin());
+    double step[6];
+    bool ok = least_squares_qr(A.data(), (int)rows + 6, 6, rhs.data(), step);
+    reuse_diagonal = true;
+    bool valid = ok;
+    double model_cost_change = 0;
+    if (ok) {
+      for (int c = 0; c < 6; ++c) { step[c] = -step[c]; if (!std::isfinite(step[c])) valid = false; }
+    }
+    if (valid) {
+      // model_cost_change = -(J step)^T (r + J step / 2)
+      for (size_t i = 0; i < rows; ++i) {
+        double m = 0;
+        for (int c = 0; c < 6; ++c) m += e.J[i * 6 + c] * step[c];
+        model_cost_change -= m * (e.r[i] + m / 2.0);
+      }
+      if (model_cost_change <= 0.0) valid = false;
+    }
+    if (!valid) {
+      if (++invalid_run >= opt.max_num_consecutive_invalid_steps) { push_trace(cost, radius, 0); break; }
+      radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;  // StepIsInvalid
+      push_trace(cost, radius, 0);
+      if (radius < opt.min_trust_region_radius) break;
+      continue;
+    }
+    invalid_run = 0;
+    double delta[6], xp[7];
+    for (int c = 0; c < 6; ++c) delta[c] = step[c] * scale[c];
+    plus7(x, delta, xp);
+    Evaluation ec;
+    evaluate(F, xp, opt.huber, false, ec);
+    double new_cost = ec.cost;
+    double step_norm = 0;
+    for (int i = 0; i < 7; ++i) step_norm += (x[i] - xp[i]) * (x[i] - xp[i]);
+    step_norm = sqrt(step_norm);
+    if (step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) {
+      push_trace(cost, radius, 1 | 4);  // candidate discarded
+      break;
+    }
+    double cost_change = cost - new_cost;
+    if (fabs(cost_change) <= opt.function_tolerance * cost) {
+      push_trace(cost, radius, 1 | 8);  // candidate discarded
+      break;
+    }
+    double relative_decrease = cost_change / model_cost_change;
+    if (relative_decrease > opt.min_relative_decrease) {
+      ++sum.num_successful;
+      radius = radius / std::max(1.0 / 3.0, 1.0 - pow(2.0 * relative_decrease - 1.0, 3));  // StepAccepted
+      radius = std::min(opt.max_trust_region_radius, radius);
+      decrease_factor = 2.0;
+      reuse_diagonal = false;
+      for (int i = 0; i < 7; ++i) x[i] = xp[i];
+      x_norm = 0;
+      for (int i = 0; i < 7; ++i) x_norm += x[i] * x[i];
+      x_norm = sqrt(x_norm);
+      evaluate(F, x, opt.huber, true, e);
+      cost = e.cost;
+      gmax = gradient_max_norm(e);
+      scale_columns(e);
+      sum.final_cost = cost;
+      bool gconv = gmax <= opt.gradient_tolerance;
+      push_trace(cost, radius, 1 | 2 | (gconv ? 16 : 0));
+      if (gconv) break;
+    } else {
+      radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;  // StepRejected
+      push_trace(cost, radius, 1);
+    }
+    if (radius < opt.min_trust_region_radius) break;
+  }
+  return sum;
+}
+
+}  // namespace lvo_oracle
