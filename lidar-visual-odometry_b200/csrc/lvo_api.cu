@@ -1,0 +1,699 @@
+// lvo_api.cu — the C ABI of liblvo.so (include/lvo.h): context, device arenas, and the host-side enqueue logic.
+// Single translation unit: the kernels live in the .cuh files included below.  Compiled with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo
+// (-fmad=false: the reference's x86 build has no FMA contraction, SURVEY §7 hard part 1).
+#include "lvo_internal.h"
+#include "lvo_prims.cuh"
+#include "lvo_extract.cuh"
+#include "lvo_voxel.cuh"
+#include "lvo_knn.cuh"
+#include "lvo_solver.cuh"
+#include "lvo_odometry.cuh"
+#include "lvo_mapping.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+struct lvo_ctx {
+  lvo_config cfg;
+  int lanes, P, cap_sharp, cap_lsharp, cap_flat;
+  cudaStream_t st = nullptr;
+  std::string err;
+  std::vector<void*> allocs, pinned;
+  LaneState* d_ls = nullptr;
+  LaneState* h_ls = nullptr;  // pinned mirror
+  ExtractArgs ex;
+  OdoArgs odo;
+  MapArgs map;
+  SolveArgs solve;
+  GridSet gknn;               // 1-problem grid for the stand-alone lvo_knn operator (shares storage with map.grid)
+  GridProblem* d_knn_prob = nullptr;
+  int* d_knn_n = nullptr;
+  unsigned char* d_raw = nullptr;   // [lanes][P * 32] raw sweep records
+  size_t raw_lane_bytes = 0;
+  const unsigned char** d_in_ptr = nullptr; const unsigned char** h_in_ptr = nullptr;
+  int* d_in_n = nullptr; int* h_in_n = nullptr;
+  float4* d_upload = nullptr;       // scratch for strided uploads (P * 32 bytes)
+  int* d_knn_ind = nullptr; float* d_knn_sq = nullptr;
+  double* d_trace[2] = {nullptr, nullptr};
+  long long launches = 0;
+  long long frame = 0;
+  std::vector<int> lane_status;
+  cudaEvent_t ev[8];
+  std::vector<cudaEvent_t> knn_ev;
+  lvo_timings tim;
+  bool have_knn_events = false;
+};
+
+void lvo_set_error(lvo_ctx* ctx, const std::string& msg) { if (ctx) ctx->err = msg; }
+
+namespace {
+
+template <class T>
+int dalloc(lvo_ctx* c, T** p, size_t n, bool zero = true) {
+  void* q = nullptr;
+  size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) { lvo_set_error(c, std::string("cudaMalloc: ") + cudaGetErrorString(e)); return LVO_E_CUDA; }
+  if (zero) cudaMemset(q, 0, bytes);
+  c->allocs.push_back(q);
+  *p = (T*)q;
+  return LVO_OK;
+}
+template <class T>
+int halloc(lvo_ctx* c, T** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t e = cudaMallocHost(&q, std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) { lvo_set_error(c, std::string("cudaMallocHost: ") + cudaGetErrorString(e)); return LVO_E_CUDA; }
+  memset(q, 0, std::max<size_t>(n, 1) * sizeof(T));
+  c->pinned.push_back(q);
+  *p = (T*)q;
+  return LVO_OK;
+}
+#define LVO_TRY(x) do { int _r = (x); if (_r != LVO_OK) return _r; } while (0)
+
+int alloc_scan(lvo_ctx* c, LvoScanScratch* s, size_t n_cap) {
+  s->cap_tiles = lvo_div_up((long long)n_cap, LVO_SCAN_TILE) + 2;
+  return dalloc(c, &s->partial, (size_t)s->cap_tiles);
+}
+int alloc_grid(lvo_ctx* c, GridSet* g, int nprob, int cells_cap, size_t pts_total, int pts_per_problem) {
+  g->nprob = nprob; g->cells_cap_per_problem = cells_cap; g->pts_cap_per_problem = pts_per_problem;
+  LVO_TRY(dalloc(c, &g->prob, (size_t)nprob));
+  LVO_TRY(dalloc(c, &g->table, (size_t)nprob * cells_cap + 1));
+  LVO_TRY(dalloc(c, &g->d_table_len, 1));
+  LVO_TRY(dalloc(c, &g->rank, pts_total));
+  LVO_TRY(dalloc(c, &g->pt_off, (size_t)nprob + 1));
+  LVO_TRY(dalloc(c, &g->sorted_pts, pts_total));
+  LVO_TRY(dalloc(c, &g->sorted_id, pts_total));
+  LVO_TRY(alloc_scan(c, &g->scan, (size_t)nprob * cells_cap + 1));
+  return LVO_OK;
+}
+
+__global__ void k_unpack(const unsigned char* raw, int n, int stride, int off_xyz, int off_i, float4* out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride + off_xyz);
+    const float w = *reinterpret_cast<const float*>(raw + (size_t)i * stride + off_i);
+    out[i] = make_float4(p[0], p[1], p[2], w);
+  }
+}
+struct SetCounts { int what; int v[4]; double pose[7]; };
+__global__ void k_set_lane(LaneState* ls, int lane, SetCounts sc) {
+  LaneState& s = ls[lane];
+  if (sc.what == 0) { s.n_sharp = sc.v[0]; s.n_less_sharp = sc.v[1]; s.n_flat = sc.v[2]; s.n_less_flat = sc.v[3]; }
+  else if (sc.what == 1) { s.n_less_sharp = sc.v[0]; s.n_less_flat = sc.v[1]; s.n_kept = sc.v[2]; for (int k = 0; k < 4; ++k) s.q_wodom[k] = sc.pose[k]; for (int k = 0; k < 3; ++k) s.t_wodom[k] = sc.pose[4 + k]; }
+  else if (sc.what == 2) { for (int k = 0; k < 4; ++k) s.q_wmap_wodom[k] = sc.pose[k]; for (int k = 0; k < 3; ++k) s.t_wmap_wodom[k] = sc.pose[4 + k]; }
+  else if (sc.what == 3) { for (int k = 0; k < 4; ++k) s.para_q[k] = sc.pose[k]; for (int k = 0; k < 3; ++k) s.para_t[k] = sc.pose[4 + k]; }
+  else if (sc.what == 4) { for (int k = 0; k < 4; ++k) s.q_w[k] = sc.pose[k]; for (int k = 0; k < 3; ++k) s.t_w[k] = sc.pose[4 + k]; }
+  else if (sc.what == 5) { s.n_map[0] = sc.v[0]; s.n_map[1] = sc.v[1]; }
+}
+__global__ void k_init_lanes(LaneState* ls, int lanes) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= lanes) return;
+  LaneState& s = ls[l];
+  s.para_q[3] = 1.0; s.q_w[3] = 1.0; s.map_x[3] = 1.0; s.q_wmap_wodom[3] = 1.0; s.q_wodom[3] = 1.0;
+  s.cen[0] = 10; s.cen[1] = 10; s.cen[2] = 5;  // laserMapping.cpp:74-76
+}
+__global__ void k_setup_grid_problems(GridProblem* prob, int nprob, const float4* base0, size_t stride0, const float4* base1, size_t stride1,
+                                      LaneState* ls, int which, float cell) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nprob) return;
+  const int lane = p >> 1, t = p & 1;
+  prob[p].pts = (t ? base1 + (size_t)lane * stride1 : base0 + (size_t)lane * stride0);
+  if (which == 0) prob[p].d_n = t ? &ls[lane].n_surf_last : &ls[lane].n_corner_last;
+  else prob[p].d_n = &ls[lane].from_off[t][LVO_MAX_VALID];
+  prob[p].want_cell = cell;
+}
+__global__ void k_setup_one_problem(GridProblem* prob, const float4* pts, const int* d_n, float cell) {
+  prob[0].pts = pts; prob[0].d_n = d_n; prob[0].want_cell = cell;
+}
+__global__ void k_vx_single_setup(VoxelEngine e, int n, float leaf) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *e.d_n = n; *e.d_nsegs = 1; e.seg_leaf[0] = leaf; }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { e.in_seg[i] = 0; e.in_aux[i] = 0; }
+}
+
+int check_view(lvo_ctx* c, const lvo_cloud_view& v, size_t cap) {
+  if (v.n == 0) return LVO_OK;
+  if (!v.data || v.stride < 16 || v.stride > 64 || (v.stride & 3) || (v.off_xyz & 3) || (v.off_intensity & 3) || v.off_xyz + 12 > v.stride ||
+      v.off_intensity + 4 > v.stride) { lvo_set_error(c, "bad cloud view"); return LVO_E_BADARG; }
+  if (v.n > cap) { lvo_set_error(c, "input cloud exceeds context capacity"); return LVO_E_CAPACITY; }
+  return LVO_OK;
+}
+// strided host cloud -> packed float4 on device
+int upload_cloud(lvo_ctx* c, const lvo_cloud_view& v, float4* dst) {
+  if (v.n == 0) return LVO_OK;
+  LVO_CUDA_OK(c, cudaMemcpyAsync(c->d_upload, v.data, v.n * v.stride, cudaMemcpyHostToDevice, c->st));
+  k_unpack<<<std::max(1, std::min(lvo_div_up((long long)v.n, 256), 592)), 256, 0, c->st>>>((const unsigned char*)c->d_upload, (int)v.n, (int)v.stride,
+                                                                                             (int)v.off_xyz, (int)v.off_intensity, dst);
+  c->launches++;
+  return LVO_OK;
+}
+int download_cloud(lvo_ctx* c, const float4* src, size_t n, lvo_cloud_out* out) {
+  if (!out) return LVO_OK;
+  out->n = n;
+  if (n > out->cap || (n && !out->data)) { lvo_set_error(c, "output cloud buffer too small"); return LVO_E_CAPACITY; }
+  if (n) LVO_CUDA_OK(c, cudaMemcpyAsync(out->data, src, n * sizeof(float4), cudaMemcpyDeviceToHost, c->st));
+  return LVO_OK;
+}
+int sync_state(lvo_ctx* c) {
+  LVO_CUDA_OK(c, cudaMemcpyAsync(c->h_ls, c->d_ls, sizeof(LaneState) * c->lanes, cudaMemcpyDeviceToHost, c->st));
+  LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  LVO_CUDA_OK(c, cudaGetLastError());
+  return LVO_OK;
+}
+void pose_out(lvo_pose* p, const double* q, const double* t) {
+  if (!p) return;
+  for (int k = 0; k < 4; ++k) p->q[k] = q[k];
+  for (int k = 0; k < 3; ++k) p->t[k] = t[k];
+}
+int set_inputs(lvo_ctx* c) {
+  LVO_CUDA_OK(c, cudaMemcpyAsync(c->d_in_ptr, c->h_in_ptr, sizeof(void*) * c->lanes, cudaMemcpyHostToDevice, c->st));
+  LVO_CUDA_OK(c, cudaMemcpyAsync(c->d_in_n, c->h_in_n, sizeof(int) * c->lanes, cudaMemcpyHostToDevice, c->st));
+  return LVO_OK;
+}
+void enqueue_extract(lvo_ctx* c, int stride, int off_xyz, int max_n) {
+  ExtractArgs a = c->ex;
+  a.in_stride = stride; a.in_off_xyz = off_xyz;
+  lvo_launch_extract(c->st, a, c->lanes, max_n, &c->launches);
+}
+void enqueue_odometry(lvo_ctx* c) { lvo_launch_odometry(c->st, c->odo, c->solve, c->cfg.outer_iters, c->lanes, &c->launches); }
+void enqueue_mapping(lvo_ctx* c, int from_odo, bool want_registered, bool time_knn) {
+  MapArgs a = c->map;
+  a.from_odo = from_odo;
+  lvo_launch_mapping(c->st, a, c->solve, c->cfg.outer_iters, c->lanes, want_registered, &c->launches, time_knn ? c->knn_ev.data() : nullptr);
+  c->map.gen ^= 1;
+  c->have_knn_events = time_knn;
+}
+void collect_knn_timing(lvo_ctx* c) {
+  c->tim.knn_ms = 0; c->tim.knn_launches = 0; c->tim.knn_bytes = 0;
+  if (!c->have_knn_events) return;
+  for (int o = 0; o < c->cfg.outer_iters; ++o) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->knn_ev[2 * o], c->knn_ev[2 * o + 1]) == cudaSuccess) c->tim.knn_ms += ms;
+    c->tim.knn_launches++;
+  }
+  for (int l = 0; l < c->lanes; ++l) {
+    const LaneState& s = c->h_ls[l];
+    if (s.map_too_small) continue;
+    const double M = (double)s.from_off[0][LVO_MAX_VALID] + (double)s.from_off[1][LVO_MAX_VALID];
+    const double Q = (double)s.n_stack[0] + (double)s.n_stack[1];
+    c->tim.knn_bytes += c->cfg.outer_iters * (16.0 * M + 56.0 * Q);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+void lvo_default_config(lvo_config* cfg) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->n_scans = 64; cfg->minimum_range = 5.0; cfg->line_res = 0.4; cfg->plane_res = 0.8;  // launch/aloam_velodyne_HDL_64.launch:3-13
+  cfg->skip_frame = 1; cfg->outer_iters = 10; cfg->lm_max_iters = 4; cfg->huber = 0.1; cfg->device = 0; cfg->lanes = 1;
+  cfg->max_points = 0; cfg->max_map_corner = 0; cfg->max_map_surf = 0;
+}
+
+int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
+  if (!cfg || !out) return LVO_E_BADARG;
+  *out = nullptr;
+  if (cfg->n_scans != 16 && cfg->n_scans != 32 && cfg->n_scans != 64) return LVO_E_BADARG;  // "wrong scan number", scanRegistration.cpp:203
+  if (cfg->lanes < 1 || cfg->outer_iters < 1 || cfg->outer_iters > LVO_MAX_OUTER || cfg->lm_max_iters < 0 || cfg->lm_max_iters > LVO_MAX_LM) return LVO_E_BADARG;
+  lvo_ctx* c = new (std::nothrow) lvo_ctx();
+  if (!c) return LVO_E_CUDA;
+  *out = c;  // returned even on failure so that lvo_last_error works; caller destroys it
+  c->cfg = *cfg;
+  if (c->cfg.skip_frame < 1) c->cfg.skip_frame = 1;
+  c->lanes = cfg->lanes;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { lvo_set_error(c, "no CUDA device: liblvo has no CPU fallback"); return LVO_E_CUDA; }
+  LVO_CUDA_OK(c, cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  LVO_CUDA_OK(c, cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) { lvo_set_error(c, "liblvo is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor)); return LVO_E_CUDA; }
+  LVO_CUDA_OK(c, cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; ++i) LVO_CUDA_OK(c, cudaEventCreate(&c->ev[i]));
+  c->knn_ev.resize(2 * LVO_MAX_OUTER);
+  for (auto& e : c->knn_ev) LVO_CUDA_OK(c, cudaEventCreate(&e));
+  memset(&c->tim, 0, sizeof(c->tim));
+
+  const int L = c->lanes;
+  const int P = c->P = cfg->max_points > 0 ? cfg->max_points : 262144;
+  c->cap_sharp = cfg->n_scans * LVO_SECTORS * 2;
+  c->cap_lsharp = cfg->n_scans * LVO_SECTORS * 20;
+  c->cap_flat = cfg->n_scans * LVO_SECTORS * 4;
+  const int mapc[2] = {cfg->max_map_corner > 0 ? cfg->max_map_corner : (1 << 20), cfg->max_map_surf > 0 ? cfg->max_map_surf : (1 << 21)};
+  c->lane_status.assign(L, 0);
+
+  LVO_TRY(dalloc(c, &c->d_ls, (size_t)L));
+  LVO_TRY(halloc(c, &c->h_ls, (size_t)L));
+  k_init_lanes<<<lvo_div_up(L, 64), 64, 0, c->st>>>(c->d_ls, L);
+  c->raw_lane_bytes = (size_t)P * 32;
+  LVO_TRY(dalloc(c, &c->d_raw, c->raw_lane_bytes * L, false));
+  LVO_TRY(dalloc(c, &c->d_in_ptr, (size_t)L)); LVO_TRY(halloc(c, &c->h_in_ptr, (size_t)L));
+  LVO_TRY(dalloc(c, &c->d_in_n, (size_t)L)); LVO_TRY(halloc(c, &c->h_in_n, (size_t)L));
+  LVO_TRY(dalloc(c, (unsigned char**)&c->d_upload, (size_t)std::max(P, std::max(mapc[0], mapc[1])) * 64, false));
+
+  // ---- extract
+  ExtractArgs& ex = c->ex;
+  memset(&ex, 0, sizeof(ex));
+  ex.in_ptr = c->d_in_ptr; ex.in_n = c->d_in_n; ex.n_scans = cfg->n_scans; ex.thres = (float)cfg->minimum_range;
+  ex.P = P; ex.nblk_cap = lvo_div_up(P, LVO_EX_THREADS); ex.ls = c->d_ls;
+  LVO_TRY(dalloc(c, &ex.ring, (size_t)L * P)); LVO_TRY(dalloc(c, &ex.ori, (size_t)L * P));
+  LVO_TRY(dalloc(c, &ex.blkcnt, (size_t)L * ex.nblk_cap * LVO_MAX_RINGS));
+  LVO_TRY(dalloc(c, &ex.full, (size_t)L * P)); LVO_TRY(dalloc(c, &ex.curv, (size_t)L * P)); LVO_TRY(dalloc(c, &ex.gapbig, (size_t)L * P));
+  LVO_TRY(dalloc(c, &ex.sort_ind, (size_t)L * P)); LVO_TRY(dalloc(c, &ex.picked, (size_t)L * P)); LVO_TRY(dalloc(c, &ex.label, (size_t)L * P));
+  const size_t nsec = (size_t)L * LVO_MAX_RINGS * LVO_SECTORS;
+  LVO_TRY(dalloc(c, &ex.slot_sharp, nsec * 2)); LVO_TRY(dalloc(c, &ex.slot_lsharp, nsec * 20)); LVO_TRY(dalloc(c, &ex.slot_flat, nsec * 4));
+  LVO_TRY(dalloc(c, &ex.slot_cnt, nsec * 3));
+  LVO_TRY(dalloc(c, &ex.lf_ring, (size_t)L * P)); LVO_TRY(dalloc(c, &ex.lf_cnt, (size_t)L * LVO_MAX_RINGS));
+  LVO_TRY(dalloc(c, &ex.sort_scratch, (size_t)L * 2 * P, false));
+  LVO_TRY(dalloc(c, &ex.sharp, (size_t)L * c->cap_sharp)); LVO_TRY(dalloc(c, &ex.less_sharp, (size_t)L * c->cap_lsharp));
+  LVO_TRY(dalloc(c, &ex.flat, (size_t)L * c->cap_flat)); LVO_TRY(dalloc(c, &ex.less_flat, (size_t)L * P));
+  ex.cap_sharp = c->cap_sharp; ex.cap_lsharp = c->cap_lsharp; ex.cap_flat = c->cap_flat;
+
+  // ---- solver
+  SolveArgs& so = c->solve;
+  memset(&so, 0, sizeof(so));
+  so.ls = c->d_ls; so.max_iters = cfg->lm_max_iters; so.huber = cfg->huber;
+  const size_t trace_n = (size_t)L * LVO_MAX_OUTER * (LVO_MAX_LM + 1) * LVO_TRACE_W;
+  LVO_TRY(dalloc(c, &c->d_trace[0], trace_n)); LVO_TRY(dalloc(c, &c->d_trace[1], trace_n));
+
+  // ---- odometry
+  OdoArgs& od = c->odo;
+  memset(&od, 0, sizeof(od));
+  od.ls = c->d_ls; od.lanes = L;
+  od.sharp = ex.sharp; od.less_sharp = ex.less_sharp; od.flat = ex.flat; od.less_flat = ex.less_flat;
+  od.cap_sharp = c->cap_sharp; od.cap_lsharp = c->cap_lsharp; od.cap_flat = c->cap_flat; od.P = P;
+  LVO_TRY(dalloc(c, &od.corner_last, (size_t)L * c->cap_lsharp)); LVO_TRY(dalloc(c, &od.surf_last, (size_t)L * P));
+  od.factor_cap = std::max(c->cap_sharp + c->cap_flat, c->cap_lsharp + P);
+  LVO_TRY(dalloc(c, &od.factors, (size_t)L * od.factor_cap));
+  LVO_TRY(dalloc(c, &od.corner_corr, (size_t)L * LVO_MAX_OUTER * c->cap_sharp * 2));
+  LVO_TRY(dalloc(c, &od.plane_corr, (size_t)L * LVO_MAX_OUTER * c->cap_flat * 3));
+  LVO_TRY(alloc_grid(c, &od.grid, 2 * L, 1 << 20, (size_t)L * (c->cap_lsharp + P), P));
+  k_setup_grid_problems<<<lvo_div_up(2 * L, 64), 64, 0, c->st>>>(od.grid.prob, 2 * L, od.corner_last, (size_t)c->cap_lsharp, od.surf_last, (size_t)P, c->d_ls, 0, 2.0f);
+
+  // ---- mapping
+  MapArgs& mp = c->map;
+  memset(&mp, 0, sizeof(mp));
+  mp.ls = c->d_ls; mp.lanes = L; mp.leaf[0] = (float)cfg->line_res; mp.leaf[1] = (float)cfg->plane_res;
+  mp.in_pts[0] = ex.less_sharp; mp.in_pts[1] = ex.less_flat; mp.in_cap[0] = c->cap_lsharp; mp.in_cap[1] = P;
+  mp.full = ex.full; mp.P = P; mp.gen = 0;
+  for (int t = 0; t < 2; ++t) {
+    mp.map_cap[t] = mapc[t];
+    for (int g = 0; g < 2; ++g) {
+      LVO_TRY(dalloc(c, &mp.map_pts[g][t], (size_t)L * mapc[t], false));
+      LVO_TRY(dalloc(c, &mp.cube_start[g][t], (size_t)L * (LVO_NCUBES + 1)));
+    }
+    LVO_TRY(dalloc(c, &mp.from_map[t], (size_t)L * mapc[t], false));
+    LVO_TRY(dalloc(c, &mp.stack[t], (size_t)L * mp.in_cap[t]));
+    LVO_TRY(dalloc(c, &mp.knn_ind[t], (size_t)L * LVO_MAX_OUTER * mp.in_cap[t] * 5));
+    LVO_TRY(dalloc(c, &mp.fac_valid[t], (size_t)L * LVO_MAX_OUTER * mp.in_cap[t]));
+  }
+  LVO_TRY(alloc_grid(c, &mp.grid, 2 * L, 1 << 22, (size_t)L * ((size_t)mapc[0] + mapc[1]), std::max(mapc[0], mapc[1])));
+  k_setup_grid_problems<<<lvo_div_up(2 * L, 64), 64, 0, c->st>>>(mp.grid.prob, 2 * L, mp.from_map[0], (size_t)mapc[0], mp.from_map[1], (size_t)mapc[1], c->d_ls, 1, 1.0f);
+  LVO_TRY(dalloc(c, &mp.item_off, (size_t)2 * L + 1));
+  mp.factors = od.factors; mp.factor_cap = od.factor_cap;
+  LVO_TRY(dalloc(c, &mp.app_cnt, (size_t)2 * L * LVO_NCUBES)); LVO_TRY(dalloc(c, &mp.app_first, (size_t)2 * L * LVO_NCUBES));
+  LVO_TRY(dalloc(c, &mp.new_cnt, (size_t)2 * L * (LVO_NCUBES + 1)));
+  LVO_TRY(dalloc(c, &mp.registered, (size_t)L * P, false));
+  // voxel engine shared by the stack downsample and the cube re-filter
+  VoxelEngine& vx = mp.vx;
+  vx.cap_items = (int)std::min<size_t>((size_t)L * ((size_t)mapc[0] + mapc[1] + c->cap_lsharp + P), (size_t)INT_MAX - 4096);
+  vx.cap_segs = 2 * L * LVO_MSEGS;
+  const size_t NI = (size_t)vx.cap_items, NS = (size_t)vx.cap_segs;
+  LVO_TRY(dalloc(c, &vx.in_pts, NI, false)); LVO_TRY(dalloc(c, &vx.in_seg, NI)); LVO_TRY(dalloc(c, &vx.in_aux, NI));
+  LVO_TRY(dalloc(c, &vx.d_n, 1)); LVO_TRY(dalloc(c, &vx.seg_leaf, NS)); LVO_TRY(dalloc(c, &vx.d_nsegs, 1));
+  LVO_TRY(dalloc(c, &vx.seg_mn, 3 * NS)); LVO_TRY(dalloc(c, &vx.seg_mx, 3 * NS)); LVO_TRY(dalloc(c, &vx.seg_minb, 3 * NS));
+  LVO_TRY(dalloc(c, &vx.seg_div, 2 * NS)); LVO_TRY(dalloc(c, &vx.seg_mode, NS)); LVO_TRY(dalloc(c, &vx.d_vbits, 1)); LVO_TRY(dalloc(c, &vx.d_bits, 1));
+  for (int k = 0; k < 2; ++k) { LVO_TRY(dalloc(c, &vx.sort.keys[k], NI, false)); LVO_TRY(dalloc(c, &vx.sort.vals[k], NI, false)); }
+  const size_t tiles = (size_t)lvo_div_up((long long)NI, LVO_SORT_TILE) + 1;
+  LVO_TRY(dalloc(c, &vx.sort.hist, 256 * tiles)); LVO_TRY(dalloc(c, &vx.sort.d_hist_len, 1));
+  LVO_TRY(alloc_scan(c, &vx.sort.scan, 256 * tiles));
+  vx.sort.cap = vx.cap_items;
+  LVO_TRY(dalloc(c, &vx.outpos, NI)); LVO_TRY(dalloc(c, &vx.out_pts, NI, false)); LVO_TRY(dalloc(c, &vx.out_aux, NI));
+  LVO_TRY(dalloc(c, &vx.seg_out_cnt, NS)); LVO_TRY(dalloc(c, &vx.seg_out_start, NS + 1)); LVO_TRY(dalloc(c, &vx.d_n_out, 1));
+  LVO_TRY(alloc_scan(c, &vx.scan, std::max(NI, NS + 1)));
+
+  // stand-alone kNN operator: one problem, storage borrowed from the mapping grid
+  c->gknn = mp.grid; c->gknn.nprob = 1;
+  LVO_TRY(dalloc(c, &c->d_knn_prob, 1)); LVO_TRY(dalloc(c, &c->d_knn_n, 1));
+  c->gknn.prob = c->d_knn_prob;
+  LVO_TRY(dalloc(c, &c->d_knn_ind, (size_t)P * 5)); LVO_TRY(dalloc(c, &c->d_knn_sq, (size_t)P * 5));
+
+  LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  LVO_CUDA_OK(c, cudaGetLastError());
+  return LVO_OK;
+}
+
+int lvo_destroy(lvo_ctx* c) {
+  if (!c) return LVO_E_BADARG;
+  if (c->st) cudaStreamSynchronize(c->st);
+  for (void* p : c->allocs) cudaFree(p);
+  for (void* p : c->pinned) cudaFreeHost(p);
+  if (c->st) { for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]); for (auto& e : c->knn_ev) cudaEventDestroy(e); cudaStreamDestroy(c->st); }
+  delete c;
+  return LVO_OK;
+}
+
+const char* lvo_last_error(const lvo_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int lvo_get_stats(const lvo_ctx* c, int lane, lvo_stats* out, size_t bytes) {
+  if (!c || !out || lane < 0 || lane >= c->lanes) return LVO_E_BADARG;
+  memcpy(out, &c->h_ls[lane].stats, std::min(bytes, sizeof(lvo_stats)));
+  return LVO_OK;
+}
+int lvo_lane_status(const lvo_ctx* c, int lane) { return (c && lane >= 0 && lane < c->lanes) ? c->lane_status[lane] : LVO_E_BADARG; }
+int lvo_get_timings(const lvo_ctx* c, lvo_timings* out) { if (!c || !out) return LVO_E_BADARG; *out = c->tim; out->kernel_launches = (int)c->launches; return LVO_OK; }
+
+// ---------------------------------------------------------------------------------------------------------------
+int lvo_extract_features(lvo_ctx* c, lvo_cloud_view sweep, lvo_cloud_out* full, lvo_cloud_out* sharp, lvo_cloud_out* less_sharp, lvo_cloud_out* flat,
+                         lvo_cloud_out* less_flat) {
+  if (!c) return LVO_E_BADARG;
+  LVO_TRY(check_view(c, sweep, (size_t)c->P));
+  c->launches = 0;
+  cudaEventRecord(c->ev[0], c->st);
+  if (sweep.n) LVO_CUDA_OK(c, cudaMemcpyAsync(c->d_raw, sweep.data, sweep.n * sweep.stride, cudaMemcpyHostToDevice, c->st));
+  for (int l = 0; l < c->lanes; ++l) { c->h_in_ptr[l] = c->d_raw + c->raw_lane_bytes * l; c->h_in_n[l] = l == 0 ? (int)sweep.n : 0; }
+  LVO_TRY(set_inputs(c));
+  enqueue_extract(c, sweep.n ? (int)sweep.stride : 16, sweep.n ? (int)sweep.off_xyz : 0, (int)sweep.n);
+  cudaEventRecord(c->ev[1], c->st);
+  LVO_TRY(sync_state(c));
+  cudaEventElapsedTime(&c->tim.extract_ms, c->ev[0], c->ev[1]);
+  const LaneState& s = c->h_ls[0];
+  int r = LVO_OK, q;
+  if ((q = download_cloud(c, c->ex.full, (size_t)s.n_kept, full)) != LVO_OK) r = q;
+  if ((q = download_cloud(c, c->ex.sharp, (size_t)s.n_sharp, sharp)) != LVO_OK) r = q;
+  if ((q = download_cloud(c, c->ex.less_sharp, (size_t)s.n_less_sharp, less_sharp)) != LVO_OK) r = q;
+  if ((q = download_cloud(c, c->ex.flat, (size_t)s.n_flat, flat)) != LVO_OK) r = q;
+  if ((q = download_cloud(c, c->ex.less_flat, (size_t)s.n_less_flat, less_flat)) != LVO_OK) r = q;
+  LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  c->lane_status[0] = r;
+  return r;
+}
+
+int lvo_scan_to_scan(lvo_ctx* c, lvo_cloud_view sharp, lvo_cloud_view less_sharp, lvo_cloud_view flat, lvo_cloud_view less_flat, lvo_pose* T_last_curr,
+                     lvo_pose* T_w_curr) {
+  if (!c) return LVO_E_BADARG;
+  LVO_TRY(check_view(c, sharp, (size_t)c->cap_sharp)); LVO_TRY(check_view(c, less_sharp, (size_t)c->cap_lsharp));
+  LVO_TRY(check_view(c, flat, (size_t)c->cap_flat)); LVO_TRY(check_view(c, less_flat, (size_t)c->P));
+  c->launches = 0;
+  cudaEventRecord(c->ev[2], c->st);
+  LVO_TRY(upload_cloud(c, sharp, c->ex.sharp)); LVO_TRY(upload_cloud(c, less_sharp, c->ex.less_sharp));
+  LVO_TRY(upload_cloud(c, flat, c->ex.flat)); LVO_TRY(upload_cloud(c, less_flat, c->ex.less_flat));
+  SetCounts sc; memset(&sc, 0, sizeof(sc));
+  sc.what = 0; sc.v[0] = (int)sharp.n; sc.v[1] = (int)less_sharp.n; sc.v[2] = (int)flat.n; sc.v[3] = (int)less_flat.n;
+  k_set_lane<<<1, 1, 0, c->st>>>(c->d_ls, 0, sc);
+  c->odo.corner_corr = c->odo.corner_corr; c->solve.trace = c->d_trace[0];
+  enqueue_odometry(c);
+  cudaEventRecord(c->ev[3], c->st);
+  LVO_TRY(sync_state(c));
+  cudaEventElapsedTime(&c->tim.odometry_ms, c->ev[2], c->ev[3]);
+  const LaneState& s = c->h_ls[0];
+  pose_out(T_last_curr, s.para_q, s.para_t);
+  pose_out(T_w_curr, s.q_w, s.t_w);
+  c->lane_status[0] = s.odo_status;
+  return s.odo_status;
+}
+
+int lvo_scan_to_map(lvo_ctx* c, lvo_cloud_view corner_last, lvo_cloud_view surf_last, lvo_cloud_view full_or_null, const lvo_pose* T_wodom_curr,
+                    lvo_pose* T_wmap_curr, lvo_cloud_out* registered_or_null) {
+  if (!c || !T_wodom_curr) return LVO_E_BADARG;
+  LVO_TRY(check_view(c, corner_last, (size_t)c->cap_lsharp)); LVO_TRY(check_view(c, surf_last, (size_t)c->P));
+  LVO_TRY(check_view(c, full_or_null, (size_t)c->P));
+  c->launches = 0;
+  cudaEventRecord(c->ev[4], c->st);
+  LVO_TRY(upload_cloud(c, corner_last, c->ex.less_sharp)); LVO_TRY(upload_cloud(c, surf_last, c->ex.less_flat));
+  const bool want_reg = registered_or_null && full_or_null.n > 0;
+  if (full_or_null.n) LVO_TRY(upload_cloud(c, full_or_null, c->ex.full));
+  SetCounts sc; memset(&sc, 0, sizeof(sc));
+  sc.what = 1; sc.v[0] = (int)corner_last.n; sc.v[1] = (int)surf_last.n; sc.v[2] = (int)full_or_null.n;
+  for (int k = 0; k < 4; ++k) sc.pose[k] = T_wodom_curr->q[k];
+  for (int k = 0; k < 3; ++k) sc.pose[4 + k] = T_wodom_curr->t[k];
+  k_set_lane<<<1, 1, 0, c->st>>>(c->d_ls, 0, sc);
+  c->solve.trace = c->d_trace[1];
+  enqueue_mapping(c, 0, want_reg, true);
+  cudaEventRecord(c->ev[5], c->st);
+  LVO_TRY(sync_state(c));
+  cudaEventElapsedTime(&c->tim.mapping_ms, c->ev[4], c->ev[5]);
+  collect_knn_timing(c);
+  const LaneState& s = c->h_ls[0];
+  pose_out(T_wmap_curr, s.map_x, s.map_x + 4);
+  int r = s.map_status;
+  if (registered_or_null) {
+    int q = download_cloud(c, c->map.registered, want_reg ? full_or_null.n : 0, registered_or_null);
+    if (q != LVO_OK) r = q;
+    LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  }
+  if (r == LVO_E_CAPACITY) lvo_set_error(c, "map capacity exceeded (max_map_corner / max_map_surf)");
+  c->lane_status[0] = r;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+static int step_common(lvo_ctx* c, int stride, int off_xyz, int max_n, lvo_pose* T_wodom, lvo_pose* T_wmap) {
+  c->launches = 0;
+  LVO_TRY(set_inputs(c));
+  cudaEventRecord(c->ev[0], c->st);
+  enqueue_extract(c, stride, off_xyz, max_n);
+  cudaEventRecord(c->ev[1], c->st);
+  c->solve.trace = c->d_trace[0];
+  enqueue_odometry(c);
+  cudaEventRecord(c->ev[2], c->st);
+  const bool do_map = (c->frame % c->cfg.skip_frame) == 0;  // laserOdometry.cpp:643
+  if (do_map) { c->solve.trace = c->d_trace[1]; enqueue_mapping(c, 1, true, true); }
+  cudaEventRecord(c->ev[3], c->st);
+  c->frame++;
+  LVO_TRY(sync_state(c));
+  cudaEventElapsedTime(&c->tim.extract_ms, c->ev[0], c->ev[1]);
+  cudaEventElapsedTime(&c->tim.odometry_ms, c->ev[1], c->ev[2]);
+  cudaEventElapsedTime(&c->tim.mapping_ms, c->ev[2], c->ev[3]);
+  if (do_map) collect_knn_timing(c);
+  int worst = LVO_OK;
+  for (int l = 0; l < c->lanes; ++l) {
+    const LaneState& s = c->h_ls[l];
+    if (T_wodom) pose_out(&T_wodom[l], s.q_w, s.t_w);
+    if (T_wmap) {
+      if (do_map) pose_out(&T_wmap[l], s.map_x, s.map_x + 4);
+      else {  // high-frequency pose: q_wmap_wodom * odom (laserMapping.cpp:214-215), evaluated on the host
+        const double* a = s.q_wmap_wodom; const double* b = s.q_w;
+        double q[4] = {a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1], a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2],
+                       a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0], a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2]};
+        const double v[3] = {s.t_w[0], s.t_w[1], s.t_w[2]};
+        const double uv[3] = {2 * (a[1] * v[2] - a[2] * v[1]), 2 * (a[2] * v[0] - a[0] * v[2]), 2 * (a[0] * v[1] - a[1] * v[0])};
+        const double t[3] = {v[0] + a[3] * uv[0] + (a[1] * uv[2] - a[2] * uv[1]) + s.t_wmap_wodom[0], v[1] + a[3] * uv[1] + (a[2] * uv[0] - a[0] * uv[2]) + s.t_wmap_wodom[1],
+                             v[2] + a[3] * uv[2] + (a[0] * uv[1] - a[1] * uv[0]) + s.t_wmap_wodom[2]};
+        pose_out(&T_wmap[l], q, t);
+      }
+    }
+    int st = s.odo_status;
+    if (do_map && s.map_status != LVO_OK) st = s.map_status < 0 ? s.map_status : std::max(st, s.map_status);
+    c->lane_status[l] = st;
+    if (st < 0) worst = st; else if (worst >= 0) worst = std::max(worst, st);
+  }
+  if (worst == LVO_E_CAPACITY) lvo_set_error(c, "map capacity exceeded (max_map_corner / max_map_surf)");
+  return worst;
+}
+
+int lvo_step_batch(lvo_ctx* c, const lvo_cloud_view* sweeps, lvo_pose* T_wodom, lvo_pose* T_wmap) {
+  if (!c || !sweeps) return LVO_E_BADARG;
+  int max_n = 0;
+  for (int l = 0; l < c->lanes; ++l) {
+    LVO_TRY(check_view(c, sweeps[l], (size_t)c->P));
+    if (sweeps[l].stride != sweeps[0].stride || sweeps[l].off_xyz != sweeps[0].off_xyz) { lvo_set_error(c, "all lanes must share one point layout"); return LVO_E_BADARG; }
+    if (sweeps[l].stride > 32) { lvo_set_error(c, "stride > 32 unsupported in lvo_step_batch"); return LVO_E_BADARG; }
+    max_n = std::max(max_n, (int)sweeps[l].n);
+  }
+  for (int l = 0; l < c->lanes; ++l) {
+    unsigned char* dst = c->d_raw + c->raw_lane_bytes * l;
+    if (sweeps[l].n) LVO_CUDA_OK(c, cudaMemcpyAsync(dst, sweeps[l].data, sweeps[l].n * sweeps[l].stride, cudaMemcpyHostToDevice, c->st));
+    c->h_in_ptr[l] = dst; c->h_in_n[l] = (int)sweeps[l].n;
+  }
+  return step_common(c, (int)sweeps[0].stride, (int)sweeps[0].off_xyz, max_n, T_wodom, T_wmap);
+}
+
+int lvo_step_batch_dev(lvo_ctx* c, const lvo_point* const* d_sweeps, const size_t* n, lvo_pose* T_wodom, lvo_pose* T_wmap) {
+  if (!c || !d_sweeps || !n) return LVO_E_BADARG;
+  int max_n = 0;
+  for (int l = 0; l < c->lanes; ++l) {
+    if (n[l] > (size_t)c->P) { lvo_set_error(c, "input cloud exceeds context capacity"); return LVO_E_CAPACITY; }
+    c->h_in_ptr[l] = (const unsigned char*)d_sweeps[l]; c->h_in_n[l] = (int)n[l];
+    max_n = std::max(max_n, (int)n[l]);
+  }
+  return step_common(c, 16, 0, max_n, T_wodom, T_wmap);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int lvo_map_import(lvo_ctx* c, int lane, const lvo_point* corner, const int* corner_cube, size_t n_corner, const lvo_point* surf, const int* surf_cube,
+                   size_t n_surf) {
+  if (!c || lane < 0 || lane >= c->lanes) return LVO_E_BADARG;
+  const lvo_point* pts[2] = {corner, surf}; const int* cubes[2] = {corner_cube, surf_cube}; const size_t ns[2] = {n_corner, n_surf};
+  LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  for (int t = 0; t < 2; ++t) {
+    if (ns[t] > (size_t)c->map.map_cap[t]) { lvo_set_error(c, "map import exceeds capacity"); return LVO_E_CAPACITY; }
+    if (ns[t] && (!pts[t] || !cubes[t])) return LVO_E_BADARG;
+    std::vector<unsigned> start(LVO_NCUBES + 1, 0);
+    for (size_t i = 0; i < ns[t]; ++i) { if (cubes[t][i] < 0 || cubes[t][i] >= LVO_NCUBES) return LVO_E_BADARG; start[cubes[t][i] + 1]++; }
+    for (int k = 0; k < LVO_NCUBES; ++k) start[k + 1] += start[k];
+    std::vector<lvo_point> sorted(ns[t]);
+    std::vector<unsigned> cur(start.begin(), start.end() - 1);
+    for (size_t i = 0; i < ns[t]; ++i) sorted[cur[cubes[t][i]]++] = pts[t][i];  // stable inside a cube
+    if (ns[t]) LVO_CUDA_OK(c, cudaMemcpy(c->map.map_pts[c->map.gen][t] + (size_t)lane * c->map.map_cap[t], sorted.data(), ns[t] * sizeof(lvo_point), cudaMemcpyHostToDevice));
+    LVO_CUDA_OK(c, cudaMemcpy(c->map.cube_start[c->map.gen][t] + (size_t)lane * (LVO_NCUBES + 1), start.data(), sizeof(unsigned) * (LVO_NCUBES + 1), cudaMemcpyHostToDevice));
+  }
+  SetCounts sc; memset(&sc, 0, sizeof(sc));
+  sc.what = 5; sc.v[0] = (int)n_corner; sc.v[1] = (int)n_surf;
+  k_set_lane<<<1, 1, 0, c->st>>>(c->d_ls, lane, sc);
+  LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  return LVO_OK;
+}
+
+int lvo_map_export(lvo_ctx* c, int lane, int which, lvo_cloud_out* pts, int* cube_out) {
+  if (!c || lane < 0 || lane >= c->lanes || which < 0 || which > 1 || !pts) return LVO_E_BADARG;
+  LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  std::vector<unsigned> start(LVO_NCUBES + 1);
+  LVO_CUDA_OK(c, cudaMemcpy(start.data(), c->map.cube_start[c->map.gen][which] + (size_t)lane * (LVO_NCUBES + 1), sizeof(unsigned) * (LVO_NCUBES + 1), cudaMemcpyDeviceToHost));
+  const size_t n = start[LVO_NCUBES];
+  pts->n = n;
+  if (n > pts->cap) return LVO_E_CAPACITY;
+  if (n) LVO_CUDA_OK(c, cudaMemcpy(pts->data, c->map.map_pts[c->map.gen][which] + (size_t)lane * c->map.map_cap[which], n * sizeof(lvo_point), cudaMemcpyDeviceToHost));
+  if (cube_out) for (int k = 0; k < LVO_NCUBES; ++k) for (unsigned i = start[k]; i < start[k + 1]; ++i) cube_out[i] = k;
+  return LVO_OK;
+}
+
+static int set_pose(lvo_ctx* c, int lane, int what, const lvo_pose* p) {
+  if (!c || !p || lane < 0 || lane >= c->lanes) return LVO_E_BADARG;
+  SetCounts sc; memset(&sc, 0, sizeof(sc));
+  sc.what = what;
+  for (int k = 0; k < 4; ++k) sc.pose[k] = p->q[k];
+  for (int k = 0; k < 3; ++k) sc.pose[4 + k] = p->t[k];
+  k_set_lane<<<1, 1, 0, c->st>>>(c->d_ls, lane, sc);
+  LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  return LVO_OK;
+}
+int lvo_set_map_correction(lvo_ctx* c, int lane, const lvo_pose* T) { return set_pose(c, lane, 2, T); }
+int lvo_get_map_correction(lvo_ctx* c, int lane, lvo_pose* T) {
+  if (!c || !T || lane < 0 || lane >= c->lanes) return LVO_E_BADARG;
+  LVO_TRY(sync_state(c));
+  pose_out(T, c->h_ls[lane].q_wmap_wodom, c->h_ls[lane].t_wmap_wodom);
+  return LVO_OK;
+}
+int lvo_set_odometry_state(lvo_ctx* c, int lane, const lvo_pose* T_last_curr, const lvo_pose* T_w_curr) {
+  int r = LVO_OK;
+  if (T_last_curr) r = set_pose(c, lane, 3, T_last_curr);
+  if (r == LVO_OK && T_w_curr) r = set_pose(c, lane, 4, T_w_curr);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int lvo_probe_fetch(lvo_ctx* c, int lane, int what, void* out, size_t cap_bytes, size_t* n_bytes) {
+  if (!c || lane < 0 || lane >= c->lanes) return LVO_E_BADARG;
+  LVO_TRY(sync_state(c));
+  const LaneState& s = c->h_ls[lane];
+  const ExtractArgs& ex = c->ex;
+  const int P = c->P, O = c->cfg.outer_iters;
+  const void* src = nullptr; size_t bytes = 0;
+  // 2-D probes (outer x rows) are gathered row block by row block below
+  size_t row_bytes = 0, row_stride = 0; int rows = 1;
+  switch (what) {
+    case LVO_P_FULL: src = ex.full + (size_t)lane * P; bytes = (size_t)s.n_kept * 16; break;
+    case LVO_P_CURVATURE: src = ex.curv + (size_t)lane * P; bytes = (size_t)s.n_kept * 4; break;
+    case LVO_P_SORT_IND: src = ex.sort_ind + (size_t)lane * P; bytes = (size_t)s.n_kept * 4; break;
+    case LVO_P_LABEL: src = ex.label + (size_t)lane * P; bytes = (size_t)s.n_kept * 4; break;
+    case LVO_P_PICKED: src = ex.picked + (size_t)lane * P; bytes = (size_t)s.n_kept * 4; break;
+    case LVO_P_SCAN_START: src = (const char*)(c->d_ls + lane) + offsetof(LaneState, scan_start); bytes = (size_t)c->cfg.n_scans * 4; break;
+    case LVO_P_SCAN_END: src = (const char*)(c->d_ls + lane) + offsetof(LaneState, scan_end); bytes = (size_t)c->cfg.n_scans * 4; break;
+    case LVO_P_SHARP: src = ex.sharp + (size_t)lane * c->cap_sharp; bytes = (size_t)s.n_sharp * 16; break;
+    case LVO_P_LESS_SHARP: src = ex.less_sharp + (size_t)lane * c->cap_lsharp; bytes = (size_t)s.n_less_sharp * 16; break;
+    case LVO_P_FLAT: src = ex.flat + (size_t)lane * c->cap_flat; bytes = (size_t)s.n_flat * 16; break;
+    case LVO_P_LESS_FLAT: src = ex.less_flat + (size_t)lane * P; bytes = (size_t)s.n_less_flat * 16; break;
+    case LVO_P_ODO_CORNER_CORR: src = c->odo.corner_corr + (size_t)lane * LVO_MAX_OUTER * c->cap_sharp * 2; rows = O; row_bytes = (size_t)s.n_sharp * 8; row_stride = (size_t)c->cap_sharp * 8; break;
+    case LVO_P_ODO_PLANE_CORR: src = c->odo.plane_corr + (size_t)lane * LVO_MAX_OUTER * c->cap_flat * 3; rows = O; row_bytes = (size_t)s.n_flat * 12; row_stride = (size_t)c->cap_flat * 12; break;
+    case LVO_P_ODO_LM_TRACE: case LVO_P_MAP_LM_TRACE: {
+      const double* base = c->d_trace[what == LVO_P_ODO_LM_TRACE ? 0 : 1] + (size_t)lane * LVO_MAX_OUTER * (LVO_MAX_LM + 1) * LVO_TRACE_W;
+      src = base; rows = O; row_bytes = (size_t)(c->cfg.lm_max_iters + 1) * LVO_TRACE_W * 8; row_stride = (size_t)(LVO_MAX_LM + 1) * LVO_TRACE_W * 8; break;
+    }
+    case LVO_P_MAP_CORNER_STACK: src = c->map.stack[0] + (size_t)lane * c->map.in_cap[0]; bytes = (size_t)s.n_stack[0] * 16; break;
+    case LVO_P_MAP_SURF_STACK: src = c->map.stack[1] + (size_t)lane * c->map.in_cap[1]; bytes = (size_t)s.n_stack[1] * 16; break;
+    case LVO_P_MAP_CORNER_FROM_MAP: src = c->map.from_map[0] + (size_t)lane * c->map.map_cap[0]; bytes = (size_t)s.from_off[0][LVO_MAX_VALID] * 16; break;
+    case LVO_P_MAP_SURF_FROM_MAP: src = c->map.from_map[1] + (size_t)lane * c->map.map_cap[1]; bytes = (size_t)s.from_off[1][LVO_MAX_VALID] * 16; break;
+    case LVO_P_MAP_CORNER_KNN: case LVO_P_MAP_SURF_KNN: {
+      const int t = what == LVO_P_MAP_CORNER_KNN ? 0 : 1;
+      src = c->map.knn_ind[t] + (size_t)lane * LVO_MAX_OUTER * c->map.in_cap[t] * 5; rows = O; row_bytes = (size_t)s.n_stack[t] * 20; row_stride = (size_t)c->map.in_cap[t] * 20; break;
+    }
+    case LVO_P_MAP_CORNER_VALID: case LVO_P_MAP_SURF_VALID: {
+      const int t = what == LVO_P_MAP_CORNER_VALID ? 0 : 1;
+      src = c->map.fac_valid[t] + (size_t)lane * LVO_MAX_OUTER * c->map.in_cap[t]; rows = O; row_bytes = (size_t)s.n_stack[t] * 4; row_stride = (size_t)c->map.in_cap[t] * 4; break;
+    }
+    case LVO_P_REGISTERED: src = c->map.registered + (size_t)lane * P; bytes = (size_t)s.n_kept * 16; break;
+    default: return LVO_E_BADARG;
+  }
+  if (rows > 1 || row_bytes) bytes = row_bytes * rows;
+  if (n_bytes) *n_bytes = bytes;
+  if (!out) return LVO_OK;  // size query
+  if (cap_bytes < bytes) return LVO_E_CAPACITY;
+  if (bytes == 0) return LVO_OK;
+  if (row_bytes) {
+    LVO_CUDA_OK(c, cudaMemcpy2D(out, row_bytes, src, row_stride, row_bytes, rows, cudaMemcpyDeviceToHost));
+  } else {
+    LVO_CUDA_OK(c, cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
+  }
+  return LVO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int lvo_voxel_downsample(lvo_ctx* c, lvo_cloud_view in, float leaf, lvo_cloud_out* out) {
+  if (!c || !out || !(leaf > 0.f)) return LVO_E_BADARG;
+  LVO_TRY(check_view(c, in, (size_t)c->map.vx.cap_items));
+  if (in.n * in.stride > (size_t)std::max(c->P, std::max(c->map.map_cap[0], c->map.map_cap[1])) * 64) return LVO_E_CAPACITY;
+  c->launches = 0;
+  VoxelEngine& vx = c->map.vx;
+  LVO_TRY(upload_cloud(c, in, vx.in_pts));
+  k_vx_single_setup<<<std::max(1, std::min(lvo_div_up((long long)in.n, 256), 592)), 256, 0, c->st>>>(vx, (int)in.n, leaf);
+  lvo_voxel_run(c->st, vx, (int)std::max<size_t>(in.n, 1), 1, 1, &c->launches);
+  unsigned n_out = 0;
+  LVO_CUDA_OK(c, cudaMemcpyAsync(&n_out, vx.d_n_out, 4, cudaMemcpyDeviceToHost, c->st));
+  LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  LVO_CUDA_OK(c, cudaGetLastError());
+  if (in.n == 0) n_out = 0;
+  int r = download_cloud(c, vx.out_pts, n_out, out);
+  LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  return r;
+}
+
+int lvo_knn(lvo_ctx* c, lvo_cloud_view cloud, lvo_cloud_view queries, int K, float max_sq, int* ind, float* sq) {
+  if (!c || !ind || !sq || (K != 1 && K != 5)) return LVO_E_BADARG;
+  LVO_TRY(check_view(c, cloud, (size_t)c->map.map_cap[1])); LVO_TRY(check_view(c, queries, (size_t)c->P));
+  c->launches = 0;
+  float4* d_cloud = c->map.from_map[1];
+  float4* d_q = c->map.registered;
+  LVO_TRY(upload_cloud(c, cloud, d_cloud)); LVO_TRY(upload_cloud(c, queries, d_q));
+  const int n = (int)cloud.n;
+  LVO_CUDA_OK(c, cudaMemcpyAsync(c->d_knn_n, &n, 4, cudaMemcpyHostToDevice, c->st));
+  // cell size: the smallest power of two >= sqrt(max_sq), at least 1/16 m, so that 27 cells cover the gate
+  float cell = 0.0625f;
+  while (cell * cell < max_sq && cell < 64.f) cell *= 2.f;
+  if (K == 1 && cell > 2.f) cell = 2.f;  // 1-NN with a wide gate: small cells + expanding rings (as the odometry stage)
+  k_setup_one_problem<<<1, 1, 0, c->st>>>(c->d_knn_prob, d_cloud, c->d_knn_n, cell);
+  lvo_grid_build(c->st, c->gknn, &c->launches);
+  const int nq = (int)queries.n;
+  const int blocks = std::max(1, std::min(lvo_div_up((long long)nq, 8), 1184));
+  if (K == 5) k_knn_queries<5><<<blocks, 256, 0, c->st>>>(c->gknn, d_q, nq, max_sq, c->d_knn_ind, c->d_knn_sq);
+  else k_knn_queries<1><<<blocks, 256, 0, c->st>>>(c->gknn, d_q, nq, max_sq, c->d_knn_ind, c->d_knn_sq);
+  c->launches += 2;
+  if (nq) {
+    LVO_CUDA_OK(c, cudaMemcpyAsync(ind, c->d_knn_ind, (size_t)nq * K * 4, cudaMemcpyDeviceToHost, c->st));
+    LVO_CUDA_OK(c, cudaMemcpyAsync(sq, c->d_knn_sq, (size_t)nq * K * 4, cudaMemcpyDeviceToHost, c->st));
+  }
+  LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  LVO_CUDA_OK(c, cudaGetLastError());
+  return LVO_OK;
+}
+
+int lvo_knn5_throughput(lvo_ctx* c, const lvo_point* d_maps, const int* map_counts, const lvo_point* d_queries, const int* query_counts, int S, int reps,
+                        int* d_ind_out, float* d_sq_out, float* ms) {
+  (void)d_maps; (void)map_counts; (void)d_queries; (void)query_counts; (void)S; (void)reps; (void)d_ind_out; (void)d_sq_out; (void)ms;
+  lvo_set_error(c, "lvo_knn5_throughput: not built yet");
+  return LVO_E_STATE;
+}
+
+}  // extern "C"

@@ -1,0 +1,535 @@
+// lvo_extract.cuh — lvo_extract_features: the laserCloudHandler body, reference src/scanRegistration.cpp:127-411,
+// as sm_100a kernels.  One launch sequence serves every lane (blockIdx.y = lane).
+//
+//   k_classify      :136-137 range/NaN filter, :166-200 ring id, :208 azimuth                 (A1, A2)
+//   k_ring_count    :141-153 start/end azimuth, :209-236 halfPassed switch point as a min-index reduction,
+//                   per-block ring histogram for the stable bucket                             (A3, A4)
+//   k_ring_offsets  per-ring exclusive offsets, scanStartInd/scanEndInd :246-252               (A4)
+//   k_ring_scatter  :238-240 relTime/intensity + stable counting sort by ring                  (A3, A4)
+//   k_curvature     :256-266 11-tap curvature, plus the neighbour gap flags of :319-342         (A5)
+//   k_sector_pick   one CTA per ring: :277-399 sector sort + greedy sharp/flat picking, :392-407 less-flat
+//                   gather and the per-ring 0.2 m voxel filter (block bitonic sorts in shared memory) (A6-A10)
+//   k_feature_compact  concatenation of the per-sector / per-ring results in reference order   (A7-A9)
+//
+// Exactness: this TU is compiled with -fmad=false, every float expression is written in the
+// reference's association order, float-vs-double-literal comparisons widen the float first.
+#pragma once
+#include "lvo_internal.h"
+#include "lvo_prims.cuh"
+#include <float.h>
+#include <limits.h>
+
+#define LVO_EX_THREADS 256
+#define LVO_PICK_THREADS 256
+#define LVO_PICK_SMEM_KEYS 4096  // sectors / ring voxel inputs up to this size sort in shared memory
+
+struct ExtractArgs {
+  // input
+  const unsigned char* const* in_ptr;  // [lanes] device pointers to raw point records
+  const int* in_n;                     // [lanes]
+  int in_stride, in_off_xyz;
+  int n_scans;
+  float thres;                         // (float)MINIMUM_RANGE
+  int P;                               // capacity per lane
+  int nblk_cap;                        // ceil(P / LVO_EX_THREADS)
+  LaneState* ls;
+  // per-lane arrays of stride P
+  signed char* ring;       // -2 dropped by range/NaN, -1 rejected by ring test, else ring id
+  float* ori;
+  int* blkcnt;             // [lanes][nblk_cap][64]
+  float4* full;
+  float* curv;
+  unsigned char* gapbig;
+  int* sort_ind; int* picked; int* label;
+  // sector results: [lanes][64][6][...]
+  int* slot_sharp;   // 2 per sector
+  int* slot_lsharp;  // 20 per sector
+  int* slot_flat;    // 4 per sector
+  int* slot_cnt;     // 3 per sector: n_sharp, n_less_sharp, n_flat
+  float4* lf_ring;   // per-ring voxel-filtered less-flat, stored at ring_start[ring]
+  int* lf_cnt;       // [lanes][64]
+  unsigned long long* sort_scratch;  // [lanes][2P] global fallback for oversize sorts
+  // outputs (stride P except sharp/flat which have their own caps)
+  float4* sharp; float4* less_sharp; float4* flat; float4* less_flat;
+  int cap_sharp, cap_lsharp, cap_flat;
+};
+
+// ring id, literal C++ conversions of scanRegistration.cpp:166-200 (see oracle/scan_registration.hpp ring_of)
+__device__ __forceinline__ int ring_of_dev(float x, float y, float z, int N_SCANS) {
+  float angle = (float)((double)(lvo_atanf(z / sqrtf(x * x + y * y)) * 180) / LVO_PI);
+  int scanID;
+  if (N_SCANS == 16) {
+    scanID = int((angle + 15) / 2 + 0.5);
+    if (scanID > (N_SCANS - 1) || scanID < 0) return -1;
+  } else if (N_SCANS == 32) {
+    scanID = int((angle + 92.0 / 3.0) * 3.0 / 4.0);
+    if (scanID > (N_SCANS - 1) || scanID < 0) return -1;
+  } else {
+    if (angle >= -8.83) scanID = int((2 - angle) * 3.0 + 0.5);
+    else scanID = N_SCANS / 2 + int((-8.83 - angle) * 2.0 + 0.5);
+    if (angle > 2 || angle < -24.33 || scanID > 50 || scanID < 0) return -1;
+  }
+  return scanID;
+}
+
+__device__ __forceinline__ float3 load_xyz(const unsigned char* base, int stride, int off, int i) {
+  const float* p = reinterpret_cast<const float*>(base + (size_t)i * stride + off);
+  return make_float3(p[0], p[1], p[2]);
+}
+
+__global__ void k_extract_reset(ExtractArgs a) {
+  LaneState& s = a.ls[blockIdx.x];
+  if (threadIdx.x == 0) {
+    s.n_in = a.in_n[blockIdx.x];
+    s.first_kept = INT_MAX; s.last_kept = -1; s.switch_idx = INT_MAX; s.n_kept = 0;
+    s.n_sharp = s.n_less_sharp = s.n_flat = s.n_less_flat = 0;
+  }
+}
+
+__global__ void __launch_bounds__(LVO_EX_THREADS) k_classify(ExtractArgs a) {
+  const int lane = blockIdx.y;
+  const int n = a.in_n[lane];
+  const int i = blockIdx.x * LVO_EX_THREADS + threadIdx.x;
+  bool kept = false;
+  if (i < n) {
+    float3 p = load_xyz(a.in_ptr[lane], a.in_stride, a.in_off_xyz, i);
+    kept = isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && !(p.x * p.x + p.y * p.y + p.z * p.z < a.thres * a.thres);
+    int ring = -2;
+    float ori = 0.f;
+    if (kept) {
+      ring = ring_of_dev(p.x, p.y, p.z, a.n_scans);
+      ori = -lvo_atan2f(p.y, p.x);
+    }
+    a.ring[(size_t)lane * a.P + i] = (signed char)ring;
+    a.ori[(size_t)lane * a.P + i] = ori;
+  }
+  // first / last kept index
+  int mn = kept ? i : INT_MAX, mx = kept ? i : -1;
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if ((threadIdx.x & 31) == 0) {
+    if (mn != INT_MAX) atomicMin(&a.ls[lane].first_kept, mn);
+    if (mx >= 0) atomicMax(&a.ls[lane].last_kept, mx);
+  }
+}
+
+// start / end azimuth of the sweep, scanRegistration.cpp:141-153
+__device__ __forceinline__ void sweep_ori(const ExtractArgs& a, int lane, float* startOri, float* endOri) {
+  const LaneState& s = a.ls[lane];
+  float so = 0.f, eo = 0.f;
+  if (s.last_kept >= 0) {
+    so = a.ori[(size_t)lane * a.P + s.first_kept];
+    eo = (float)((double)a.ori[(size_t)lane * a.P + s.last_kept] + 2 * LVO_PI);
+    if (eo - so > 3 * LVO_PI) eo = (float)((double)eo - 2 * LVO_PI);
+    else if (eo - so < LVO_PI) eo = (float)((double)eo + 2 * LVO_PI);
+  }
+  *startOri = so; *endOri = eo;
+}
+
+__global__ void __launch_bounds__(LVO_EX_THREADS) k_ring_count(ExtractArgs a) {
+  __shared__ int h[LVO_MAX_RINGS];
+  __shared__ float s_ori[2];
+  const int lane = blockIdx.y;
+  const int n = a.in_n[lane];
+  if (blockIdx.x * LVO_EX_THREADS >= n) return;
+  if (threadIdx.x < LVO_MAX_RINGS) h[threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    sweep_ori(a, lane, &s_ori[0], &s_ori[1]);
+    if (blockIdx.x == 0) { a.ls[lane].start_ori = s_ori[0]; a.ls[lane].end_ori = s_ori[1]; }
+  }
+  __syncthreads();
+  const float startOri = s_ori[0];
+  const int i = blockIdx.x * LVO_EX_THREADS + threadIdx.x;
+  int sw = INT_MAX;
+  if (i < n) {
+    int ring = a.ring[(size_t)lane * a.P + i];
+    if (ring >= 0) {
+      atomicAdd(&h[ring], 1);
+      float ori = a.ori[(size_t)lane * a.P + i];
+      // the unwrapping every point gets while !halfPassed (:211-218); the first point for which the test of :220
+      // fires is where the sequential flag flips
+      if (ori < startOri - LVO_PI / 2) ori = (float)((double)ori + 2 * LVO_PI);
+      else if (ori > startOri + LVO_PI * 3 / 2) ori = (float)((double)ori - 2 * LVO_PI);
+      if (ori - startOri > LVO_PI) sw = i;
+    }
+  }
+  sw = __reduce_min_sync(0xffffffffu, sw);
+  if ((threadIdx.x & 31) == 0 && sw != INT_MAX) atomicMin(&a.ls[lane].switch_idx, sw);
+  __syncthreads();
+  if (threadIdx.x < LVO_MAX_RINGS) a.blkcnt[((size_t)lane * a.nblk_cap + blockIdx.x) * LVO_MAX_RINGS + threadIdx.x] = h[threadIdx.x];
+}
+
+__global__ void k_ring_offsets(ExtractArgs a) {
+  const int lane = blockIdx.x;
+  LaneState& s = a.ls[lane];
+  const int n = a.in_n[lane];
+  const int nblk = (n + LVO_EX_THREADS - 1) / LVO_EX_THREADS;
+  const int r = threadIdx.x;  // 64 threads
+  int run = 0;
+  int* col = a.blkcnt + (size_t)lane * a.nblk_cap * LVO_MAX_RINGS + r;
+  for (int b = 0; b < nblk; ++b) {
+    int c = col[(size_t)b * LVO_MAX_RINGS];
+    col[(size_t)b * LVO_MAX_RINGS] = run;
+    run += c;
+  }
+  s.ring_count[r] = run;
+  __syncthreads();
+  if (r == 0) {
+    int acc = 0;
+    for (int k = 0; k < LVO_MAX_RINGS; ++k) {
+      s.ring_start[k] = acc;
+      if (k < a.n_scans) s.scan_start[k] = acc + 5;   // :249
+      acc += s.ring_count[k];
+      if (k < a.n_scans) s.scan_end[k] = acc - 6;     // :251
+    }
+    s.ring_start[LVO_MAX_RINGS] = acc;
+    s.n_kept = acc;
+    s.stats.n_in = n;
+    s.stats.n_kept = acc;
+  }
+}
+
+__global__ void __launch_bounds__(LVO_EX_THREADS) k_ring_scatter(ExtractArgs a) {
+  __shared__ int wcnt[LVO_EX_THREADS / 32][LVO_MAX_RINGS];
+  const int lane = blockIdx.y;
+  const int n = a.in_n[lane];
+  if (blockIdx.x * LVO_EX_THREADS >= n) return;
+  const LaneState& s = a.ls[lane];
+  for (int k = threadIdx.x; k < (LVO_EX_THREADS / 32) * LVO_MAX_RINGS; k += LVO_EX_THREADS) (&wcnt[0][0])[k] = 0;
+  __syncthreads();
+  const int i = blockIdx.x * LVO_EX_THREADS + threadIdx.x;
+  const unsigned ln = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int ring = -1;
+  if (i < n) ring = a.ring[(size_t)lane * a.P + i];
+  const unsigned m = __match_any_sync(0xffffffffu, ring);
+  const int rank = __popc(m & ((1u << ln) - 1u));
+  if (ring >= 0 && rank == 0) wcnt[w][ring] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x < LVO_MAX_RINGS) {
+    int run = 0;
+    for (int ww = 0; ww < LVO_EX_THREADS / 32; ++ww) { int t = wcnt[ww][threadIdx.x]; wcnt[ww][threadIdx.x] = run; run += t; }
+  }
+  __syncthreads();
+  if (ring >= 0) {
+    const float startOri = s.start_ori, endOri = s.end_ori;
+    float ori = a.ori[(size_t)lane * a.P + i];
+    if (i <= s.switch_idx) {   // processed while !halfPassed (:209-224)
+      if (ori < startOri - LVO_PI / 2) ori = (float)((double)ori + 2 * LVO_PI);
+      else if (ori > startOri + LVO_PI * 3 / 2) ori = (float)((double)ori - 2 * LVO_PI);
+    } else {                   // :225-236
+      ori = (float)((double)ori + 2 * LVO_PI);
+      if (ori < endOri - LVO_PI * 3 / 2) ori = (float)((double)ori + 2 * LVO_PI);
+      else if (ori > endOri + LVO_PI / 2) ori = (float)((double)ori - 2 * LVO_PI);
+    }
+    float relTime = (ori - startOri) / (endOri - startOri);  // :238
+    float3 p = load_xyz(a.in_ptr[lane], a.in_stride, a.in_off_xyz, i);
+    const int dst = s.ring_start[ring] + a.blkcnt[((size_t)lane * a.nblk_cap + blockIdx.x) * LVO_MAX_RINGS + ring] + wcnt[w][ring] + rank;
+    a.full[(size_t)lane * a.P + dst] = make_float4(p.x, p.y, p.z, (float)(ring + 0.1 * relTime));  // :239 scanPeriod = 0.1
+  }
+}
+
+__global__ void __launch_bounds__(LVO_EX_THREADS) k_curvature(ExtractArgs a) {
+  const int lane = blockIdx.y;
+  const int n = a.ls[lane].n_kept;
+  const int i = blockIdx.x * LVO_EX_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const float4* P = a.full + (size_t)lane * a.P;
+  float c = 0.f;
+  const float4 p0 = P[i];
+  if (i >= 5 && i < n - 5) {  // :256-266, strictly left to right
+    float4 m5 = P[i - 5], m4 = P[i - 4], m3 = P[i - 3], m2 = P[i - 2], m1 = P[i - 1];
+    float4 p1 = P[i + 1], p2 = P[i + 2], p3 = P[i + 3], p4 = P[i + 4], p5 = P[i + 5];
+    float diffX = m5.x + m4.x + m3.x + m2.x + m1.x - 10 * p0.x + p1.x + p2.x + p3.x + p4.x + p5.x;
+    float diffY = m5.y + m4.y + m3.y + m2.y + m1.y - 10 * p0.y + p1.y + p2.y + p3.y + p4.y + p5.y;
+    float diffZ = m5.z + m4.z + m3.z + m2.z + m1.z - 10 * p0.z + p1.z + p2.z + p3.z + p4.z + p5.z;
+    c = diffX * diffX + diffY * diffY + diffZ * diffZ;
+  }
+  unsigned char g = 0;
+  if (i + 1 < n) {  // gap test of :321-324 between points i and i+1 (the squared distance is symmetric)
+    float4 q = P[i + 1];
+    float dx = q.x - p0.x, dy = q.y - p0.y, dz = q.z - p0.z;
+    g = (dx * dx + dy * dy + dz * dz > 0.05) ? 1 : 0;
+  }
+  const size_t o = (size_t)lane * a.P + i;
+  a.curv[o] = c; a.gapbig[o] = g;
+  a.sort_ind[o] = (i >= 5 && i < n - 5) ? i : 0;
+  a.picked[o] = 0; a.label[o] = 0;
+}
+
+// ascending bitonic sort of keys[0..npad), npad a power of two; whole block participates
+__device__ __forceinline__ void block_bitonic_sort(unsigned long long* keys, int npad) {
+  for (int k = 2; k <= npad; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long x = keys[i], y = keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { keys[i] = y; keys[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+}
+__device__ __forceinline__ int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// Marks the neighbours of a picked point (:319-342 / :365-388).  Called by a full warp.
+__device__ __forceinline__ void mark_neighbours(volatile int* picked, const unsigned char* gapbig, int ind, unsigned ln) {
+  // lanes 0..4: l = 1..5 forward, gap between ind+l-1 and ind+l ; lanes 8..12: l = -1..-5, gap between ind+l and ind+l+1
+  bool brk = false;
+  int tgt = -1;
+  if (ln < 5) { int l = (int)ln + 1; brk = gapbig[ind + l - 1] != 0; tgt = ind + l; }
+  else if (ln >= 8 && ln < 13) { int l = -((int)ln - 8) - 1; brk = gapbig[ind + l] != 0; tgt = ind + l; }
+  const unsigned b = __ballot_sync(0xffffffffu, brk);
+  const unsigned bf = b & 0x1fu, bb = (b >> 8) & 0x1fu;
+  const int stopf = bf ? (__ffs(bf) - 1) : 5, stopb = bb ? (__ffs(bb) - 1) : 5;
+  if (ln < 5 && (int)ln < stopf) picked[tgt] = 1;
+  if (ln >= 8 && ln < 13 && (int)(ln - 8) < stopb) picked[tgt] = 1;
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(LVO_PICK_THREADS) k_sector_pick(ExtractArgs a) {
+  extern __shared__ unsigned long long skeys[];  // LVO_PICK_SMEM_KEYS
+  __shared__ float s_red[6][LVO_PICK_THREADS / 32];
+  __shared__ int s_i[8];
+  __shared__ unsigned s_scan[33];
+  const int lane = blockIdx.y, ring = blockIdx.x;
+  LaneState& s = a.ls[lane];
+  const size_t lo = (size_t)lane * a.P;
+  const float4* P = a.full + lo;
+  const float* curv = a.curv + lo;
+  const unsigned char* gapbig = a.gapbig + lo;
+  int* sort_ind = a.sort_ind + lo;
+  volatile int* picked = a.picked + lo;
+  int* label = a.label + lo;
+  const unsigned ln = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int sbase = (lane * LVO_MAX_RINGS + ring) * LVO_SECTORS;
+  const int S = s.scan_start[ring], E = s.scan_end[ring];
+  if (threadIdx.x == 0) a.lf_cnt[lane * LVO_MAX_RINGS + ring] = 0;
+  if (threadIdx.x < LVO_SECTORS * 3) a.slot_cnt[sbase * 3 + threadIdx.x] = 0;
+  if (E - S < 6) return;  // :279-280
+
+  for (int j = 0; j < LVO_SECTORS; ++j) {
+    const int sp = S + (E - S) * j / 6;            // :284
+    const int ep = S + (E - S) * (j + 1) / 6 - 1;  // :285
+    const int m = ep - sp + 1;
+    // ---- :288 sort cloudSortInd[sp..ep] by (curvature, index) ascending
+    const int npad = next_pow2(m);
+    unsigned long long* keys = (npad <= LVO_PICK_SMEM_KEYS) ? skeys : (a.sort_scratch + (size_t)lane * 2 * a.P + 2 * (size_t)sp);
+    for (int t = threadIdx.x; t < npad; t += blockDim.x) {
+      unsigned long long k = ~0ull;
+      if (t < m) k = ((unsigned long long)__float_as_uint(curv[sp + t]) << 32) | (unsigned)(sp + t);  // curvature >= 0: bit order == value order
+      keys[t] = k;
+    }
+    __syncthreads();
+    block_bitonic_sort(keys, npad);
+    for (int t = threadIdx.x; t < m; t += blockDim.x) sort_ind[sp + t] = (int)(unsigned)(keys[t] & 0xffffffffull);
+    __syncthreads();
+    // ---- greedy picks, warp 0 (sequential semantics, 32 candidates examined per step)
+    if (w == 0) {
+      int nsharp = 0, nls = 0, largest = 0;
+      int pos = ep;
+      while (pos >= sp) {  // :292-344, k = ep .. sp
+        const int k = pos - (int)ln;
+        const bool valid = k >= sp;
+        const int ind = valid ? sort_ind[k] : 0;
+        const float c = valid ? curv[ind] : 0.f;
+        const bool big = valid && ((double)c > 0.1);
+        const bool ok = big && picked[ind] == 0;
+        const unsigned bo = __ballot_sync(0xffffffffu, ok);
+        if (bo == 0) {
+          if (__ballot_sync(0xffffffffu, valid && !big)) break;  // sorted: nothing further can exceed 0.1
+          pos -= 32;
+          continue;
+        }
+        const int first = __ffs(bo) - 1;
+        const int sel = __shfl_sync(0xffffffffu, ind, first);
+        largest++;
+        if (largest <= 2) {
+          if (ln == 0) { label[sel] = 2; a.slot_sharp[sbase * 2 + j * 2 + nsharp] = sel; a.slot_lsharp[sbase * 20 + j * 20 + nls] = sel; }
+          nsharp++; nls++;
+        } else if (largest <= 20) {
+          if (ln == 0) { label[sel] = 1; a.slot_lsharp[sbase * 20 + j * 20 + nls] = sel; }
+          nls++;
+        } else {
+          break;
+        }
+        if (ln == 0) picked[sel] = 1;
+        __syncwarp();
+        mark_neighbours(picked, gapbig, sel, ln);
+        pos = pos - first - 1;
+      }
+      int nflat = 0;
+      pos = sp;
+      while (pos <= ep) {  // :347-390, k = sp .. ep
+        const int k = pos + (int)ln;
+        const bool valid = k <= ep;
+        const int ind = valid ? sort_ind[k] : 0;
+        const float c = valid ? curv[ind] : 0.f;
+        const bool small = valid && ((double)c < 0.1);
+        const bool ok = small && picked[ind] == 0;
+        const unsigned bo = __ballot_sync(0xffffffffu, ok);
+        if (bo == 0) {
+          if (__ballot_sync(0xffffffffu, valid && !small)) break;
+          pos += 32;
+          continue;
+        }
+        const int first = __ffs(bo) - 1;
+        const int sel = __shfl_sync(0xffffffffu, ind, first);
+        if (ln == 0) { label[sel] = -1; a.slot_flat[sbase * 4 + j * 4 + nflat] = sel; }
+        nflat++;
+        if (nflat >= 4) break;  // :359-362 before the marking
+        if (ln == 0) picked[sel] = 1;
+        __syncwarp();
+        mark_neighbours(picked, gapbig, sel, ln);
+        pos = pos + first + 1;
+      }
+      if (ln == 0) { a.slot_cnt[(sbase + j) * 3 + 0] = nsharp; a.slot_cnt[(sbase + j) * 3 + 1] = nls; a.slot_cnt[(sbase + j) * 3 + 2] = nflat; }
+    }
+    __syncthreads();
+  }
+  __threadfence_block();
+  __syncthreads();
+
+  // ---- :392-398 less-flat candidates k in [S, E-1] with label <= 0, in index order; then :401-407 VoxelGrid(0.2)
+  // pass 1: bounding box of the candidates
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  int cnt = 0;
+  for (int k = S + threadIdx.x; k <= E - 1; k += blockDim.x) {
+    if (label[k] <= 0) {
+      float4 p = P[k];
+      mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+      mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+      cnt++;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    for (int o = 16; o > 0; o >>= 1) { mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o)); mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o)); }
+    if (ln == 0) { s_red[c][w] = mn[c]; s_red[3 + c][w] = mx[c]; }
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0) s_i[0] = 0;
+  __syncthreads();
+  if (ln == 0) atomicAdd(&s_i[0], cnt);
+  __syncthreads();
+  const int ncand = s_i[0];
+  if (ncand == 0) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float a0 = s_red[c][0], b0 = s_red[3 + c][0];
+    for (int ww = 1; ww < LVO_PICK_THREADS / 32; ++ww) { a0 = fminf(a0, s_red[c][ww]); b0 = fmaxf(b0, s_red[3 + c][ww]); }
+    mn[c] = a0; mx[c] = b0;
+  }
+  const float inv = 1.0f / 0.2f;  // inverse_leaf_size_ for setLeafSize(0.2, 0.2, 0.2)
+  const long long ddx = (long long)((mx[0] - mn[0]) * inv) + 1, ddy = (long long)((mx[1] - mn[1]) * inv) + 1, ddz = (long long)((mx[2] - mn[2]) * inv) + 1;
+  const bool passthrough = (ddx * ddy * ddz) > (long long)INT_MAX;
+  const int min_b0 = (int)floorf(mn[0] * inv), min_b1 = (int)floorf(mn[1] * inv), min_b2 = (int)floorf(mn[2] * inv);
+  const int max_b0 = (int)floorf(mx[0] * inv), max_b1 = (int)floorf(mx[1] * inv);
+  const int div0 = max_b0 - min_b0 + 1, div1 = max_b1 - min_b1 + 1;
+  // pass 2: keys (voxel idx, candidate rank) — the rank makes the sort stable and addresses the point
+  const int npad = next_pow2(ncand);
+  unsigned long long* keys = (npad <= LVO_PICK_SMEM_KEYS) ? skeys : (a.sort_scratch + (size_t)lane * 2 * a.P + 2 * (size_t)S);
+  // stable compaction of the candidates: block scan over chunks of the ring
+  int carry = 0;
+  for (int base = S; base <= E - 1; base += blockDim.x) {
+    const int k = base + threadIdx.x;
+    const bool c = (k <= E - 1) && label[k] <= 0;
+    unsigned tot;
+    const unsigned ex = block_excl_scan(c ? 1u : 0u, s_scan, &tot);
+    if (c) {
+      float4 p = P[k];
+      unsigned idx;
+      if (passthrough) idx = (unsigned)(carry + ex);
+      else {
+        int ijk0 = (int)(floorf(p.x * inv) - (float)min_b0);
+        int ijk1 = (int)(floorf(p.y * inv) - (float)min_b1);
+        int ijk2 = (int)(floorf(p.z * inv) - (float)min_b2);
+        idx = (unsigned)(ijk0 + ijk1 * div0 + ijk2 * div0 * div1);
+      }
+      // low word: offset of the point inside the ring (k - S) — ascending with the candidate rank
+      keys[carry + ex] = ((unsigned long long)idx << 32) | (unsigned)(k - S);
+    }
+    carry += (int)tot;
+  }
+  for (int t = ncand + threadIdx.x; t < npad; t += blockDim.x) keys[t] = ~0ull;
+  __syncthreads();
+  block_bitonic_sort(keys, npad);
+  // pass 3: one centroid per run of equal voxel idx, accumulated in sorted order (float, as PCL's CentroidPoint)
+  float4* out = a.lf_ring + lo + s.ring_start[ring];
+  carry = 0;
+  for (int base = 0; base < ncand; base += blockDim.x) {
+    const int t = base + threadIdx.x;
+    bool head = false;
+    if (t < ncand) head = (t == 0) || ((keys[t] >> 32) != (keys[t - 1] >> 32));
+    unsigned tot;
+    const unsigned ex = block_excl_scan(head ? 1u : 0u, s_scan, &tot);
+    if (head) {
+      const unsigned long long v = keys[t] >> 32;
+      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+      int u = t;
+      for (; u < ncand && (keys[u] >> 32) == v; ++u) {
+        const float4 p = P[S + (int)(unsigned)(keys[u] & 0xffffffffull)];
+        sx += p.x; sy += p.y; sz += p.z; si += p.w;
+      }
+      const float c = (float)(u - t);
+      out[carry + ex] = make_float4(sx / c, sy / c, sz / c, si / c);
+    }
+    carry += (int)tot;
+  }
+  if (threadIdx.x == 0) a.lf_cnt[lane * LVO_MAX_RINGS + ring] = carry;
+}
+
+// Concatenate per-sector picks and per-ring less-flat clouds in reference order.  One block per lane.
+__global__ void __launch_bounds__(256) k_feature_compact(ExtractArgs a) {
+  __shared__ int off[4][LVO_MAX_RINGS * LVO_SECTORS + 1];
+  __shared__ int lfo[LVO_MAX_RINGS + 1];
+  const int lane = blockIdx.x;
+  LaneState& s = a.ls[lane];
+  const int nsec = a.n_scans * LVO_SECTORS;
+  if (threadIdx.x == 0) {
+    int a0 = 0, a1 = 0, a2 = 0;
+    for (int k = 0; k < nsec; ++k) {
+      const int r = k / LVO_SECTORS, j = k % LVO_SECTORS;
+      const int* c = a.slot_cnt + ((size_t)(lane * LVO_MAX_RINGS + r) * LVO_SECTORS + j) * 3;
+      off[0][k] = a0; off[1][k] = a1; off[2][k] = a2;
+      a0 += c[0]; a1 += c[1]; a2 += c[2];
+    }
+    off[0][nsec] = a0; off[1][nsec] = a1; off[2][nsec] = a2;
+    int acc = 0;
+    for (int r = 0; r < a.n_scans; ++r) { lfo[r] = acc; s.lf_ring_off[r] = acc; acc += a.lf_cnt[lane * LVO_MAX_RINGS + r]; }
+    lfo[a.n_scans] = acc; s.lf_ring_off[a.n_scans] = acc;
+    s.n_sharp = a0; s.n_less_sharp = a1; s.n_flat = a2; s.n_less_flat = acc;
+    s.stats.n_sharp = a0; s.stats.n_less_sharp = a1; s.stats.n_flat = a2; s.stats.n_less_flat = acc;
+  }
+  __syncthreads();
+  const float4* P = a.full + (size_t)lane * a.P;
+  for (int k = threadIdx.x; k < nsec; k += blockDim.x) {
+    const int r = k / LVO_SECTORS, j = k % LVO_SECTORS;
+    const size_t sb = (size_t)(lane * LVO_MAX_RINGS + r) * LVO_SECTORS;
+    const int* c = a.slot_cnt + (sb + j) * 3;
+    for (int t = 0; t < c[0]; ++t) a.sharp[(size_t)lane * a.cap_sharp + off[0][k] + t] = P[a.slot_sharp[sb * 2 + j * 2 + t]];
+    for (int t = 0; t < c[1]; ++t) a.less_sharp[(size_t)lane * a.cap_lsharp + off[1][k] + t] = P[a.slot_lsharp[sb * 20 + j * 20 + t]];
+    for (int t = 0; t < c[2]; ++t) a.flat[(size_t)lane * a.cap_flat + off[2][k] + t] = P[a.slot_flat[sb * 4 + j * 4 + t]];
+  }
+  for (int r = 0; r < a.n_scans; ++r) {
+    const int c = lfo[r + 1] - lfo[r];
+    const float4* src = a.lf_ring + (size_t)lane * a.P + s.ring_start[r];
+    for (int t = threadIdx.x; t < c; t += blockDim.x) a.less_flat[(size_t)lane * a.P + lfo[r] + t] = src[t];
+  }
+}
+
+static inline void lvo_launch_extract(cudaStream_t st, const ExtractArgs& a, int lanes, int max_n_in, long long* launches) {
+  if (max_n_in < 1) max_n_in = 1;
+  dim3 gpts(lvo_div_up(max_n_in, LVO_EX_THREADS), lanes);
+  k_extract_reset<<<lanes, 32, 0, st>>>(a);
+  k_classify<<<gpts, LVO_EX_THREADS, 0, st>>>(a);
+  k_ring_count<<<gpts, LVO_EX_THREADS, 0, st>>>(a);
+  k_ring_offsets<<<lanes, LVO_MAX_RINGS, 0, st>>>(a);
+  k_ring_scatter<<<gpts, LVO_EX_THREADS, 0, st>>>(a);
+  k_curvature<<<gpts, LVO_EX_THREADS, 0, st>>>(a);
+  k_sector_pick<<<dim3(a.n_scans, lanes), LVO_PICK_THREADS, LVO_PICK_SMEM_KEYS * sizeof(unsigned long long), st>>>(a);
+  k_feature_compact<<<lanes, 256, 0, st>>>(a);
+  if (launches) *launches += 8;
+}

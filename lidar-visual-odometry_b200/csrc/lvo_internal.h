@@ -1,0 +1,133 @@
+// lvo_internal.h — context layout and helpers shared by the .cu translation units of liblvo.so.
+//
+// Data layout in HBM: every per-lane array lives at `base + lane * cap` inside one arena owned by
+// the context; clouds are AoS float4 (x, y, z, intensity) so that one 128-bit load fetches a point.  All counts
+// that depend on the data (n_kept, feature counts, map sizes, ...) stay on the device in `LaneState`; kernels are
+// launched with capacity-derived grids and grid-stride over the device-side counts, so a whole frame is enqueued
+// without a host round trip.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/lvo.h"
+#include "lvo_math.h"
+
+#define LVO_MAX_RINGS 64
+#define LVO_SECTORS 6
+#define LVO_MAX_OUTER 16
+#define LVO_MAX_LM 8
+#define LVO_TRACE_W 10
+#define LVO_CUBE_W 21
+#define LVO_CUBE_H 21
+#define LVO_CUBE_D 11
+#define LVO_NCUBES (LVO_CUBE_W * LVO_CUBE_H * LVO_CUBE_D)  // 4851, laserMapping.cpp:82
+#define LVO_MAX_VALID 75                                     // 5 x 5 x 3, laserMapping.cpp:512-516
+#define LVO_VSEGS (LVO_MAX_VALID + 1)                        // + one pseudo segment for inserts into non-valid cubes
+
+// One residual block, the parameters of the reference functors (lidarFactor.hpp):
+//   type 0 LidarEdgeFactor      : c = curr_point, a = last_point_a, b = last_point_b
+//   type 1 LidarPlaneFactor     : c = curr_point, a = last_point_j, b = ljm_norm (unit normal, built at construction)
+//   type 2 LidarPlaneNormFactor : c = curr_point, a = plane_unit_norm, d = negative_OA_dot_norm
+//   type -1 : no factor for this feature
+struct __align__(16) LvoFactor {
+  double c[3], a[3], b[3], d;
+  int type, pad;
+};
+
+// Scalars of one lane that live on the device.
+struct LaneState {
+  // ---- extract
+  int n_in, first_kept, last_kept, switch_idx, n_kept;
+  float start_ori, end_ori;
+  int ring_count[LVO_MAX_RINGS], ring_start[LVO_MAX_RINGS + 1];
+  int scan_start[LVO_MAX_RINGS], scan_end[LVO_MAX_RINGS];
+  int n_sharp, n_less_sharp, n_flat, n_less_flat;
+  int n_lf_cand;                       // less-flat candidates before the per-ring voxel filter
+  int lf_ring_off[LVO_MAX_RINGS + 1];  // offsets of the per-ring less-flat output
+  // ---- odometry
+  int odo_inited;
+  double para_q[4], para_t[3];  // laserOdometry.cpp:131-133
+  double q_w[4], t_w[3];        // laserOdometry.cpp:126-128
+  int n_corner_last, n_surf_last;
+  int corner_ring_first[LVO_MAX_RINGS + 2], surf_ring_first[LVO_MAX_RINGS + 2];
+  int odo_status;
+  // ---- mapping
+  double map_x[7];              // parameters[7], laserMapping.cpp:110
+  double q_wmap_wodom[4], t_wmap_wodom[3];
+  double q_wodom[4], t_wodom[3];
+  int cen[3];                   // laserCloudCen{Width,Height,Depth}
+  int center[3];                // centerCubeI/J/K
+  int shift[3];                 // pending cube shift of the stored map relative to `cen` (applied at rebuild)
+  int n_valid, valid_cube[LVO_MAX_VALID];
+  int from_off[2][LVO_MAX_VALID + 1];  // offsets of each valid cube inside corner/surf FromMap
+  int n_stack[2];               // corner / surf stack sizes
+  int n_map[2];                 // points stored in all cubes
+  int map_status;
+  int map_too_small;
+  // ---- solver bookkeeping
+  int n_factors;
+  lvo_stats stats;
+  int status;
+};
+
+// Launch accounting (bench.py's gpu_launches) and error capture.
+struct LvoLaunchCounter { long long launches; };
+
+#define LVO_CUDA_OK(ctx, expr)                                                                          \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) {                                                                            \
+      lvo_set_error((ctx), std::string(#expr) + ": " + cudaGetErrorString(_e));                         \
+      return LVO_E_CUDA;                                                                                \
+    }                                                                                                   \
+  } while (0)
+
+struct lvo_ctx;
+void lvo_set_error(lvo_ctx* ctx, const std::string& msg);
+
+static inline int lvo_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------------------
+// Device helpers shared by all kernels
+// ------------------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+struct d3 { double x, y, z; };
+__device__ __forceinline__ d3 d3cross(const d3& a, const d3& b) { return d3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+// Eigen 3.3.7 QuaternionBase::_transformVector: uv = vec x v; uv += uv; v + w*uv + vec x uv.  q = (x,y,z,w).
+__device__ __forceinline__ d3 quat_rotate(const double* q, const d3& v) {
+  d3 qv{q[0], q[1], q[2]};
+  d3 uv = d3cross(qv, v);
+  uv.x += uv.x; uv.y += uv.y; uv.z += uv.z;
+  d3 c2 = d3cross(qv, uv);
+  return d3{(v.x + q[3] * uv.x) + c2.x, (v.y + q[3] * uv.y) + c2.y, (v.z + q[3] * uv.z) + c2.z};
+}
+// Eigen generic quaternion product
+__device__ __forceinline__ void quat_mul(const double* a, const double* b, double* r) {
+  double w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+  double x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+  double y = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+  double z = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z; r[3] = w;
+}
+// pointAssociateToMap (laserMapping.cpp:154-163) / TransformToStart with s = 1 (laserOdometry.cpp:154-172):
+// rotate + translate in double, round to float once.
+__device__ __forceinline__ float4 transform_point(const double* q, const double* t, float4 p) {
+  d3 r = quat_rotate(q, d3{(double)p.x, (double)p.y, (double)p.z});
+  return make_float4((float)(r.x + t[0]), (float)(r.y + t[1]), (float)(r.z + t[2]), p.w);
+}
+// FLANN L2_Simple accumulation order, no FMA (TU compiled with -fmad=false)
+__device__ __forceinline__ float sqdist3(float4 a, float qx, float qy, float qz) {
+  float dx = a.x - qx, dy = a.y - qy, dz = a.z - qz;
+  return dx * dx + dy * dy + dz * dz;
+}
+// cube index of laserMapping.cpp:741-750: int((v + 25.0) / 50.0) + cen, minus one on the negative side
+__device__ __forceinline__ int cube_coord(double v, int cen) {
+  int c = int((v + 25.0) / 50.0) + cen;
+  if (v + 25.0 < 0) c--;
+  return c;
+}
+#endif  // __CUDACC__

@@ -1,0 +1,439 @@
+// lvo_mapping.cuh — lvo_scan_to_map: the body of process(), reference src/laserMapping.cpp:307-848.
+//
+// Map layout in HBM: per lane and per type (corner / surf) ONE array of float4 sorted by the reference's cube array
+// index i + 21 j + 441 k (:522) plus a 4852-entry exclusive offset table; two generations (ping-pong) so that the
+// per-frame rebuild is a pure gather.  The pointer rotations of :323-507 never move data: a shift only changes
+// laserCloudCen* and a pending offset that the rebuild applies (cubes that leave the 21x21x11 window are dropped,
+// which is what `->clear()` on the recycled cube does).
+//
+//   k_map_begin        transformAssociateToMap :142-146, centre cube + shift loops :312-507, valid list :512-529
+//   k_map_gather       concatenation of the 75 valid cubes in i,j,k loop order :531-537 (defines the kNN point ids)
+//   stack downsample   lvo_voxel_run over 2 segments per lane (corner lineRes / surf planeRes) :542-550
+//   lvo_grid_build     replaces the two kd-tree builds :558-559
+//   k_map_assoc        per outer iteration (:562): pointAssociateToMap :154-163, 5-NN + d5^2 < 1 gate :582-584 /
+//                      :648-652, line fit by 3x3 symmetric eigen-solve :586-621, plane fit by 5x3 least squares
+//                      :650-686, factor records for LidarEdgeFactor / LidarPlaneNormFactor
+//   k_lm_solve         ceres::Solve :712-720
+//   k_map_finish       transformUpdate :148-152
+//   refilter           insert the transformed stack points into their cubes :737-783 and VoxelGrid every valid cube
+//                      :788-801: one lvo_voxel_run over 77 segments per lane and type
+//   k_rebuild_*        new cube offset table + gather into the other map generation
+//   k_register         registered full-resolution cloud :838-842
+#pragma once
+#include "lvo_internal.h"
+#include "lvo_knn.cuh"
+#include "lvo_solver.cuh"
+#include "lvo_voxel.cuh"
+
+#define LVO_SEG_NONVALID 75
+#define LVO_SEG_TRASH 76
+#define LVO_MSEGS 77
+
+struct MapArgs {
+  LaneState* ls;
+  int lanes, outer, from_odo;
+  float leaf[2];                     // lineRes, planeRes as float (setLeafSize takes floats)
+  // inputs: corner_last / surf_last / full-res of this frame
+  const float4* in_pts[2]; int in_cap[2];   // less_sharp [cap_lsharp], less_flat [P]; counts n_less_sharp / n_less_flat
+  const float4* full; int P;
+  // map generations
+  float4* map_pts[2][2];             // [gen][type] -> [lanes][map_cap[type]]
+  unsigned* cube_start[2][2];        // [gen][type] -> [lanes][LVO_NCUBES + 1]
+  int map_cap[2];
+  int gen;                           // generation holding the current map
+  float4* from_map[2];               // [type] -> [lanes][map_cap[type]]
+  float4* stack[2];                  // [type] -> [lanes][in_cap[type]]
+  GridSet grid;                      // problems 2*lane+type over from_map
+  VoxelEngine vx;
+  unsigned* item_off;                // [2*lanes + 1] offsets of each (lane,type) block inside the engine input
+  LvoFactor* factors; int factor_cap;
+  unsigned* app_cnt;                 // [2*lanes][LVO_NCUBES] appended (non-valid cube) counts
+  unsigned* app_first;               // [2*lanes][LVO_NCUBES] first engine output position of those
+  unsigned* new_cnt;                 // [2*lanes][LVO_NCUBES + 1]
+  // probes
+  int* knn_ind[2];                   // [type] -> [lanes][LVO_MAX_OUTER][in_cap[type]][5]
+  int* fac_valid[2];                 // [type] -> [lanes][LVO_MAX_OUTER][in_cap[type]]
+  float4* registered;                // [lanes][P] or null
+};
+
+__device__ __forceinline__ int cube_index(int i, int j, int k) { return i + LVO_CUBE_W * j + LVO_CUBE_W * LVO_CUBE_H * k; }
+
+__global__ void k_map_begin(MapArgs a) {
+  const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= a.lanes) return;
+  LaneState& s = a.ls[lane];
+  if (a.from_odo) { for (int k = 0; k < 4; ++k) s.q_wodom[k] = s.q_w[k]; for (int k = 0; k < 3; ++k) s.t_wodom[k] = s.t_w[k]; }
+  // transformAssociateToMap
+  quat_mul(s.q_wmap_wodom, s.q_wodom, s.map_x);
+  const d3 r = quat_rotate(s.q_wmap_wodom, d3{s.t_wodom[0], s.t_wodom[1], s.t_wodom[2]});
+  s.map_x[4] = r.x + s.t_wmap_wodom[0]; s.map_x[5] = r.y + s.t_wmap_wodom[1]; s.map_x[6] = r.z + s.t_wmap_wodom[2];
+  const int dims[3] = {LVO_CUBE_W, LVO_CUBE_H, LVO_CUBE_D};
+  for (int c = 0; c < 3; ++c) {
+    int center = cube_coord(s.map_x[4 + c], s.cen[c]);  // :312-321
+    int sh = 0;
+    while (center < 3) { center++; sh++; }                 // :323-352 etc: contents move to higher indices
+    while (center >= dims[c] - 3) { center--; sh--; }      // :354-383 etc
+    s.center[c] = center; s.cen[c] += sh; s.shift[c] = sh;
+  }
+  int nv = 0;
+  for (int i = s.center[0] - 2; i <= s.center[0] + 2; i++)
+    for (int j = s.center[1] - 2; j <= s.center[1] + 2; j++)
+      for (int k = s.center[2] - 1; k <= s.center[2] + 1; k++)
+        if (i >= 0 && i < LVO_CUBE_W && j >= 0 && j < LVO_CUBE_H && k >= 0 && k < LVO_CUBE_D) s.valid_cube[nv++] = cube_index(i, j, k);
+  s.n_valid = nv;
+  // sizes of the valid cubes in the stored (pre-shift) indexing
+  for (int t = 0; t < 2; ++t) {
+    const unsigned* cs = a.cube_start[a.gen][t] + (size_t)lane * (LVO_NCUBES + 1);
+    int acc = 0;
+    for (int v = 0; v < nv; ++v) {
+      const int c = s.valid_cube[v];
+      const int i = c % LVO_CUBE_W - s.shift[0], j = (c / LVO_CUBE_W) % LVO_CUBE_H - s.shift[1], k = c / (LVO_CUBE_W * LVO_CUBE_H) - s.shift[2];
+      int cnt = 0;
+      if (i >= 0 && i < LVO_CUBE_W && j >= 0 && j < LVO_CUBE_H && k >= 0 && k < LVO_CUBE_D) { const int oc = cube_index(i, j, k); cnt = (int)(cs[oc + 1] - cs[oc]); }
+      s.from_off[t][v] = acc;
+      acc += cnt;
+    }
+    for (int v = nv; v <= LVO_MAX_VALID; ++v) s.from_off[t][v] = acc;
+  }
+  s.stats.map_corner_from_map = s.from_off[0][LVO_MAX_VALID];
+  s.stats.map_surf_from_map = s.from_off[1][LVO_MAX_VALID];
+  s.map_too_small = !(s.from_off[0][LVO_MAX_VALID] > 10 && s.from_off[1][LVO_MAX_VALID] > 50);  // :554
+  s.map_status = s.map_too_small ? LVO_W_MAP_TOO_SMALL : LVO_OK;
+  for (int o = 0; o < LVO_MAX_OUTER; ++o) { s.stats.map_corner_corr[o] = 0; s.stats.map_surf_corr[o] = 0; s.stats.map_lm_iters[o] = 0; s.stats.map_final_cost[o] = 0; }
+  for (int c = 0; c < 3; ++c) { s.stats.center_cube[c] = s.center[c]; s.stats.cen[c] = s.cen[c]; }
+}
+
+// grid (LVO_MAX_VALID, 2 * lanes): copy one valid cube into FromMap
+__global__ void k_map_gather(MapArgs a) {
+  const int v = blockIdx.x, lt = blockIdx.y, lane = lt >> 1, t = lt & 1;
+  const LaneState& s = a.ls[lane];
+  if (v >= s.n_valid) return;
+  const int c = s.valid_cube[v];
+  const int i = c % LVO_CUBE_W - s.shift[0], j = (c / LVO_CUBE_W) % LVO_CUBE_H - s.shift[1], k = c / (LVO_CUBE_W * LVO_CUBE_H) - s.shift[2];
+  if (!(i >= 0 && i < LVO_CUBE_W && j >= 0 && j < LVO_CUBE_H && k >= 0 && k < LVO_CUBE_D)) return;
+  const int oc = cube_index(i, j, k);
+  const unsigned* cs = a.cube_start[a.gen][t] + (size_t)lane * (LVO_NCUBES + 1);
+  const unsigned b = cs[oc], e = cs[oc + 1];
+  const float4* src = a.map_pts[a.gen][t] + (size_t)lane * a.map_cap[t];
+  float4* dst = a.from_map[t] + (size_t)lane * a.map_cap[t] + s.from_off[t][v];
+  for (unsigned x = b + threadIdx.x; x < e; x += blockDim.x) dst[x - b] = src[x];
+}
+
+// ---- stack downsample (engine run A) -------------------------------------------------------------------------------
+__global__ void k_stack_offsets(MapArgs a) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  unsigned acc = 0;
+  for (int lt = 0; lt < 2 * a.lanes; ++lt) {
+    a.item_off[lt] = acc;
+    const LaneState& s = a.ls[lt >> 1];
+    acc += (unsigned)((lt & 1) ? s.n_less_flat : s.n_less_sharp);
+    a.vx.seg_leaf[lt] = a.leaf[lt & 1];
+  }
+  a.item_off[2 * a.lanes] = acc;
+  *a.vx.d_n = (int)acc;
+  *a.vx.d_nsegs = 2 * a.lanes;
+}
+__global__ void k_stack_gather(MapArgs a) {
+  const int lt = blockIdx.y, lane = lt >> 1, t = lt & 1;
+  const LaneState& s = a.ls[lane];
+  const int n = t ? s.n_less_flat : s.n_less_sharp;
+  const float4* src = a.in_pts[t] + (size_t)lane * a.in_cap[t];
+  const unsigned off = a.item_off[lt];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    a.vx.in_pts[off + i] = src[i];
+    a.vx.in_seg[off + i] = lt;
+    a.vx.in_aux[off + i] = 0;
+  }
+}
+__global__ void k_stack_scatter(MapArgs a) {
+  const int lt = blockIdx.y, lane = lt >> 1, t = lt & 1;
+  LaneState& s = a.ls[lane];
+  const unsigned b = a.vx.seg_out_start[lt], n = a.vx.seg_out_cnt[lt];
+  float4* dst = a.stack[t] + (size_t)lane * a.in_cap[t];
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = a.vx.out_pts[b + i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    s.n_stack[t] = (int)n;
+    if (t == 0) s.stats.map_corner_stack = (int)n; else s.stats.map_surf_stack = (int)n;
+  }
+}
+
+// ---- association + fit ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_map_assoc(MapArgs a) {
+  const int lane = blockIdx.y;
+  LaneState& s = a.ls[lane];
+  if (s.map_too_small) return;
+  const int n0 = s.n_stack[0], n1 = s.n_stack[1];
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const unsigned ln = threadIdx.x & 31;
+  const GridView g0 = grid_view(a.grid, 2 * lane), g1 = grid_view(a.grid, 2 * lane + 1);
+  const float4* M0 = a.from_map[0] + (size_t)lane * a.map_cap[0];
+  const float4* M1 = a.from_map[1] + (size_t)lane * a.map_cap[1];
+  int nc = 0, nsf = 0;
+  for (int f = wid; f < n0 + n1; f += nw) {
+    const int t = f < n0 ? 0 : 1;
+    const int i = t ? f - n0 : f;
+    const float4 ori = a.stack[t][(size_t)lane * a.in_cap[t] + i];
+    const float4 sel = transform_point(s.map_x, s.map_x + 4, ori);  // pointAssociateToMap
+    TopK<5> tk;
+    const bool ok = warp_knn<5>(t ? g1 : g0, sel.x, sel.y, sel.z, 1.0f, tk);
+    if (ln == 0) {
+      LvoFactor fac;
+      fac.type = -1; fac.pad = 0; fac.d = 0;
+      const float4* M = t ? M1 : M0;
+      if (ok) {
+        float4 nb[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) nb[j] = M[tk.id[j]];
+        if (t == 0) {
+          d3 center{0, 0, 0};
+#pragma unroll
+          for (int j = 0; j < 5; ++j) { center.x = center.x + (double)nb[j].x; center.y = center.y + (double)nb[j].y; center.z = center.z + (double)nb[j].z; }
+          center.x = center.x / 5.0; center.y = center.y / 5.0; center.z = center.z / 5.0;
+          double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const double z[3] = {(double)nb[j].x - center.x, (double)nb[j].y - center.y, (double)nb[j].z - center.z};
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) cov[r * 3 + c] = cov[r * 3 + c] + z[r] * z[c];
+          }
+          double w[3], V[9];
+          sym_eigen3_dev(cov, w, V);
+          if (w[2] > 3 * w[1]) {  // :611
+            const double ux = V[0 * 3 + 2], uy = V[1 * 3 + 2], uz = V[2 * 3 + 2];
+            fac.type = 0;
+            fac.c[0] = ori.x; fac.c[1] = ori.y; fac.c[2] = ori.z;
+            fac.a[0] = 0.1 * ux + center.x; fac.a[1] = 0.1 * uy + center.y; fac.a[2] = 0.1 * uz + center.z;
+            fac.b[0] = -0.1 * ux + center.x; fac.b[1] = -0.1 * uy + center.y; fac.b[2] = -0.1 * uz + center.z;
+          }
+        } else {
+          double A[15], b[5] = {-1, -1, -1, -1, -1}, n[3];
+#pragma unroll
+          for (int j = 0; j < 5; ++j) { A[j * 3 + 0] = nb[j].x; A[j * 3 + 1] = nb[j].y; A[j * 3 + 2] = nb[j].z; }
+          if (!lsq_qr_5x3(A, b, n)) { n[0] = n[1] = n[2] = 0; }
+          const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+          const double negOA = 1 / nn;
+          n[0] /= nn; n[1] /= nn; n[2] /= nn;
+          bool planeValid = true;
+#pragma unroll
+          for (int j = 0; j < 5; ++j)
+            if (fabs(n[0] * nb[j].x + n[1] * nb[j].y + n[2] * nb[j].z + negOA) > 0.2) { planeValid = false; }  // :672-678
+          if (planeValid) {
+            fac.type = 2;
+            fac.c[0] = ori.x; fac.c[1] = ori.y; fac.c[2] = ori.z;
+            fac.a[0] = n[0]; fac.a[1] = n[1]; fac.a[2] = n[2];
+            fac.b[0] = fac.b[1] = fac.b[2] = 0;
+            fac.d = negOA;
+          }
+        }
+      }
+      a.factors[(size_t)lane * a.factor_cap + f] = fac;
+      int* ki = a.knn_ind[t] + (((size_t)lane * LVO_MAX_OUTER + a.outer) * a.in_cap[t] + i) * 5;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) ki[j] = ok ? tk.id[j] : -1;
+      a.fac_valid[t][((size_t)lane * LVO_MAX_OUTER + a.outer) * a.in_cap[t] + i] = fac.type >= 0 ? 1 : 0;
+      if (fac.type >= 0) { if (t == 0) nc++; else nsf++; }
+    }
+  }
+  if (ln == 0) {
+    if (nc) atomicAdd(&s.stats.map_corner_corr[a.outer], nc);
+    if (nsf) atomicAdd(&s.stats.map_surf_corr[a.outer], nsf);
+  }
+}
+
+__global__ void k_map_finish(MapArgs a) {
+  const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= a.lanes) return;
+  LaneState& s = a.ls[lane];
+  // transformUpdate :148-152: q_wmap_wodom = q_w_curr * q_wodom_curr.inverse(); t_wmap_wodom = t_w_curr - q_wmap_wodom * t_wodom_curr
+  const double* q = s.q_wodom;
+  const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  const double qi[4] = {-q[0] / n2, -q[1] / n2, -q[2] / n2, q[3] / n2};
+  quat_mul(s.map_x, qi, s.q_wmap_wodom);
+  const d3 r = quat_rotate(s.q_wmap_wodom, d3{s.t_wodom[0], s.t_wodom[1], s.t_wodom[2]});
+  s.t_wmap_wodom[0] = s.map_x[4] - r.x; s.t_wmap_wodom[1] = s.map_x[5] - r.y; s.t_wmap_wodom[2] = s.map_x[6] - r.z;
+}
+
+// ---- insertion + per-cube re-filter (engine run B) ------------------------------------------------------------------
+__global__ void k_refilter_offsets(MapArgs a) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  unsigned acc = 0;
+  for (int lt = 0; lt < 2 * a.lanes; ++lt) {
+    const int t = lt & 1;
+    const LaneState& s = a.ls[lt >> 1];
+    a.item_off[lt] = acc;
+    acc += (unsigned)(s.from_off[t][LVO_MAX_VALID] + s.n_stack[t]);
+    for (int v = 0; v < LVO_MSEGS; ++v) a.vx.seg_leaf[lt * LVO_MSEGS + v] = v < LVO_MAX_VALID ? a.leaf[t] : 0.f;
+  }
+  a.item_off[2 * a.lanes] = acc;
+  *a.vx.d_n = (int)acc;
+  *a.vx.d_nsegs = 2 * a.lanes * LVO_MSEGS;
+}
+__global__ void k_refilter_gather(MapArgs a) {
+  const int lt = blockIdx.y, lane = lt >> 1, t = lt & 1;
+  const LaneState& s = a.ls[lane];
+  const int nfrom = s.from_off[t][LVO_MAX_VALID], nst = s.n_stack[t];
+  const unsigned off = a.item_off[lt];
+  const float4* FM = a.from_map[t] + (size_t)lane * a.map_cap[t];
+  const float4* ST = a.stack[t] + (size_t)lane * a.in_cap[t];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nfrom + nst; i += gridDim.x * blockDim.x) {
+    float4 p; int seg; unsigned aux = 0;
+    if (i < nfrom) {
+      p = FM[i];
+      // valid-cube rank by binary search in from_off
+      int lo = 0, hi = s.n_valid - 1;
+      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s.from_off[t][mid] <= i) lo = mid; else hi = mid - 1; }
+      seg = lo;
+    } else {
+      p = transform_point(s.map_x, s.map_x + 4, ST[i - nfrom]);  // :739 / :763 with the final pose
+      const int ci = cube_coord((double)p.x, s.cen[0]), cj = cube_coord((double)p.y, s.cen[1]), ck = cube_coord((double)p.z, s.cen[2]);
+      if (ci >= 0 && ci < LVO_CUBE_W && cj >= 0 && cj < LVO_CUBE_H && ck >= 0 && ck < LVO_CUBE_D) {
+        const int di = ci - (s.center[0] - 2), dj = cj - (s.center[1] - 2), dk = ck - (s.center[2] - 1);
+        aux = (unsigned)cube_index(ci, cj, ck);
+        if (di >= 0 && di < 5 && dj >= 0 && dj < 5 && dk >= 0 && dk < 3) seg = (di * 5 + dj) * 3 + dk;  // centre is >= 3 cubes from every face: the list is never clipped
+        else seg = LVO_SEG_NONVALID;
+      } else seg = LVO_SEG_TRASH;
+    }
+    a.vx.in_pts[off + i] = p;
+    a.vx.in_seg[off + i] = lt * LVO_MSEGS + seg;
+    a.vx.in_aux[off + i] = aux;
+  }
+}
+__global__ void k_rebuild_reset(MapArgs a) {
+  const int n = 2 * a.lanes * LVO_NCUBES;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { a.app_cnt[i] = 0; a.app_first[i] = 0xffffffffu; }
+}
+// appended points (non-valid cubes): count per cube and first engine-output position
+__global__ void k_rebuild_appended(MapArgs a) {
+  const int lt = blockIdx.y;
+  const int seg = lt * LVO_MSEGS + LVO_SEG_NONVALID;
+  const unsigned b = a.vx.seg_out_start[seg], n = a.vx.seg_out_cnt[seg];
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned cube = a.vx.out_aux[b + i];
+    atomicAdd(&a.app_cnt[(size_t)lt * LVO_NCUBES + cube], 1u);
+    atomicMin(&a.app_first[(size_t)lt * LVO_NCUBES + cube], b + i);
+  }
+}
+// one block per (lane, type): new per-cube counts and their exclusive scan
+__global__ void __launch_bounds__(256) k_rebuild_offsets(MapArgs a) {
+  __shared__ unsigned sm[33];
+  __shared__ signed char vrank[LVO_NCUBES];
+  const int lt = blockIdx.x, lane = lt >> 1, t = lt & 1;
+  LaneState& s = a.ls[lane];
+  for (int c = threadIdx.x; c < LVO_NCUBES; c += blockDim.x) vrank[c] = -1;
+  __syncthreads();
+  if (threadIdx.x < s.n_valid) vrank[s.valid_cube[threadIdx.x]] = (signed char)threadIdx.x;
+  __syncthreads();
+  const unsigned* cs = a.cube_start[a.gen][t] + (size_t)lane * (LVO_NCUBES + 1);
+  unsigned* ncs = a.cube_start[a.gen ^ 1][t] + (size_t)lane * (LVO_NCUBES + 1);
+  unsigned carry = 0;
+  for (int base = 0; base < LVO_NCUBES; base += blockDim.x) {
+    const int c = base + threadIdx.x;
+    unsigned cnt = 0;
+    if (c < LVO_NCUBES) {
+      const int v = vrank[c];
+      if (v >= 0) cnt = a.vx.seg_out_cnt[lt * LVO_MSEGS + v];
+      else {
+        const int i = c % LVO_CUBE_W - s.shift[0], j = (c / LVO_CUBE_W) % LVO_CUBE_H - s.shift[1], k = c / (LVO_CUBE_W * LVO_CUBE_H) - s.shift[2];
+        if (i >= 0 && i < LVO_CUBE_W && j >= 0 && j < LVO_CUBE_H && k >= 0 && k < LVO_CUBE_D) { const int oc = cube_index(i, j, k); cnt = cs[oc + 1] - cs[oc]; }
+        cnt += a.app_cnt[(size_t)lt * LVO_NCUBES + c];
+      }
+    }
+    unsigned tot;
+    const unsigned ex = block_excl_scan(cnt, sm, &tot);
+    if (c < LVO_NCUBES) ncs[c] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) {
+    ncs[LVO_NCUBES] = carry;
+    s.n_map[t] = (int)carry;
+    if (t == 0) s.stats.map_corner_total = (int)carry; else s.stats.map_surf_total = (int)carry;
+    if ((int)carry > a.map_cap[t]) s.map_status = LVO_E_CAPACITY;
+  }
+}
+// destination-parallel gather into the other generation
+__global__ void __launch_bounds__(256) k_rebuild_copy(MapArgs a) {
+  __shared__ signed char vrank[LVO_NCUBES];
+  const int lt = blockIdx.y, lane = lt >> 1, t = lt & 1;
+  const LaneState& s = a.ls[lane];
+  for (int c = threadIdx.x; c < LVO_NCUBES; c += blockDim.x) vrank[c] = -1;
+  __syncthreads();
+  if (threadIdx.x < s.n_valid) vrank[s.valid_cube[threadIdx.x]] = (signed char)threadIdx.x;
+  __syncthreads();
+  const unsigned* cs = a.cube_start[a.gen][t] + (size_t)lane * (LVO_NCUBES + 1);
+  const unsigned* ncs = a.cube_start[a.gen ^ 1][t] + (size_t)lane * (LVO_NCUBES + 1);
+  const float4* src = a.map_pts[a.gen][t] + (size_t)lane * a.map_cap[t];
+  float4* dst = a.map_pts[a.gen ^ 1][t] + (size_t)lane * a.map_cap[t];
+  const unsigned n = min(ncs[LVO_NCUBES], (unsigned)a.map_cap[t]);
+  for (unsigned d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x) {
+    int lo = 0, hi = LVO_NCUBES - 1;  // last cube with ncs[c] <= d
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (ncs[mid] <= d) lo = mid; else hi = mid - 1; }
+    const int c = lo;
+    const unsigned r = d - ncs[c];
+    const int v = vrank[c];
+    float4 p;
+    if (v >= 0) p = a.vx.out_pts[a.vx.seg_out_start[lt * LVO_MSEGS + v] + r];
+    else {
+      const int i = c % LVO_CUBE_W - s.shift[0], j = (c / LVO_CUBE_W) % LVO_CUBE_H - s.shift[1], k = c / (LVO_CUBE_W * LVO_CUBE_H) - s.shift[2];
+      unsigned ocnt = 0, ob = 0;
+      if (i >= 0 && i < LVO_CUBE_W && j >= 0 && j < LVO_CUBE_H && k >= 0 && k < LVO_CUBE_D) { const int oc = cube_index(i, j, k); ob = cs[oc]; ocnt = cs[oc + 1] - ob; }
+      if (r < ocnt) p = src[ob + r];
+      else p = a.vx.out_pts[a.app_first[(size_t)lt * LVO_NCUBES + c] + (r - ocnt)];
+    }
+    dst[d] = p;
+  }
+}
+__global__ void k_map_end(MapArgs a) {
+  const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= a.lanes) return;
+  LaneState& s = a.ls[lane];
+  s.shift[0] = s.shift[1] = s.shift[2] = 0;
+}
+__global__ void k_register(MapArgs a) {
+  const int lane = blockIdx.y;
+  const LaneState& s = a.ls[lane];
+  const int n = s.n_kept;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    a.registered[(size_t)lane * a.P + i] = transform_point(s.map_x, s.map_x + 4, a.full[(size_t)lane * a.P + i]);
+}
+
+static inline void lvo_launch_mapping(cudaStream_t st, MapArgs a, const SolveArgs& solve_proto, int outer_iters, int lanes, bool want_registered,
+                                      long long* launches, cudaEvent_t* knn_ev /* [2*outer] or null */) {
+  const int L2 = 2 * lanes;
+  k_map_begin<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a);
+  k_map_gather<<<dim3(LVO_MAX_VALID, L2), 128, 0, st>>>(a);
+  k_stack_offsets<<<1, 32, 0, st>>>(a);
+  k_stack_gather<<<dim3(16, L2), 256, 0, st>>>(a);
+  if (launches) *launches += 4;
+  int seg_bits = 1; while ((1 << seg_bits) < L2) seg_bits++;
+  lvo_voxel_run(st, a.vx, lanes * (a.in_cap[0] + a.in_cap[1]), L2, seg_bits, launches);
+  k_stack_scatter<<<dim3(8, L2), 256, 0, st>>>(a);
+  if (launches) *launches += 1;
+  lvo_grid_build(st, a.grid, launches);
+  const int nstack_cap = a.in_cap[0] + a.in_cap[1];
+  dim3 ga(max(1, min(lvo_div_up(nstack_cap, 8), 296)), lanes);
+  for (int o = 0; o < outer_iters; ++o) {
+    a.outer = o;
+    if (knn_ev) cudaEventRecord(knn_ev[2 * o], st);
+    k_map_assoc<<<ga, 256, 0, st>>>(a);
+    if (knn_ev) cudaEventRecord(knn_ev[2 * o + 1], st);
+    SolveArgs sa = solve_proto;
+    sa.which = 1; sa.outer = o; sa.factors = a.factors; sa.factor_cap = a.factor_cap;
+    k_lm_solve<<<lanes, LVO_LM_THREADS, 0, st>>>(sa);
+    if (launches) *launches += 2;
+  }
+  k_map_finish<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a);
+  k_refilter_offsets<<<1, 32, 0, st>>>(a);
+  k_refilter_gather<<<dim3(64, L2), 256, 0, st>>>(a);
+  if (launches) *launches += 3;
+  int seg_bits2 = 1; while ((1 << seg_bits2) < L2 * LVO_MSEGS) seg_bits2++;
+  lvo_voxel_run(st, a.vx, a.vx.cap_items, L2 * LVO_MSEGS, seg_bits2, launches);
+  k_rebuild_reset<<<148, 256, 0, st>>>(a);
+  k_rebuild_appended<<<dim3(4, L2), 256, 0, st>>>(a);
+  k_rebuild_offsets<<<L2, 256, 0, st>>>(a);
+  k_rebuild_copy<<<dim3(64, L2), 256, 0, st>>>(a);
+  k_map_end<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a);
+  if (launches) *launches += 5;
+  if (want_registered && a.registered) { k_register<<<dim3(64, lanes), 256, 0, st>>>(a); if (launches) *launches += 1; }
+}

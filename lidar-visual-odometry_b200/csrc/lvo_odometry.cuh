@@ -1,0 +1,203 @@
+// lvo_odometry.cuh — lvo_scan_to_scan: the odometry frame body, reference src/laserOdometry.cpp:353-641
+// (DISTORTION 0, :67).
+//
+//   k_odo_begin      first-frame handling (:355-358), per-outer-iteration counter reset
+//   k_odo_assoc      one warp per feature: TransformToStart (:154-172, s = 1), 1-NN in the previous sweep's
+//                    less-sharp / less-flat cloud on the uniform grid with the d^2 < 25 gate (:386-389, :470-473),
+//                    then the adjacent-ring searches of :395-440 / :481-532 as range scans over a ring-offset table
+//                    (the clouds are ring-ordered by construction), with the reference's walk order as tie-break;
+//                    emits LidarEdgeFactor / LidarPlaneFactor parameter records (:444-462, :536-557)
+//   k_lm_solve       (lvo_solver.cuh) ceres::Solve, :571-576
+//   k_odo_finish     pose integration :581-582, swap of the "last" clouds :627-636, ring-offset tables
+//   lvo_grid_build   (lvo_knn.cuh) replaces kdtree->setInputCloud :640-641
+#pragma once
+#include "lvo_internal.h"
+#include "lvo_knn.cuh"
+#include "lvo_solver.cuh"
+
+struct OdoArgs {
+  LaneState* ls;
+  int lanes, outer;
+  // current features (stride caps)
+  const float4* sharp; const float4* less_sharp; const float4* flat; const float4* less_flat;
+  int cap_sharp, cap_lsharp, cap_flat, P;
+  // previous sweep
+  float4* corner_last; float4* surf_last;  // [lanes][cap_lsharp], [lanes][P]
+  GridSet grid;                            // problems 2*lane (corner_last), 2*lane+1 (surf_last)
+  LvoFactor* factors; int factor_cap;
+  int* corner_corr;  // [lanes][LVO_MAX_OUTER][cap_sharp][2]   probes
+  int* plane_corr;   // [lanes][LVO_MAX_OUTER][cap_flat][3]
+};
+
+__global__ void k_odo_begin(OdoArgs a) {
+  const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= a.lanes) return;
+  LaneState& s = a.ls[lane];
+  s.odo_status = s.odo_inited ? LVO_OK : LVO_W_FIRST_FRAME;
+  for (int o = 0; o < LVO_MAX_OUTER; ++o) { s.stats.odo_corner_corr[o] = 0; s.stats.odo_plane_corr[o] = 0; s.stats.odo_lm_iters[o] = 0; s.stats.odo_final_cost[o] = 0; }
+}
+
+struct Best { float d; int pos; int j; };
+__device__ __forceinline__ Best best_min(Best a, Best b) { return (b.d < a.d || (b.d == a.d && b.pos < a.pos)) ? b : a; }
+__device__ __forceinline__ Best warp_best(Best v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Best w;
+    w.d = __shfl_xor_sync(0xffffffffu, v.d, o); w.pos = __shfl_xor_sync(0xffffffffu, v.pos, o); w.j = __shfl_xor_sync(0xffffffffu, v.j, o);
+    v = best_min(v, w);
+  }
+  return v;
+}
+// Nearest point (d^2 < 25, strict) over the walk  j = ub .. ue-1 ascending, then j = de-1 .. db descending;
+// earlier positions in the walk win ties, exactly like the reference's strict `<` updates.
+__device__ __forceinline__ int walk_min(const float4* C, int ub, int ue, int db, int de, float4 sel, unsigned ln) {
+  Best b{25.0f, INT_MAX, -1};
+  for (int j = ub + (int)ln; j < ue; j += 32) {
+    const float4 p = C[j];
+    const float d = (p.x - sel.x) * (p.x - sel.x) + (p.y - sel.y) * (p.y - sel.y) + (p.z - sel.z) * (p.z - sel.z);
+    if (d < 25.0f) b = best_min(b, Best{d, j - ub, j});
+  }
+  const int ulen = max(ue - ub, 0);
+  for (int j = de - 1 - (int)ln; j >= db; j -= 32) {
+    const float4 p = C[j];
+    const float d = (p.x - sel.x) * (p.x - sel.x) + (p.y - sel.y) * (p.y - sel.y) + (p.z - sel.z) * (p.z - sel.z);
+    if (d < 25.0f) b = best_min(b, Best{d, ulen + (de - 1 - j), j});
+  }
+  b = warp_best(b);
+  return b.j;
+}
+
+__global__ void __launch_bounds__(256) k_odo_assoc(OdoArgs a) {
+  const int lane = blockIdx.y;
+  LaneState& s = a.ls[lane];
+  if (!s.odo_inited) return;
+  const int ns = s.n_sharp, nf = s.n_flat;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const unsigned ln = threadIdx.x & 31;
+  const double* q = s.para_q; const double* t = s.para_t;
+  const float4* CL = a.corner_last + (size_t)lane * a.cap_lsharp;
+  const float4* SL = a.surf_last + (size_t)lane * a.P;
+  const GridView gc = grid_view(a.grid, 2 * lane), gsf = grid_view(a.grid, 2 * lane + 1);
+  int ncorr_c = 0, ncorr_p = 0;
+  for (int f = wid; f < ns + nf; f += nw) {
+    const bool corner = f < ns;
+    const float4 pt = corner ? a.sharp[(size_t)lane * a.cap_sharp + f] : a.flat[(size_t)lane * a.cap_flat + (f - ns)];
+    const float4 sel = transform_point(q, t, pt);  // TransformToStart
+    TopK<1> tk;
+    const bool ok = warp_knn<1>(corner ? gc : gsf, sel.x, sel.y, sel.z, 25.0f, tk);
+    LvoFactor fac;
+    fac.type = -1; fac.pad = 0; fac.d = 0;
+    int i1 = -1, i2 = -1, i3 = -1;
+    if (ok) {
+      const float4* C = corner ? CL : SL;
+      const int* rf = corner ? s.corner_ring_first : s.surf_ring_first;
+      const int closest = tk.id[0];
+      int cid = int(C[closest].w);
+      cid = min(max(cid, 0), LVO_MAX_RINGS - 1);
+      const int r_lo2 = rf[max(cid - 2, 0)], r_c = rf[cid], r_c1 = rf[cid + 1], r_hi = rf[min(cid + 3, LVO_MAX_RINGS + 1)];
+      // rings cid+1, cid+2 walked upwards, then cid-1, cid-2 walked downwards (:395-440 / the `> closestPointScanID` arms of :481-532)
+      const int other = walk_min(C, r_c1, r_hi, r_lo2, r_c, sel, ln);
+      if (corner) {
+        if (other >= 0) {
+          i1 = closest; i2 = other;
+          const float4 pa = C[closest], pb = C[other];
+          fac.type = 0;
+          fac.c[0] = pt.x; fac.c[1] = pt.y; fac.c[2] = pt.z;
+          fac.a[0] = pa.x; fac.a[1] = pa.y; fac.a[2] = pa.z;
+          fac.b[0] = pb.x; fac.b[1] = pb.y; fac.b[2] = pb.z;
+        }
+      } else {
+        // same ring: upwards from closest+1 to the end of the ring, then downwards from closest-1 (:493-497, :520-524)
+        const int same = walk_min(C, closest + 1, r_c1, r_c, closest, sel, ln);
+        if (same >= 0 && other >= 0) {
+          i1 = closest; i2 = same; i3 = other;
+          const float4 pj = C[closest], pl = C[same], pm = C[other];
+          // LidarPlaneFactor constructor, lidarFactor.hpp:64-65
+          const d3 jl{(double)pj.x - (double)pl.x, (double)pj.y - (double)pl.y, (double)pj.z - (double)pl.z};
+          const d3 jm{(double)pj.x - (double)pm.x, (double)pj.y - (double)pm.y, (double)pj.z - (double)pm.z};
+          d3 n = d3cross(jl, jm);
+          const double nn = sqrt(n.x * n.x + n.y * n.y + n.z * n.z);
+          fac.type = 1;
+          fac.c[0] = pt.x; fac.c[1] = pt.y; fac.c[2] = pt.z;
+          fac.a[0] = pj.x; fac.a[1] = pj.y; fac.a[2] = pj.z;
+          fac.b[0] = n.x / nn; fac.b[1] = n.y / nn; fac.b[2] = n.z / nn;
+        }
+      }
+    }
+    if (ln == 0) {
+      a.factors[(size_t)lane * a.factor_cap + f] = fac;
+      if (corner) {
+        int* c = a.corner_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer) * a.cap_sharp + f) * 2;
+        c[0] = i1; c[1] = i2;
+        if (fac.type >= 0) ncorr_c++;
+      } else {
+        int* c = a.plane_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer) * a.cap_flat + (f - ns)) * 3;
+        c[0] = i1; c[1] = i2; c[2] = i3;
+        if (fac.type >= 0) ncorr_p++;
+      }
+    }
+  }
+  if (ln == 0) {
+    if (ncorr_c) atomicAdd(&s.stats.odo_corner_corr[a.outer], ncorr_c);
+    if (ncorr_p) atomicAdd(&s.stats.odo_plane_corr[a.outer], ncorr_p);
+  }
+}
+
+// after the outer loop: few-correspondence warning (:566-568), pose integration (:581-582)
+__global__ void k_odo_integrate(OdoArgs a, int outer_iters) {
+  const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= a.lanes) return;
+  LaneState& s = a.ls[lane];
+  if (s.odo_inited) {
+    for (int o = 0; o < outer_iters; ++o)
+      if (s.stats.odo_corner_corr[o] + s.stats.odo_plane_corr[o] < 10) s.odo_status = LVO_W_FEW_CORR;
+    const d3 dt = quat_rotate(s.q_w, d3{s.para_t[0], s.para_t[1], s.para_t[2]});
+    s.t_w[0] = s.t_w[0] + dt.x; s.t_w[1] = s.t_w[1] + dt.y; s.t_w[2] = s.t_w[2] + dt.z;
+    double qn[4];
+    quat_mul(s.q_w, s.para_q, qn);
+    for (int k = 0; k < 4; ++k) s.q_w[k] = qn[k];
+  }
+  s.odo_inited = 1;
+  s.n_corner_last = s.n_less_sharp;
+  s.n_surf_last = s.n_less_flat;
+  for (int r = 0; r < LVO_MAX_RINGS + 2; ++r) { s.corner_ring_first[r] = s.n_less_sharp; s.surf_ring_first[r] = s.n_less_flat; }
+}
+// copy less-sharp / less-flat into the "last" buffers (the pointer swap of :627-636) and build the ring-offset tables:
+// ring_first[r] = first index whose ring id int(intensity) is >= r
+__global__ void k_odo_swap(OdoArgs a) {
+  const int lane = blockIdx.y;
+  LaneState& s = a.ls[lane];
+  const int nc = s.n_corner_last, nsf = s.n_surf_last;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc + nsf; i += stride) {
+    const bool corner = i < nc;
+    const int k = corner ? i : i - nc;
+    const float4* src = corner ? a.less_sharp + (size_t)lane * a.cap_lsharp : a.less_flat + (size_t)lane * a.P;
+    float4* dst = corner ? a.corner_last + (size_t)lane * a.cap_lsharp : a.surf_last + (size_t)lane * a.P;
+    int* rf = corner ? s.corner_ring_first : s.surf_ring_first;
+    const float4 p = src[k];
+    dst[k] = p;
+    const int r = min(max(int(p.w), 0), LVO_MAX_RINGS + 1);
+    const int rp = k > 0 ? min(max(int(src[k - 1].w), 0), LVO_MAX_RINGS + 1) : -1;
+    for (int x = rp + 1; x <= r; ++x) rf[x] = k;
+  }
+}
+
+static inline void lvo_launch_odometry(cudaStream_t st, OdoArgs a, const SolveArgs& solve_proto, int outer_iters, int lanes, long long* launches) {
+  k_odo_begin<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a);
+  if (launches) *launches += 1;
+  const int nfeat_cap = a.cap_sharp + a.cap_flat;
+  dim3 ga(max(1, min(lvo_div_up(nfeat_cap, 8), 148)), lanes);
+  for (int o = 0; o < outer_iters; ++o) {
+    a.outer = o;
+    k_odo_assoc<<<ga, 256, 0, st>>>(a);
+    SolveArgs sa = solve_proto;
+    sa.which = 0; sa.outer = o; sa.factors = a.factors; sa.factor_cap = a.factor_cap;
+    k_lm_solve<<<lanes, LVO_LM_THREADS, 0, st>>>(sa);
+    if (launches) *launches += 2;
+  }
+  k_odo_integrate<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a, outer_iters);
+  k_odo_swap<<<dim3(32, lanes), 256, 0, st>>>(a);
+  if (launches) *launches += 2;
+  lvo_grid_build(st, a.grid, launches);
+}

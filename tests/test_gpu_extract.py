@@ -1,0 +1,89 @@
+"""GPU parity: lvo_extract_features vs the oracle's scan registration (reference src/scanRegistration.cpp:127-411).
+Bar: bit-exact for every integer / index / float output (north_star)."""
+import numpy as np
+import pytest
+
+from oracle_py import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _compare_extract(L, lvo, O, pts, label):
+    ref = O.extract(pts)
+    st, got = lvo.extract_features(pts)
+    assert st == 0
+    for k in ("full", "sharp", "less_sharp", "flat", "less_flat"):
+        assert got[k].shape == ref[k].shape, f"{label}: {k} shape {got[k].shape} vs oracle {ref[k].shape}"
+        neq = np.nonzero((_bits(got[k]) != _bits(ref[k])).any(axis=1))[0]
+        assert neq.size == 0, f"{label}: {k} differs at {neq.size} rows, first {neq[:5]}: {got[k][neq[:3]]} vs {ref[k][neq[:3]]}"
+    n = len(ref["full"])
+    assert np.array_equal(_bits(lvo.probe(L.P_CURVATURE)), _bits(ref["curvature"])), f"{label}: curvature bits"
+    assert np.array_equal(lvo.probe(L.P_SCAN_START), ref["scan_start"]), f"{label}: scanStartInd"
+    assert np.array_equal(lvo.probe(L.P_SCAN_END), ref["scan_end"]), f"{label}: scanEndInd"
+    assert np.array_equal(lvo.probe(L.P_SORT_IND), ref["sort_ind"]), f"{label}: cloudSortInd"
+    assert np.array_equal(lvo.probe(L.P_LABEL), ref["label"]), f"{label}: cloudLabel"
+    assert np.array_equal(lvo.probe(L.P_PICKED), ref["picked"]), f"{label}: cloudNeighborPicked"
+    s = lvo.stats()
+    assert (s.n_in, s.n_kept, s.n_sharp, s.n_less_sharp, s.n_flat, s.n_less_flat) == (
+        len(pts), n, len(ref["sharp"]), len(ref["less_sharp"]), len(ref["flat"]), len(ref["less_flat"]))
+
+
+@pytest.mark.parametrize("seq,frame", [(0, 0), (1, 3), (2, 7), (3, 11)])
+def test_hdl64_sweeps_bit_exact(lvo_mod, synth, seq, frame):
+    L = lvo_mod
+    lvo = L.Lvo(n_scans=64, minimum_range=5.0)
+    pts, _ = synth.sweep(64, seq, frame)
+    _compare_extract(L, lvo, Oracle(64, 5.0), pts, f"hdl64 seq{seq} frame{frame}")
+    lvo.close()
+
+
+@pytest.mark.parametrize("seq,frame", [(0, 0), (1, 5)])
+def test_vlp16_sweeps_bit_exact(lvo_mod, synth, seq, frame):
+    L = lvo_mod
+    lvo = L.Lvo(n_scans=16, minimum_range=0.3, line_res=0.2, plane_res=0.4)
+    pts, _ = synth.sweep(16, seq, frame)
+    _compare_extract(L, lvo, Oracle(16, 0.3, 0.2, 0.4), pts, f"vlp16 seq{seq} frame{frame}")
+    lvo.close()
+
+
+def test_32_line_mode_and_pcl_layout(lvo_mod, synth):
+    """N_SCANS == 32 branch (:178-186) on a VLP-16-shaped sweep, passed with pcl::PointXYZI stride 32."""
+    L = lvo_mod
+    lvo = L.Lvo(n_scans=32, minimum_range=0.3)
+    pts, _ = synth.sweep(16, 0, 2)
+    ref = Oracle(32, 0.3).extract(pts)
+    st, got = lvo.extract_features(L.to_pcl_layout(pts))
+    assert st == 0
+    for k in ("full", "sharp", "less_sharp", "flat", "less_flat"):
+        assert got[k].shape == ref[k].shape and np.array_equal(_bits(got[k]), _bits(ref[k])), k
+    lvo.close()
+
+
+def test_edge_cases(lvo_mod, synth):
+    L = lvo_mod
+    lvo = L.Lvo(n_scans=64, minimum_range=5.0)
+    O = Oracle(64, 5.0)
+    # empty sweep
+    st, got = lvo.extract_features(np.zeros((0, 4), np.float32))
+    assert st == 0 and all(len(v) == 0 for v in got.values())
+    # everything closer than minimum_range
+    near = np.random.default_rng(0).normal(0, 1, (1000, 4)).astype(np.float32)
+    st, got = lvo.extract_features(near)
+    assert st == 0 and all(len(v) == 0 for v in got.values())
+    # NaN / inf points are dropped, ragged rings (random subset of a sweep), points on few rings only
+    pts, _ = synth.sweep(64, 0, 1)
+    rng = np.random.default_rng(1)
+    sub = pts[np.sort(rng.choice(len(pts), 40000, replace=False))].copy()
+    sub[::97, 0] = np.nan
+    sub[5::131, 2] = np.inf
+    _compare_extract(L, lvo, O, sub, "ragged+nan")
+    # a sweep small enough that most rings have < 6 usable points (:279-280)
+    tiny = pts[np.sort(rng.choice(len(pts), 700, replace=False))]
+    _compare_extract(L, lvo, O, tiny, "tiny")
+    # consecutive calls on one context must not leak state
+    _compare_extract(L, lvo, O, pts, "after-tiny")
+    lvo.close()

@@ -1,0 +1,137 @@
+"""GPU parity: lvo_scan_to_map vs the oracle's laserMapping restatement (reference src/laserMapping.cpp:307-848)."""
+import numpy as np
+import pytest
+
+from oracle_py import Oracle
+
+pytestmark = pytest.mark.gpu
+POS_TOL, ROT_TOL = 1e-4, 1e-5
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def rot_err(qa, qb):
+    return 2 * np.arccos(min(1.0, abs(float(np.dot(qa, qb)))))
+
+
+def _frames(synth, O, model, seq, n):
+    """Run the oracle pipeline; yield per-frame inputs of the mapping stage."""
+    out = []
+    for k in range(n):
+        pts, _ = synth.sweep(model, seq, k)
+        f = O.extract(pts)
+        _, _, w = O.odometry(f["sharp"], f["less_sharp"], f["flat"], f["less_flat"], keep_log=False)
+        out.append((f, w))
+    return out
+
+
+@pytest.mark.parametrize("model,cfg,seq", [(64, (64, 5.0, 0.4, 0.8), 0), (16, (16, 0.3, 0.2, 0.4), 1)])
+def test_scan_to_map_from_imported_state(lvo_mod, synth, model, cfg, seq):
+    L = lvo_mod
+    O = Oracle(*cfg)
+    lvo = L.Lvo(n_scans=cfg[0], minimum_range=cfg[1], line_res=cfg[2], plane_res=cfg[3], max_map_corner=1 << 18, max_map_surf=1 << 19)
+    frames = _frames(synth, O, model, seq, 7)
+    flips = rows = 0
+    corr_prev = np.array([0, 0, 0, 1, 0, 0, 0], float)
+    for k, (f, w) in enumerate(frames):
+        # identical starting state on both sides: the oracle's map and map correction
+        pc, cc = O.map_export(0)
+        ps, cs = O.map_export(1)
+        lvo.map_import(0, pc, cc, ps, cs)
+        lvo.set_map_correction(0, corr_prev)
+        st_o, pose_o, corr_o = O.mapping(f["less_sharp"], f["less_flat"], f["full"], w)
+        st_g, pose_g, reg_g = lvo.scan_to_map(f["less_sharp"], f["less_flat"], f["full"], w, want_registered=True)
+        assert st_g == st_o, (k, st_g, st_o)
+        info = O.mapping_info()
+        assert np.array_equal(_bits(lvo.probe(L.P_MAP_CORNER_STACK)), _bits(info["corner_stack"])), f"frame {k}: corner stack (VoxelGrid lineRes)"
+        assert np.array_equal(_bits(lvo.probe(L.P_MAP_SURF_STACK)), _bits(info["surf_stack"])), f"frame {k}: surf stack (VoxelGrid planeRes)"
+        assert np.array_equal(_bits(lvo.probe(L.P_MAP_CORNER_FROM_MAP)), _bits(info["corner_from_map"])), f"frame {k}: corner FromMap order"
+        assert np.array_equal(_bits(lvo.probe(L.P_MAP_SURF_FROM_MAP)), _bits(info["surf_from_map"])), f"frame {k}: surf FromMap order"
+        s = lvo.stats()
+        assert list(s.center_cube) == list(info["info"][:3]) and list(s.cen) == list(info["info"][3:6])
+        if st_o == 0:
+            kc, ks = lvo.probe(L.P_MAP_CORNER_KNN), lvo.probe(L.P_MAP_SURF_KNN)
+            vc, vs = lvo.probe(L.P_MAP_CORNER_VALID), lvo.probe(L.P_MAP_SURF_VALID)
+            tr = lvo.probe(L.P_MAP_LM_TRACE)
+            for o in range(O.outer):
+                lg = O.mapping_log(o)
+                f1 = (kc[o] != lg["corner_knn"]).any(axis=1).sum() + (ks[o] != lg["surf_knn"]).any(axis=1).sum()
+                f2 = (vc[o] != lg["corner_valid"]).sum() + (vs[o] != lg["surf_valid"]).sum()
+                if o == 0:  # identical pose -> identical queries: kNN index sets and accept flags must be bit-exact
+                    assert f1 == 0, f"frame {k} outer 0: {f1} kNN rows differ"
+                    assert f2 == 0, f"frame {k} outer 0: {f2} factor accept flags differ"
+                flips += f1 + f2
+                rows += 2 * (len(kc[o]) + len(ks[o]))
+                if f1 == 0 and f2 == 0:
+                    n = len(lg["lm"])
+                    assert np.array_equal(tr[o][:n, 9], lg["lm"][:, 9]), f"frame {k} outer {o}: LM control flow {tr[o][:n, 9]} vs {lg['lm'][:, 9]}"
+                    assert np.allclose(tr[o][:n, :7], lg["lm"][:, :7], atol=1e-7, rtol=0)
+                    assert np.allclose(tr[o][:n, 7], lg["lm"][:, 7], rtol=1e-7, atol=1e-12)
+        assert np.linalg.norm(pose_g[4:] - pose_o[4:]) < POS_TOL and rot_err(pose_g[:4], pose_o[:4]) < ROT_TOL, (k, pose_g, pose_o)
+        corr_g = lvo.get_map_correction(0)
+        corr_prev = corr_o
+        assert np.linalg.norm(corr_g[4:] - corr_o[4:]) < POS_TOL and rot_err(corr_g[:4], corr_o[:4]) < ROT_TOL
+        # map after insertion + per-cube re-filter: same cube occupancy; coordinates equal up to the pose difference
+        for which in (0, 1):
+            pg, cg = lvo.map_export(0, which)
+            po, co = O.map_export(which)
+            assert len(pg) == len(po) or abs(len(pg) - len(po)) <= 3, (k, which, len(pg), len(po))
+            if len(pg) == len(po):
+                assert np.array_equal(cg, co)
+                assert np.abs(pg[:, :3] - po[:, :3]).max() < 1e-3
+        assert (s.map_corner_total, s.map_surf_total) == (len(lvo.map_export(0, 0)[0]), len(lvo.map_export(0, 1)[0]))
+        reg_o = info["registered"]
+        assert reg_g.shape == reg_o.shape and np.abs(reg_g - reg_o).max() < 1e-3
+    assert flips <= 0.002 * max(rows, 1), f"{flips} of {rows} kNN / accept rows differ"
+    lvo.close()
+
+
+def test_full_pipeline_batch_two_lanes(lvo_mod, synth):
+    """lvo_step_batch (extract -> scan-to-scan -> scan-to-map on device, 2 lanes) vs two oracle pipelines."""
+    L = lvo_mod
+    lvo = L.Lvo(lanes=2, max_map_corner=1 << 18, max_map_surf=1 << 19)
+    Os = [Oracle(), Oracle()]
+    seqs = [0, 3]
+    for k in range(8):
+        sweeps = [synth.sweep(64, s, k)[0] for s in seqs]
+        st, odo_g, map_g = lvo.step_batch(sweeps)
+        for l in range(2):
+            st_o, odo_o, map_o = Os[l].step(sweeps[l])
+            assert np.linalg.norm(odo_g[l][4:] - odo_o[4:]) < POS_TOL and rot_err(odo_g[l][:4], odo_o[:4]) < ROT_TOL, (k, l, odo_g[l], odo_o)
+            assert np.linalg.norm(map_g[l][4:] - map_o[4:]) < POS_TOL and rot_err(map_g[l][:4], map_o[:4]) < ROT_TOL, (k, l, map_g[l], map_o)
+            s = lvo.stats(l)
+            info = Os[l].mapping_info()["info"]
+            assert abs(s.map_corner_total - info[6]) <= 5 and abs(s.map_surf_total - info[7]) <= 5
+    lvo.close()
+
+
+def test_lanes_are_bitwise_reproducible(lvo_mod, synth):
+    """The same sequence in two lanes (and in a 1-lane context) gives bitwise identical poses: deterministic reductions."""
+    L = lvo_mod
+    a = L.Lvo(lanes=2, max_map_corner=1 << 18, max_map_surf=1 << 19)
+    b = L.Lvo(lanes=1, max_map_corner=1 << 18, max_map_surf=1 << 19)
+    for k in range(5):
+        sw = synth.sweep(64, 2, k)[0]
+        _, oa, ma = a.step_batch([sw, sw])
+        _, ob, mb = b.step_batch([sw])
+        assert np.array_equal(oa[0], oa[1]) and np.array_equal(ma[0], ma[1])
+        assert np.array_equal(oa[0], ob[0]) and np.array_equal(ma[0], mb[0])
+    a.close(); b.close()
+
+
+def test_map_too_small_warning(lvo_mod, synth):
+    L = lvo_mod
+    lvo = L.Lvo(max_map_corner=1 << 18, max_map_surf=1 << 19)
+    O = Oracle()
+    f = O.extract(synth.sweep(64, 0, 0)[0])
+    ident = np.array([0, 0, 0, 1, 0, 0, 0], float)
+    st_o, pose_o, _ = O.mapping(f["less_sharp"], f["less_flat"], None, ident)
+    st_g, pose_g, _ = lvo.scan_to_map(f["less_sharp"], f["less_flat"], None, ident)
+    assert st_o == 3 and st_g == L.LVO_W_MAP_TOO_SMALL and np.array_equal(pose_g, pose_o)
+    for which in (0, 1):  # the map is still updated (laserMapping.cpp:737-801)
+        pg, cg = lvo.map_export(0, which)
+        po, co = O.map_export(which)
+        assert np.array_equal(cg, co) and np.array_equal(_bits(pg), _bits(po))
+    lvo.close()
