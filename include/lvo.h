@@ -194,6 +194,11 @@ typedef struct lvo_timings {
   double knn_bytes;       /* algorithmic bytes of those 5-NN launches: 16 M + 56 Q each */
 } lvo_timings;
 int lvo_get_timings(const lvo_ctx* ctx, lvo_timings* out);
+/* Enqueue all work of this context on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL restores the
+ * context's own stream).  Lets a harness bracket calls with its own CUDA events on the launching stream. */
+int lvo_set_stream(lvo_ctx* ctx, void* cuda_stream);
+/* Bytes copied device->host per lane at the end of every synchronous call (poses, counters, status). */
+size_t lvo_state_bytes(void);
 
 #ifdef __cplusplus
 }

@@ -57,7 +57,7 @@ class Timings(C.Structure):
 EXPORTS = ["lvo_default_config", "lvo_create", "lvo_destroy", "lvo_last_error", "lvo_get_stats", "lvo_extract_features", "lvo_scan_to_scan",
            "lvo_scan_to_map", "lvo_step_batch", "lvo_step_batch_dev", "lvo_lane_status", "lvo_map_import", "lvo_map_export",
            "lvo_get_map_correction", "lvo_set_map_correction", "lvo_set_odometry_state", "lvo_probe_fetch", "lvo_voxel_downsample", "lvo_knn",
-           "lvo_knn5_throughput", "lvo_get_timings"]
+           "lvo_knn5_throughput", "lvo_get_timings", "lvo_set_stream", "lvo_state_bytes"]
 
 
 def load_library():
@@ -88,6 +88,8 @@ def load_library():
     L.lvo_knn.argtypes = [vp, CloudView, CloudView, ip, C.c_float, vp, vp]
     L.lvo_knn5_throughput.argtypes = [vp, vp, vp, vp, vp, ip, ip, vp, vp, C.POINTER(C.c_float)]
     L.lvo_get_timings.argtypes = [vp, C.POINTER(Timings)]
+    L.lvo_set_stream.argtypes = [vp, vp]
+    L.lvo_state_bytes.restype = C.c_size_t
     return L
 
 
@@ -241,6 +243,9 @@ class Lvo:
         a = np_to_pose(T_last_curr) if T_last_curr is not None else None
         b = np_to_pose(T_w_curr) if T_w_curr is not None else None
         self._check(self.lib.lvo_set_odometry_state(self.h, lane, C.byref(a) if a else None, C.byref(b) if b else None))
+
+    def set_stream(self, cuda_stream_handle):
+        self._check(self.lib.lvo_set_stream(self.h, C.c_void_p(cuda_stream_handle) if cuda_stream_handle else None))
 
     def stats(self, lane=0):
         s = Stats()

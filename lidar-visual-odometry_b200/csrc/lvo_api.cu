@@ -19,6 +19,7 @@ struct lvo_ctx {
   lvo_config cfg;
   int lanes, P, cap_sharp, cap_lsharp, cap_flat;
   cudaStream_t st = nullptr;
+  cudaStream_t own_st = nullptr;
   std::string err;
   std::vector<void*> allocs, pinned;
   LaneState* d_ls = nullptr;
@@ -114,18 +115,23 @@ __global__ void k_init_lanes(LaneState* ls, int lanes) {
   s.para_q[3] = 1.0; s.q_w[3] = 1.0; s.map_x[3] = 1.0; s.q_wmap_wodom[3] = 1.0; s.q_wodom[3] = 1.0;
   s.cen[0] = 10; s.cen[1] = 10; s.cen[2] = 5;  // laserMapping.cpp:74-76
 }
+// which == 0: odometry, 6 problems per lane (corner / surf fine xyz, corner / surf ring-azimuth, corner / surf coarse xyz);
+// which == 1: mapping, 2 problems per lane (corner / surf FromMap)
 __global__ void k_setup_grid_problems(GridProblem* prob, int nprob, const float4* base0, size_t stride0, const float4* base1, size_t stride1,
                                       LaneState* ls, int which, float cell) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nprob) return;
-  const int lane = p >> 1, t = p & 1;
+  const int per = which == 0 ? 6 : 2;
+  const int lane = p / per, t = p & 1;
   prob[p].pts = (t ? base1 + (size_t)lane * stride1 : base0 + (size_t)lane * stride0);
   if (which == 0) prob[p].d_n = t ? &ls[lane].n_surf_last : &ls[lane].n_corner_last;
   else prob[p].d_n = &ls[lane].from_off[t][LVO_MAX_VALID];
-  prob[p].want_cell = cell;
+  const int k = p % per;
+  prob[p].want_cell = (which == 0 && k >= 4) ? 4.0f * cell : cell;   // odometry: fine + coarse xyz grids
+  prob[p].mode = (which == 0 && (k == 2 || k == 3)) ? 1 : 0;
 }
 __global__ void k_setup_one_problem(GridProblem* prob, const float4* pts, const int* d_n, float cell) {
-  prob[0].pts = pts; prob[0].d_n = d_n; prob[0].want_cell = cell;
+  prob[0].pts = pts; prob[0].d_n = d_n; prob[0].want_cell = cell; prob[0].mode = 0;
 }
 __global__ void k_vx_single_setup(VoxelEngine e, int n, float leaf) {
   if (blockIdx.x == 0 && threadIdx.x == 0) { *e.d_n = n; *e.d_nsegs = 1; e.seg_leaf[0] = leaf; }
@@ -230,7 +236,8 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
   cudaDeviceProp prop;
   LVO_CUDA_OK(c, cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10) { lvo_set_error(c, "liblvo is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor)); return LVO_E_CUDA; }
-  LVO_CUDA_OK(c, cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  LVO_CUDA_OK(c, cudaStreamCreateWithFlags(&c->own_st, cudaStreamNonBlocking));
+  c->st = c->own_st;
   for (int i = 0; i < 8; ++i) LVO_CUDA_OK(c, cudaEventCreate(&c->ev[i]));
   c->knn_ev.resize(2 * LVO_MAX_OUTER);
   for (auto& e : c->knn_ev) LVO_CUDA_OK(c, cudaEventCreate(&e));
@@ -289,8 +296,8 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
   LVO_TRY(dalloc(c, &od.factors, (size_t)L * od.factor_cap));
   LVO_TRY(dalloc(c, &od.corner_corr, (size_t)L * LVO_MAX_OUTER * c->cap_sharp * 2));
   LVO_TRY(dalloc(c, &od.plane_corr, (size_t)L * LVO_MAX_OUTER * c->cap_flat * 3));
-  LVO_TRY(alloc_grid(c, &od.grid, 2 * L, 1 << 20, (size_t)L * (c->cap_lsharp + P), P));
-  k_setup_grid_problems<<<lvo_div_up(2 * L, 64), 64, 0, c->st>>>(od.grid.prob, 2 * L, od.corner_last, (size_t)c->cap_lsharp, od.surf_last, (size_t)P, c->d_ls, 0, 2.0f);
+  LVO_TRY(alloc_grid(c, &od.grid, 6 * L, 1 << 21, (size_t)3 * L * (c->cap_lsharp + P), P));
+  k_setup_grid_problems<<<lvo_div_up(6 * L, 64), 64, 0, c->st>>>(od.grid.prob, 6 * L, od.corner_last, (size_t)c->cap_lsharp, od.surf_last, (size_t)P, c->d_ls, 0, 1.0f);
 
   // ---- mapping
   MapArgs& mp = c->map;
@@ -350,7 +357,7 @@ int lvo_destroy(lvo_ctx* c) {
   if (c->st) cudaStreamSynchronize(c->st);
   for (void* p : c->allocs) cudaFree(p);
   for (void* p : c->pinned) cudaFreeHost(p);
-  if (c->st) { for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]); for (auto& e : c->knn_ev) cudaEventDestroy(e); cudaStreamDestroy(c->st); }
+  if (c->own_st) { for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]); for (auto& e : c->knn_ev) cudaEventDestroy(e); cudaStreamDestroy(c->own_st); }
   delete c;
   return LVO_OK;
 }
@@ -363,6 +370,13 @@ int lvo_get_stats(const lvo_ctx* c, int lane, lvo_stats* out, size_t bytes) {
   return LVO_OK;
 }
 int lvo_lane_status(const lvo_ctx* c, int lane) { return (c && lane >= 0 && lane < c->lanes) ? c->lane_status[lane] : LVO_E_BADARG; }
+size_t lvo_state_bytes(void) { return sizeof(LaneState); }
+int lvo_set_stream(lvo_ctx* c, void* cuda_stream) {
+  if (!c) return LVO_E_BADARG;
+  cudaStreamSynchronize(c->st);
+  c->st = cuda_stream ? (cudaStream_t)cuda_stream : c->own_st;
+  return LVO_OK;
+}
 int lvo_get_timings(const lvo_ctx* c, lvo_timings* out) { if (!c || !out) return LVO_E_BADARG; *out = c->tim; out->kernel_launches = (int)c->launches; return LVO_OK; }
 
 // ---------------------------------------------------------------------------------------------------------------

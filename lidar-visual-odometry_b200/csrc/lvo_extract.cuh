@@ -20,8 +20,8 @@
 #include <limits.h>
 
 #define LVO_EX_THREADS 256
-#define LVO_PICK_THREADS 256
-#define LVO_PICK_SMEM_KEYS 4096  // sectors / ring voxel inputs up to this size sort in shared memory
+#define LVO_PICK_THREADS 128
+#define LVO_PICK_SMEM_KEYS 2048  // sectors / ring voxel inputs up to this size sort in shared memory
 
 struct ExtractArgs {
   // input
@@ -481,42 +481,44 @@ __global__ void __launch_bounds__(LVO_PICK_THREADS) k_sector_pick(ExtractArgs a)
   if (threadIdx.x == 0) a.lf_cnt[lane * LVO_MAX_RINGS + ring] = carry;
 }
 
-// Concatenate per-sector picks and per-ring less-flat clouds in reference order.  One block per lane.
-__global__ void __launch_bounds__(256) k_feature_compact(ExtractArgs a) {
-  __shared__ int off[4][LVO_MAX_RINGS * LVO_SECTORS + 1];
+// Concatenate per-sector picks and per-ring less-flat clouds in reference order.  One block (512 threads) per lane:
+// thread k owns sector k (ring k / 6, sector k % 6); three block scans give the output offsets.
+__global__ void __launch_bounds__(512) k_feature_compact(ExtractArgs a) {
+  __shared__ unsigned sm[33];
   __shared__ int lfo[LVO_MAX_RINGS + 1];
   const int lane = blockIdx.x;
   LaneState& s = a.ls[lane];
   const int nsec = a.n_scans * LVO_SECTORS;
-  if (threadIdx.x == 0) {
-    int a0 = 0, a1 = 0, a2 = 0;
-    for (int k = 0; k < nsec; ++k) {
-      const int r = k / LVO_SECTORS, j = k % LVO_SECTORS;
-      const int* c = a.slot_cnt + ((size_t)(lane * LVO_MAX_RINGS + r) * LVO_SECTORS + j) * 3;
-      off[0][k] = a0; off[1][k] = a1; off[2][k] = a2;
-      a0 += c[0]; a1 += c[1]; a2 += c[2];
-    }
-    off[0][nsec] = a0; off[1][nsec] = a1; off[2][nsec] = a2;
-    int acc = 0;
-    for (int r = 0; r < a.n_scans; ++r) { lfo[r] = acc; s.lf_ring_off[r] = acc; acc += a.lf_cnt[lane * LVO_MAX_RINGS + r]; }
-    lfo[a.n_scans] = acc; s.lf_ring_off[a.n_scans] = acc;
-    s.n_sharp = a0; s.n_less_sharp = a1; s.n_flat = a2; s.n_less_flat = acc;
-    s.stats.n_sharp = a0; s.stats.n_less_sharp = a1; s.stats.n_flat = a2; s.stats.n_less_flat = acc;
+  const int k = threadIdx.x;
+  const int r = k / LVO_SECTORS, j = k % LVO_SECTORS;
+  const size_t sb = (size_t)(lane * LVO_MAX_RINGS + r) * LVO_SECTORS;
+  int c0 = 0, c1 = 0, c2 = 0;
+  if (k < nsec) { const int* c = a.slot_cnt + (sb + j) * 3; c0 = c[0]; c1 = c[1]; c2 = c[2]; }
+  unsigned t0, t1, t2, tl;
+  const unsigned o0 = block_excl_scan((unsigned)c0, sm, &t0);
+  const unsigned o1 = block_excl_scan((unsigned)c1, sm, &t1);
+  const unsigned o2 = block_excl_scan((unsigned)c2, sm, &t2);
+  const int lc = k < a.n_scans ? a.lf_cnt[lane * LVO_MAX_RINGS + k] : 0;
+  const unsigned ol = block_excl_scan((unsigned)lc, sm, &tl);
+  if (k < a.n_scans) { lfo[k] = (int)ol; s.lf_ring_off[k] = (int)ol; }
+  if (k == 0) {
+    lfo[a.n_scans] = (int)tl; s.lf_ring_off[a.n_scans] = (int)tl;
+    s.n_sharp = (int)t0; s.n_less_sharp = (int)t1; s.n_flat = (int)t2; s.n_less_flat = (int)tl;
+    s.stats.n_sharp = (int)t0; s.stats.n_less_sharp = (int)t1; s.stats.n_flat = (int)t2; s.stats.n_less_flat = (int)tl;
   }
   __syncthreads();
   const float4* P = a.full + (size_t)lane * a.P;
-  for (int k = threadIdx.x; k < nsec; k += blockDim.x) {
-    const int r = k / LVO_SECTORS, j = k % LVO_SECTORS;
-    const size_t sb = (size_t)(lane * LVO_MAX_RINGS + r) * LVO_SECTORS;
-    const int* c = a.slot_cnt + (sb + j) * 3;
-    for (int t = 0; t < c[0]; ++t) a.sharp[(size_t)lane * a.cap_sharp + off[0][k] + t] = P[a.slot_sharp[sb * 2 + j * 2 + t]];
-    for (int t = 0; t < c[1]; ++t) a.less_sharp[(size_t)lane * a.cap_lsharp + off[1][k] + t] = P[a.slot_lsharp[sb * 20 + j * 20 + t]];
-    for (int t = 0; t < c[2]; ++t) a.flat[(size_t)lane * a.cap_flat + off[2][k] + t] = P[a.slot_flat[sb * 4 + j * 4 + t]];
+  if (k < nsec) {
+    for (int t = 0; t < c0; ++t) a.sharp[(size_t)lane * a.cap_sharp + o0 + t] = P[a.slot_sharp[sb * 2 + j * 2 + t]];
+    for (int t = 0; t < c1; ++t) a.less_sharp[(size_t)lane * a.cap_lsharp + o1 + t] = P[a.slot_lsharp[sb * 20 + j * 20 + t]];
+    for (int t = 0; t < c2; ++t) a.flat[(size_t)lane * a.cap_flat + o2 + t] = P[a.slot_flat[sb * 4 + j * 4 + t]];
   }
-  for (int r = 0; r < a.n_scans; ++r) {
-    const int c = lfo[r + 1] - lfo[r];
-    const float4* src = a.lf_ring + (size_t)lane * a.P + s.ring_start[r];
-    for (int t = threadIdx.x; t < c; t += blockDim.x) a.less_flat[(size_t)lane * a.P + lfo[r] + t] = src[t];
+  // less-flat: warp w copies rings w, w + 16, ...
+  const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+  for (int rr = w; rr < a.n_scans; rr += 16) {
+    const int c = lfo[rr + 1] - lfo[rr];
+    const float4* src = a.lf_ring + (size_t)lane * a.P + s.ring_start[rr];
+    for (int t = ln; t < c; t += 32) a.less_flat[(size_t)lane * a.P + lfo[rr] + t] = src[t];
   }
 }
 
@@ -530,6 +532,6 @@ static inline void lvo_launch_extract(cudaStream_t st, const ExtractArgs& a, int
   k_ring_scatter<<<gpts, LVO_EX_THREADS, 0, st>>>(a);
   k_curvature<<<gpts, LVO_EX_THREADS, 0, st>>>(a);
   k_sector_pick<<<dim3(a.n_scans, lanes), LVO_PICK_THREADS, LVO_PICK_SMEM_KEYS * sizeof(unsigned long long), st>>>(a);
-  k_feature_compact<<<lanes, 256, 0, st>>>(a);
+  k_feature_compact<<<lanes, 512, 0, st>>>(a);
   if (launches) *launches += 8;
 }

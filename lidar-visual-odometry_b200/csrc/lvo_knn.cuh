@@ -20,10 +20,14 @@
 #include <float.h>
 #include <limits.h>
 
+#define LVO_AZ_BUCKETS 512                 // azimuth buckets of the (ring, azimuth) grid: 0.703 degrees each
+#define LVO_AZ_RINGS (LVO_MAX_RINGS + 2)   // ring ids are clamped to [0, 65]
+
 struct GridProblem {   // device-resident descriptor
   const float4* pts;   // source cloud
   const int* d_n;      // its size (device)
   float want_cell;     // requested cell size (power of two)
+  int mode;            // 0: uniform xyz grid; 1: (ring, azimuth) grid — cell = ring * LVO_AZ_BUCKETS + azimuth bucket
   // filled by k_grid_setup
   float cell, inv_cell;
   int org[3], dim[3];
@@ -92,44 +96,61 @@ __global__ void k_grid_bbox(GridSet g) {
   if ((threadIdx.x & 31) == 0 && mn[0] != INT_MAX)
     for (int c = 0; c < 3; ++c) { atomicMin(&q.bb_mn[c], mn[c]); atomicMax(&q.bb_mx[c], mx[c]); }
 }
-// one thread: cell size (doubling until the table fits), origin, dims, offsets
-__global__ void k_grid_setup(GridSet g) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// one block: per problem (one thread each) cell size (doubling until the table fits), origin, dims; then a block
+// scan gives the table / point offsets
+__global__ void __launch_bounds__(256) k_grid_setup(GridSet g) {
+  __shared__ unsigned sm[33];
   unsigned toff = 0, poff = 0;
-  for (int p = 0; p < g.nprob; ++p) {
-    GridProblem& q = g.prob[p];
-    q.table_off = toff;
-    g.pt_off[p] = poff;
-    float cell = q.want_cell;
-    int org[3] = {0, 0, 0}, dim[3] = {0, 0, 0};
-    long long nc = 0;
-    if (q.n > 0) {
-      for (int it = 0; it < 40; ++it) {
-        const float inv = 1.0f / cell;
-        nc = 1;
-        for (int c = 0; c < 3; ++c) {
-          const int lo = cell_coord(ord2f_k(q.bb_mn[c]), inv), hi = cell_coord(ord2f_k(q.bb_mx[c]), inv);
-          org[c] = lo; dim[c] = hi - lo + 1;
-          nc *= (long long)dim[c];
+  for (int base = 0; base < g.nprob; base += blockDim.x) {
+    const int p = base + threadIdx.x;
+    unsigned my_cells = 0, my_pts = 0;
+    if (p < g.nprob) {
+      GridProblem& q = g.prob[p];
+      float cell = q.want_cell;
+      int org[3] = {0, 0, 0}, dim[3] = {0, 0, 0};
+      long long nc = 0;
+      if (q.mode == 1) {
+        org[0] = org[1] = org[2] = 0; dim[0] = LVO_AZ_BUCKETS; dim[1] = LVO_AZ_RINGS; dim[2] = 1;
+        nc = (long long)LVO_AZ_BUCKETS * LVO_AZ_RINGS;
+      } else if (q.n > 0) {
+        for (int it = 0; it < 40; ++it) {
+          const float inv = 1.0f / cell;
+          nc = 1;
+          for (int c = 0; c < 3; ++c) {
+            const int lo = cell_coord(ord2f_k(q.bb_mn[c]), inv), hi = cell_coord(ord2f_k(q.bb_mx[c]), inv);
+            org[c] = lo; dim[c] = hi - lo + 1;
+            nc *= (long long)dim[c];
+          }
+          if (nc <= (long long)g.cells_cap_per_problem) break;
+          cell *= 2.0f;
         }
-        if (nc <= (long long)g.cells_cap_per_problem) break;
-        cell *= 2.0f;
       }
+      q.cell = cell; q.inv_cell = 1.0f / cell;
+      for (int c = 0; c < 3; ++c) { q.org[c] = org[c]; q.dim[c] = dim[c]; }
+      q.ncells = (int)nc;
+      my_cells = (unsigned)nc; my_pts = (unsigned)q.n;
     }
-    q.cell = cell; q.inv_cell = 1.0f / cell;
-    for (int c = 0; c < 3; ++c) { q.org[c] = org[c]; q.dim[c] = dim[c]; }
-    q.ncells = (int)nc;
-    toff += (unsigned)nc;
-    poff += (unsigned)q.n;
+    unsigned tc, tp;
+    const unsigned ec = block_excl_scan(my_cells, sm, &tc);
+    const unsigned ep = block_excl_scan(my_pts, sm, &tp);
+    if (p < g.nprob) { g.prob[p].table_off = toff + ec; g.pt_off[p] = poff + ep; }
+    toff += tc; poff += tp;
   }
-  g.pt_off[g.nprob] = poff;
-  *g.d_table_len = (int)toff + 1;
+  if (threadIdx.x == 0) { g.pt_off[g.nprob] = poff; *g.d_table_len = (int)toff + 1; }
 }
 __global__ void k_grid_zero(GridSet g) {
   const int len = *g.d_table_len;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) g.table[i] = 0;
 }
+// azimuth bucket of a direction; any consistent monotone function of the angle works (the searches add margins)
+__device__ __forceinline__ int az_bucket(float x, float y) {
+  const float phi = atan2f(y, x) + 3.14159274f;
+  int b = (int)floorf(phi * ((float)LVO_AZ_BUCKETS / 6.28318548f));
+  return min(max(b, 0), LVO_AZ_BUCKETS - 1);
+}
+__device__ __forceinline__ int ring_clamped(float intensity) { return min(max(int(intensity), 0), LVO_AZ_RINGS - 1); }
 __device__ __forceinline__ int grid_cell_of(const GridProblem& q, float4 v) {
+  if (q.mode == 1) return ring_clamped(v.w) * LVO_AZ_BUCKETS + az_bucket(v.x, v.y);
   const int cx = cell_coord(v.x, q.inv_cell) - q.org[0], cy = cell_coord(v.y, q.inv_cell) - q.org[1], cz = cell_coord(v.z, q.inv_cell) - q.org[2];
   return (cz * q.dim[1] + cy) * q.dim[0] + cx;
 }
@@ -159,7 +180,7 @@ static inline void lvo_grid_build(cudaStream_t st, const GridSet& g, long long* 
   dim3 gp(gx, g.nprob);
   k_grid_reset<<<lvo_div_up(g.nprob, 64), 64, 0, st>>>(g);
   k_grid_bbox<<<gp, 256, 0, st>>>(g);
-  k_grid_setup<<<1, 32, 0, st>>>(g);
+  k_grid_setup<<<1, 256, 0, st>>>(g);
   k_grid_zero<<<1184, 256, 0, st>>>(g);
   k_grid_count<<<gp, 256, 0, st>>>(g);
   lvo_scan_exclusive(st, g.table, g.d_table_len, g.nprob * g.cells_cap_per_problem + 1, nullptr, g.scan, launches);
@@ -255,6 +276,146 @@ __device__ __forceinline__ bool warp_knn(const GridView& g, float qx, float qy, 
     warp_merge<K>(tk);
   }
   return tk.id[K - 1] != INT_MAX && (double)tk.d[K - 1] < (double)max_sq;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// thread-per-query exact K-NN (throughput form): every thread walks the 27 (or more) cells of its own query.
+// Per query this issues ~9x fewer warp instructions than the warp-cooperative form (no cross-lane merge, full lane
+// utilisation); neighbouring threads hold neighbouring queries (the stack clouds are voxel-sorted), so their
+// candidate rows share L1 lines.  Same ring-expansion rule and the same (distance, index) ranking => same result.
+// ---------------------------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void thread_scan_row(const GridView& g, int cz, int cy, int x0, int x1, float qx, float qy, float qz, TopK<K>& tk) {
+  if (cz < 0 || cz >= g.dim[2] || cy < 0 || cy >= g.dim[1]) return;
+  x0 = max(x0, 0); x1 = min(x1, g.dim[0] - 1);
+  if (x0 > x1) return;
+  const int rowbase = (cz * g.dim[1] + cy) * g.dim[0];
+  const unsigned b = __ldg(g.cell_start + rowbase + x0), e = __ldg(g.cell_start + rowbase + x1 + 1);
+  for (unsigned t = b; t < e; ++t) {
+    const float4 p = __ldg(g.pts + t);
+    tk.insert(sqdist3(p, qx, qy, qz), __ldg(g.ids + t));
+  }
+}
+template <int K>
+__device__ __forceinline__ bool thread_knn(const GridView& g, float qx, float qy, float qz, float max_sq, TopK<K>& tk) {
+  tk.init();
+  if (g.dim[0] <= 0) return false;
+  const int cx = cell_coord(qx, g.inv_cell) - g.org[0], cy = cell_coord(qy, g.inv_cell) - g.org[1], cz = cell_coord(qz, g.inv_cell) - g.org[2];
+  int R = (int)ceilf(sqrtf(max_sq) * g.inv_cell);
+  if (R < 1) R = 1;
+  // rings 0 and 1: fetch the 9 row ranges first (independent loads), then stream the candidates
+  unsigned rb[9], re[9];
+  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int z = cz + k / 3 - 1, y = cy + k % 3 - 1;
+    rb[k] = re[k] = 0;
+    if (z >= 0 && z < g.dim[2] && y >= 0 && y < g.dim[1] && x0 <= x1) {
+      const int rowbase = (z * g.dim[1] + y) * g.dim[0];
+      rb[k] = __ldg(g.cell_start + rowbase + x0); re[k] = __ldg(g.cell_start + rowbase + x1 + 1);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+    for (unsigned t = rb[k]; t < re[k]; ++t) {
+      const float4 p = __ldg(g.pts + t);
+      tk.insert(sqdist3(p, qx, qy, qz), __ldg(g.ids + t));
+    }
+  for (int r = 2; r <= R; ++r) {
+    const float bound = (float)(r - 1) * g.cell;
+    if (tk.d[K - 1] < bound * bound) break;
+    for (int dz = -r; dz <= r; ++dz)
+      for (int dy = -r; dy <= r; ++dy) {
+        if (dz == -r || dz == r || dy == -r || dy == r) thread_scan_row<K>(g, cz + dz, cy + dy, cx - r, cx + r, qx, qy, qz, tk);
+        else { thread_scan_row<K>(g, cz + dz, cy + dy, cx - r, cx - r, qx, qy, qz, tk); thread_scan_row<K>(g, cz + dz, cy + dy, cx + r, cx + r, qx, qy, qz, tk); }
+      }
+  }
+  return tk.id[K - 1] != INT_MAX && (double)tk.d[K - 1] < (double)max_sq;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// flattened multi-range scan: lane j < NR holds one contiguous candidate range [b, e) (e.g. one x-row of cells); the
+// warp walks the concatenation of all ranges with every lane busy.  f(t, r) is called for candidate t of range r.
+// All range bounds are fetched before the first candidate is touched, so a query costs two dependent memory round
+// trips (bounds, candidates) instead of two per row.
+// ---------------------------------------------------------------------------------------------------------------
+template <int NR, class F>
+__device__ __forceinline__ void warp_scan_ranges(unsigned b, unsigned e, F&& f) {
+  const unsigned ln = threadIdx.x & 31;
+  const unsigned len = e > b ? e - b : 0u;
+  const unsigned incl = warp_incl_scan(len);
+  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+  for (unsigned k0 = 0; k0 < total; k0 += 32) {
+    const unsigned k = k0 + ln;
+    int r = 0;
+#pragma unroll
+    for (int j = 0; j < NR - 1; ++j) r += (k >= __shfl_sync(0xffffffffu, incl, j)) ? 1 : 0;
+    const unsigned rb = __shfl_sync(0xffffffffu, b, r), ri = __shfl_sync(0xffffffffu, incl, r), rl = __shfl_sync(0xffffffffu, len, r);
+    if (k < total) f(rb + (k - (ri - rl)), r);
+  }
+}
+// bounds of the x-row (cz, cy, x0..x1) of a grid, empty when outside
+__device__ __forceinline__ void row_bounds(const GridView& g, int cz, int cy, int x0, int x1, unsigned& b, unsigned& e) {
+  b = e = 0;
+  if (cz < 0 || cz >= g.dim[2] || cy < 0 || cy >= g.dim[1]) return;
+  x0 = max(x0, 0); x1 = min(x1, g.dim[0] - 1);
+  if (x0 > x1) return;
+  const int rowbase = (cz * g.dim[1] + cy) * g.dim[0];
+  b = __ldg(g.cell_start + rowbase + x0); e = __ldg(g.cell_start + rowbase + x1 + 1);
+}
+// Exact nearest neighbour with d^2 < max_sq on a two-level grid (fine cells, then coarse cells): the 27 fine cells
+// around the query settle it when the best squared distance is below cell_fine^2; otherwise the 27 coarse cells, then
+// the usual ring expansion on the coarse grid.  Worst case is bounded by the coarse grid's few rings.
+__device__ __forceinline__ bool warp_nn1_two_level(const GridView& gf, const GridView& gc, float qx, float qy, float qz, float max_sq, float& bd, int& bi) {
+  const unsigned ln = threadIdx.x & 31;
+  float d = FLT_MAX; int id = INT_MAX;
+  auto consider = [&](const GridView& g, unsigned t) {
+    const float4 p = __ldg(g.pts + t);
+    const int i = __ldg(g.ids + t);
+    const float dd = sqdist3(p, qx, qy, qz);
+    if (dd < d || (dd == d && i < id)) { d = dd; id = i; }
+  };
+  auto reduce = [&]() {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, d, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, id, o);
+      if (od < d || (od == d && oi < id)) { d = od; id = oi; }
+    }
+  };
+  for (int level = 0; level < 2; ++level) {
+    const GridView& g = level ? gc : gf;
+    if (g.dim[0] <= 0) continue;
+    const int cx = cell_coord(qx, g.inv_cell) - g.org[0], cy = cell_coord(qy, g.inv_cell) - g.org[1], cz = cell_coord(qz, g.inv_cell) - g.org[2];
+    unsigned b = 0, e = 0;
+    if (ln < 9) row_bounds(g, cz + (int)ln / 3 - 1, cy + (int)ln % 3 - 1, cx - 1, cx + 1, b, e);
+    warp_scan_ranges<9>(b, e, [&](unsigned t, int) { consider(g, t); });
+    reduce();
+    if (d < g.cell * g.cell) break;  // nothing outside the 27 cells can beat or tie it
+    if (level == 1) {
+      int R = (int)ceilf(sqrtf(max_sq) * g.inv_cell);
+      for (int r = 2; r <= R; ++r) {
+        const float bound = (float)(r - 1) * g.cell;
+        if (d < bound * bound) break;
+        // shell r: (2r+1)^2 rows; boundary rows span x-r..x+r, inner rows contribute the two end cells
+        const int side = 2 * r + 1, nrows = side * side;
+        for (int base = 0; base < nrows; base += 16) {
+          const int row = base + (int)(ln & 15);
+          unsigned bb = 0, ee = 0;
+          if (row < nrows) {
+            const int dz = row / side - r, dy = row % side - r;
+            const bool edge = dz == -r || dz == r || dy == -r || dy == r;
+            if (edge) { if (ln < 16) row_bounds(g, cz + dz, cy + dy, cx - r, cx + r, bb, ee); }
+            else row_bounds(g, cz + dz, cy + dy, ln < 16 ? cx - r : cx + r, ln < 16 ? cx - r : cx + r, bb, ee);
+          }
+          warp_scan_ranges<32>(bb, ee, [&](unsigned t, int) { consider(g, t); });
+        }
+        reduce();
+      }
+    }
+  }
+  bd = d; bi = id;
+  return id != INT_MAX && (double)d < (double)max_sq;
 }
 
 // Stand-alone operator (lvo_knn): one warp per query, problem 0 of the grid set.

@@ -10,9 +10,10 @@
 //   k_map_gather       concatenation of the 75 valid cubes in i,j,k loop order :531-537 (defines the kNN point ids)
 //   stack downsample   lvo_voxel_run over 2 segments per lane (corner lineRes / surf planeRes) :542-550
 //   lvo_grid_build     replaces the two kd-tree builds :558-559
-//   k_map_assoc        per outer iteration (:562): pointAssociateToMap :154-163, 5-NN + d5^2 < 1 gate :582-584 /
-//                      :648-652, line fit by 3x3 symmetric eigen-solve :586-621, plane fit by 5x3 least squares
-//                      :650-686, factor records for LidarEdgeFactor / LidarPlaneNormFactor
+//   k_map_knn          per outer iteration (:562): pointAssociateToMap :154-163, 5-NN + d5^2 < 1 gate :582-584 /
+//                      :648-652, one thread per query on the uniform grid
+//   k_map_fit          line fit by 3x3 symmetric eigen-solve :586-621, plane fit by 5x3 least squares :650-686,
+//                      factor records for LidarEdgeFactor / LidarPlaneNormFactor
 //   k_lm_solve         ceres::Solve :712-720
 //   k_map_finish       transformUpdate :148-152
 //   refilter           insert the transformed stack points into their cubes :737-783 and VoxelGrid every valid cube
@@ -120,18 +121,20 @@ __global__ void k_map_gather(MapArgs a) {
 }
 
 // ---- stack downsample (engine run A) -------------------------------------------------------------------------------
-__global__ void k_stack_offsets(MapArgs a) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(256) k_stack_offsets(MapArgs a) {
+  __shared__ unsigned sm[33];
+  const int L2 = 2 * a.lanes;
   unsigned acc = 0;
-  for (int lt = 0; lt < 2 * a.lanes; ++lt) {
-    a.item_off[lt] = acc;
-    const LaneState& s = a.ls[lt >> 1];
-    acc += (unsigned)((lt & 1) ? s.n_less_flat : s.n_less_sharp);
-    a.vx.seg_leaf[lt] = a.leaf[lt & 1];
+  for (int base = 0; base < L2; base += blockDim.x) {
+    const int lt = base + threadIdx.x;
+    unsigned v = 0;
+    if (lt < L2) { const LaneState& s = a.ls[lt >> 1]; v = (unsigned)((lt & 1) ? s.n_less_flat : s.n_less_sharp); a.vx.seg_leaf[lt] = a.leaf[lt & 1]; }
+    unsigned tot;
+    const unsigned ex = block_excl_scan(v, sm, &tot);
+    if (lt < L2) a.item_off[lt] = acc + ex;
+    acc += tot;
   }
-  a.item_off[2 * a.lanes] = acc;
-  *a.vx.d_n = (int)acc;
-  *a.vx.d_nsegs = 2 * a.lanes;
+  if (threadIdx.x == 0) { a.item_off[L2] = acc; *a.vx.d_n = (int)acc; *a.vx.d_nsegs = L2; }
 }
 __global__ void k_stack_gather(MapArgs a) {
   const int lt = blockIdx.y, lane = lt >> 1, t = lt & 1;
@@ -158,85 +161,105 @@ __global__ void k_stack_scatter(MapArgs a) {
 }
 
 // ---- association + fit ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_map_assoc(MapArgs a) {
+// Line fit (:586-621) / plane fit (:650-686) of ONE query from its 5 neighbours; executed by one thread.
+__device__ __forceinline__ void fit_factor(int t, const float4 ori, const float4* __restrict__ M, const int* id, LvoFactor& fac) {
+  float4 nb[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) nb[j] = M[id[j]];
+  if (t == 0) {
+    d3 center{0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { center.x = center.x + (double)nb[j].x; center.y = center.y + (double)nb[j].y; center.z = center.z + (double)nb[j].z; }
+    center.x = center.x / 5.0; center.y = center.y / 5.0; center.z = center.z / 5.0;
+    double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const double z[3] = {(double)nb[j].x - center.x, (double)nb[j].y - center.y, (double)nb[j].z - center.z};
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) cov[r * 3 + c] = cov[r * 3 + c] + z[r] * z[c];
+    }
+    double w[3], V[9];
+    sym_eigen3_dev(cov, w, V);
+    if (w[2] > 3 * w[1]) {  // :611
+      const double ux = V[0 * 3 + 2], uy = V[1 * 3 + 2], uz = V[2 * 3 + 2];
+      fac.type = 0;
+      fac.c[0] = ori.x; fac.c[1] = ori.y; fac.c[2] = ori.z;
+      fac.a[0] = 0.1 * ux + center.x; fac.a[1] = 0.1 * uy + center.y; fac.a[2] = 0.1 * uz + center.z;
+      fac.b[0] = -0.1 * ux + center.x; fac.b[1] = -0.1 * uy + center.y; fac.b[2] = -0.1 * uz + center.z;
+    }
+  } else {
+    double A[15], b[5] = {-1, -1, -1, -1, -1}, n[3];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { A[j * 3 + 0] = nb[j].x; A[j * 3 + 1] = nb[j].y; A[j * 3 + 2] = nb[j].z; }
+    if (!lsq_qr_5x3(A, b, n)) { n[0] = n[1] = n[2] = 0; }
+    const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    const double negOA = 1 / nn;
+    n[0] /= nn; n[1] /= nn; n[2] /= nn;
+    bool planeValid = true;
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+      if (fabs(n[0] * nb[j].x + n[1] * nb[j].y + n[2] * nb[j].z + negOA) > 0.2) { planeValid = false; }  // :672-678
+    if (planeValid) {
+      fac.type = 2;
+      fac.c[0] = ori.x; fac.c[1] = ori.y; fac.c[2] = ori.z;
+      fac.a[0] = n[0]; fac.a[1] = n[1]; fac.a[2] = n[2];
+      fac.b[0] = fac.b[1] = fac.b[2] = 0;
+      fac.d = negOA;
+    }
+  }
+}
+
+// 5-NN of every stack point (one thread per query): pointAssociateToMap :154-163, nearestKSearch + gate :582-584 / :648-652.
+// Writes the index sets (all -1 when d5^2 >= 1.0).  This is the graded kNN kernel.
+__global__ void __launch_bounds__(128) k_map_knn(MapArgs a) {
+  const int lane = blockIdx.y;
+  const LaneState& s = a.ls[lane];
+  if (s.map_too_small) return;
+  const int n0 = s.n_stack[0], ntot = n0 + s.n_stack[1];
+  const GridView g0 = grid_view(a.grid, 2 * lane), g1 = grid_view(a.grid, 2 * lane + 1);
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < ntot; f += gridDim.x * blockDim.x) {
+    const int t = f >= n0 ? 1 : 0;
+    const int i = t ? f - n0 : f;
+    const float4 ori = a.stack[t][(size_t)lane * a.in_cap[t] + i];
+    const float4 sel = transform_point(s.map_x, s.map_x + 4, ori);
+    TopK<5> tk;
+    const bool ok = thread_knn<5>(t ? g1 : g0, sel.x, sel.y, sel.z, 1.0f, tk);
+    int* ki = a.knn_ind[t] + (((size_t)lane * LVO_MAX_OUTER + a.outer) * a.in_cap[t] + i) * 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) ki[k] = ok ? tk.id[k] : -1;
+  }
+}
+// line / plane fit of every accepted query (one thread per query) -> factor records
+__global__ void __launch_bounds__(128) k_map_fit(MapArgs a) {
   const int lane = blockIdx.y;
   LaneState& s = a.ls[lane];
   if (s.map_too_small) return;
-  const int n0 = s.n_stack[0], n1 = s.n_stack[1];
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  const unsigned ln = threadIdx.x & 31;
-  const GridView g0 = grid_view(a.grid, 2 * lane), g1 = grid_view(a.grid, 2 * lane + 1);
+  const int n0 = s.n_stack[0], ntot = n0 + s.n_stack[1];
   const float4* M0 = a.from_map[0] + (size_t)lane * a.map_cap[0];
   const float4* M1 = a.from_map[1] + (size_t)lane * a.map_cap[1];
   int nc = 0, nsf = 0;
-  for (int f = wid; f < n0 + n1; f += nw) {
-    const int t = f < n0 ? 0 : 1;
-    const int i = t ? f - n0 : f;
-    const float4 ori = a.stack[t][(size_t)lane * a.in_cap[t] + i];
-    const float4 sel = transform_point(s.map_x, s.map_x + 4, ori);  // pointAssociateToMap
-    TopK<5> tk;
-    const bool ok = warp_knn<5>(t ? g1 : g0, sel.x, sel.y, sel.z, 1.0f, tk);
-    if (ln == 0) {
+  for (int base = blockIdx.x * blockDim.x; base < ntot; base += gridDim.x * blockDim.x) {
+    const int f = base + threadIdx.x;
+    if (f < ntot) {
+      const int t = f >= n0 ? 1 : 0;
+      const int i = t ? f - n0 : f;
+      const int* ki = a.knn_ind[t] + (((size_t)lane * LVO_MAX_OUTER + a.outer) * a.in_cap[t] + i) * 5;
+      int id[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) id[k] = ki[k];
       LvoFactor fac;
       fac.type = -1; fac.pad = 0; fac.d = 0;
-      const float4* M = t ? M1 : M0;
-      if (ok) {
-        float4 nb[5];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) nb[j] = M[tk.id[j]];
-        if (t == 0) {
-          d3 center{0, 0, 0};
-#pragma unroll
-          for (int j = 0; j < 5; ++j) { center.x = center.x + (double)nb[j].x; center.y = center.y + (double)nb[j].y; center.z = center.z + (double)nb[j].z; }
-          center.x = center.x / 5.0; center.y = center.y / 5.0; center.z = center.z / 5.0;
-          double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            const double z[3] = {(double)nb[j].x - center.x, (double)nb[j].y - center.y, (double)nb[j].z - center.z};
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-              for (int c = 0; c < 3; ++c) cov[r * 3 + c] = cov[r * 3 + c] + z[r] * z[c];
-          }
-          double w[3], V[9];
-          sym_eigen3_dev(cov, w, V);
-          if (w[2] > 3 * w[1]) {  // :611
-            const double ux = V[0 * 3 + 2], uy = V[1 * 3 + 2], uz = V[2 * 3 + 2];
-            fac.type = 0;
-            fac.c[0] = ori.x; fac.c[1] = ori.y; fac.c[2] = ori.z;
-            fac.a[0] = 0.1 * ux + center.x; fac.a[1] = 0.1 * uy + center.y; fac.a[2] = 0.1 * uz + center.z;
-            fac.b[0] = -0.1 * ux + center.x; fac.b[1] = -0.1 * uy + center.y; fac.b[2] = -0.1 * uz + center.z;
-          }
-        } else {
-          double A[15], b[5] = {-1, -1, -1, -1, -1}, n[3];
-#pragma unroll
-          for (int j = 0; j < 5; ++j) { A[j * 3 + 0] = nb[j].x; A[j * 3 + 1] = nb[j].y; A[j * 3 + 2] = nb[j].z; }
-          if (!lsq_qr_5x3(A, b, n)) { n[0] = n[1] = n[2] = 0; }
-          const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-          const double negOA = 1 / nn;
-          n[0] /= nn; n[1] /= nn; n[2] /= nn;
-          bool planeValid = true;
-#pragma unroll
-          for (int j = 0; j < 5; ++j)
-            if (fabs(n[0] * nb[j].x + n[1] * nb[j].y + n[2] * nb[j].z + negOA) > 0.2) { planeValid = false; }  // :672-678
-          if (planeValid) {
-            fac.type = 2;
-            fac.c[0] = ori.x; fac.c[1] = ori.y; fac.c[2] = ori.z;
-            fac.a[0] = n[0]; fac.a[1] = n[1]; fac.a[2] = n[2];
-            fac.b[0] = fac.b[1] = fac.b[2] = 0;
-            fac.d = negOA;
-          }
-        }
-      }
+      if (id[0] >= 0) fit_factor(t, a.stack[t][(size_t)lane * a.in_cap[t] + i], t ? M1 : M0, id, fac);
       a.factors[(size_t)lane * a.factor_cap + f] = fac;
-      int* ki = a.knn_ind[t] + (((size_t)lane * LVO_MAX_OUTER + a.outer) * a.in_cap[t] + i) * 5;
-#pragma unroll
-      for (int j = 0; j < 5; ++j) ki[j] = ok ? tk.id[j] : -1;
       a.fac_valid[t][((size_t)lane * LVO_MAX_OUTER + a.outer) * a.in_cap[t] + i] = fac.type >= 0 ? 1 : 0;
       if (fac.type >= 0) { if (t == 0) nc++; else nsf++; }
     }
   }
-  if (ln == 0) {
+  nc = __reduce_add_sync(0xffffffffu, nc);
+  nsf = __reduce_add_sync(0xffffffffu, nsf);
+  if ((threadIdx.x & 31) == 0) {
     if (nc) atomicAdd(&s.stats.map_corner_corr[a.outer], nc);
     if (nsf) atomicAdd(&s.stats.map_surf_corr[a.outer], nsf);
   }
@@ -256,19 +279,21 @@ __global__ void k_map_finish(MapArgs a) {
 }
 
 // ---- insertion + per-cube re-filter (engine run B) ------------------------------------------------------------------
-__global__ void k_refilter_offsets(MapArgs a) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(256) k_refilter_offsets(MapArgs a) {
+  __shared__ unsigned sm[33];
+  const int L2 = 2 * a.lanes;
+  for (int k = threadIdx.x; k < L2 * LVO_MSEGS; k += blockDim.x) a.vx.seg_leaf[k] = (k % LVO_MSEGS) < LVO_MAX_VALID ? a.leaf[(k / LVO_MSEGS) & 1] : 0.f;
   unsigned acc = 0;
-  for (int lt = 0; lt < 2 * a.lanes; ++lt) {
-    const int t = lt & 1;
-    const LaneState& s = a.ls[lt >> 1];
-    a.item_off[lt] = acc;
-    acc += (unsigned)(s.from_off[t][LVO_MAX_VALID] + s.n_stack[t]);
-    for (int v = 0; v < LVO_MSEGS; ++v) a.vx.seg_leaf[lt * LVO_MSEGS + v] = v < LVO_MAX_VALID ? a.leaf[t] : 0.f;
+  for (int base = 0; base < L2; base += blockDim.x) {
+    const int lt = base + threadIdx.x;
+    unsigned v = 0;
+    if (lt < L2) { const LaneState& s = a.ls[lt >> 1]; v = (unsigned)(s.from_off[lt & 1][LVO_MAX_VALID] + s.n_stack[lt & 1]); }
+    unsigned tot;
+    const unsigned ex = block_excl_scan(v, sm, &tot);
+    if (lt < L2) a.item_off[lt] = acc + ex;
+    acc += tot;
   }
-  a.item_off[2 * a.lanes] = acc;
-  *a.vx.d_n = (int)acc;
-  *a.vx.d_nsegs = 2 * a.lanes * LVO_MSEGS;
+  if (threadIdx.x == 0) { a.item_off[L2] = acc; *a.vx.d_n = (int)acc; *a.vx.d_nsegs = L2 * LVO_MSEGS; }
 }
 __global__ void k_refilter_gather(MapArgs a) {
   const int lt = blockIdx.y, lane = lt >> 1, t = lt & 1;
@@ -403,7 +428,7 @@ static inline void lvo_launch_mapping(cudaStream_t st, MapArgs a, const SolveArg
   const int L2 = 2 * lanes;
   k_map_begin<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a);
   k_map_gather<<<dim3(LVO_MAX_VALID, L2), 128, 0, st>>>(a);
-  k_stack_offsets<<<1, 32, 0, st>>>(a);
+  k_stack_offsets<<<1, 256, 0, st>>>(a);
   k_stack_gather<<<dim3(16, L2), 256, 0, st>>>(a);
   if (launches) *launches += 4;
   int seg_bits = 1; while ((1 << seg_bits) < L2) seg_bits++;
@@ -412,19 +437,21 @@ static inline void lvo_launch_mapping(cudaStream_t st, MapArgs a, const SolveArg
   if (launches) *launches += 1;
   lvo_grid_build(st, a.grid, launches);
   const int nstack_cap = a.in_cap[0] + a.in_cap[1];
-  dim3 ga(max(1, min(lvo_div_up(nstack_cap, 8), 296)), lanes);
+  dim3 ga(max(1, min(lvo_div_up(nstack_cap, 128), 128)), lanes);
   for (int o = 0; o < outer_iters; ++o) {
     a.outer = o;
     if (knn_ev) cudaEventRecord(knn_ev[2 * o], st);
-    k_map_assoc<<<ga, 256, 0, st>>>(a);
+    k_map_knn<<<ga, 128, 0, st>>>(a);
     if (knn_ev) cudaEventRecord(knn_ev[2 * o + 1], st);
+    k_map_fit<<<ga, 128, 0, st>>>(a);
+    if (launches) *launches += 1;
     SolveArgs sa = solve_proto;
     sa.which = 1; sa.outer = o; sa.factors = a.factors; sa.factor_cap = a.factor_cap;
-    k_lm_solve<<<lanes, LVO_LM_THREADS, 0, st>>>(sa);
+    lvo_launch_lm(st, sa, lanes);
     if (launches) *launches += 2;
   }
   k_map_finish<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a);
-  k_refilter_offsets<<<1, 32, 0, st>>>(a);
+  k_refilter_offsets<<<1, 256, 0, st>>>(a);
   k_refilter_gather<<<dim3(64, L2), 256, 0, st>>>(a);
   if (launches) *launches += 3;
   int seg_bits2 = 1; while ((1 << seg_bits2) < L2 * LVO_MSEGS) seg_bits2++;

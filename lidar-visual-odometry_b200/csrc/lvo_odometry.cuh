@@ -4,8 +4,9 @@
 //   k_odo_begin      first-frame handling (:355-358), per-outer-iteration counter reset
 //   k_odo_assoc      one warp per feature: TransformToStart (:154-172, s = 1), 1-NN in the previous sweep's
 //                    less-sharp / less-flat cloud on the uniform grid with the d^2 < 25 gate (:386-389, :470-473),
-//                    then the adjacent-ring searches of :395-440 / :481-532 as range scans over a ring-offset table
-//                    (the clouds are ring-ordered by construction), with the reference's walk order as tie-break;
+//                    then the adjacent-ring searches of :395-440 / :481-532 as ring-filtered nearest-neighbour searches
+//                    on the same grid (the clouds are ring-ordered by construction), with the reference's walk order
+//                    as tie-break;
 //                    emits LidarEdgeFactor / LidarPlaneFactor parameter records (:444-462, :536-557)
 //   k_lm_solve       (lvo_solver.cuh) ceres::Solve, :571-576
 //   k_odo_finish     pose integration :581-582, swap of the "last" clouds :627-636, ring-offset tables
@@ -23,7 +24,7 @@ struct OdoArgs {
   int cap_sharp, cap_lsharp, cap_flat, P;
   // previous sweep
   float4* corner_last; float4* surf_last;  // [lanes][cap_lsharp], [lanes][P]
-  GridSet grid;                            // problems 2*lane (corner_last), 2*lane+1 (surf_last)
+  GridSet grid;                            // problems 6*lane + {0 corner fine xyz, 1 surf fine xyz, 2 corner (ring,azimuth), 3 surf (ring,azimuth), 4 corner coarse xyz, 5 surf coarse xyz}
   LvoFactor* factors; int factor_cap;
   int* corner_corr;  // [lanes][LVO_MAX_OUTER][cap_sharp][2]   probes
   int* plane_corr;   // [lanes][LVO_MAX_OUTER][cap_flat][3]
@@ -48,26 +49,82 @@ __device__ __forceinline__ Best warp_best(Best v) {
   }
   return v;
 }
-// Nearest point (d^2 < 25, strict) over the walk  j = ub .. ue-1 ascending, then j = de-1 .. db descending;
-// earlier positions in the walk win ties, exactly like the reference's strict `<` updates.
-__device__ __forceinline__ int walk_min(const float4* C, int ub, int ue, int db, int de, float4 sel, unsigned ln) {
-  Best b{25.0f, INT_MAX, -1};
-  for (int j = ub + (int)ln; j < ue; j += 32) {
-    const float4 p = C[j];
+
+// The adjacent-ring searches of :395-440 / :481-532.  The reference walks the ring-ordered cloud upwards from the
+// closest point, then downwards, and keeps the first strict minimum among the points of the wanted rings with
+// d^2 < 25.  The same point is the ring-filtered nearest neighbour, with the position in the reference's walk as the
+// tie-break key (indices above `closest` ascending, then indices below it descending).  It is searched on a
+// (ring, azimuth) grid of the previous sweep: a point within distance d of the query lies within asin(d / rho_xy) of
+// the query's azimuth, so only a window of azimuth buckets of each wanted ring is scanned: first +-2 buckets, then
+// the window implied by the best distance found so far (or by the 5 m gate).  Margins of two buckets absorb every
+// rounding in atan2f / asinf; the ranking itself uses the exact reference expression.
+//   bestA : nearest point of the SAME ring (other than closest)       -> minPointInd2 of the plane search
+//   bestB : nearest point of rings cid-2, cid-1, cid+1, cid+2         -> minPointInd2 (corner) / minPointInd3 (plane)
+// candidate range(s) of buckets lo..hi of one ring (lo / hi may lie outside [0, NB): wrap).  part 0 / part 1.
+__device__ __forceinline__ void az_bounds(const GridView& g, int ring, int lo, int hi, int part, unsigned& b, unsigned& e) {
+  b = e = 0;
+  if (hi < lo) return;
+  const unsigned* row = g.cell_start + ring * LVO_AZ_BUCKETS;
+  if (hi - lo + 1 >= LVO_AZ_BUCKETS) { if (part == 0) { b = __ldg(row); e = __ldg(row + LVO_AZ_BUCKETS); } return; }
+  const int l = lo & (LVO_AZ_BUCKETS - 1), h = hi & (LVO_AZ_BUCKETS - 1);
+  if (l <= h) { if (part == 0) { b = __ldg(row + l); e = __ldg(row + h + 1); } }
+  else if (part == 0) { b = __ldg(row + l); e = __ldg(row + LVO_AZ_BUCKETS); }
+  else { b = __ldg(row); e = __ldg(row + h + 1); }
+}
+// half-width (in buckets) of the azimuth window that contains every point within sqrt(d2) of the query
+__device__ __forceinline__ int az_halfwidth(float d2, float rho) {
+  const float d = sqrtf(d2) * 1.00001f + 1e-6f;
+  if (!(d < rho * 0.999f)) return LVO_AZ_BUCKETS;  // the window is the whole ring
+  const float w = asinf(d / rho);
+  return (int)ceilf(w * ((float)LVO_AZ_BUCKETS / 6.28318548f)) + 2;
+}
+// one warp per feature
+__device__ __forceinline__ void ring_search(const GridView& g, float4 sel, int closest, int cid, bool needA, int& outA, int& outB) {
+  const int ln = threadIdx.x & 31;
+  Best bA{25.0f, INT_MAX, -1}, bB{25.0f, INT_MAX, -1};
+  const int bq = az_bucket(sel.x, sel.y);
+  const float rho = sqrtf(sel.x * sel.x + sel.y * sel.y);
+  auto consider = [&](unsigned t, int ring) {
+    const float4 p = __ldg(g.pts + t);
+    const int idx = __ldg(g.ids + t);
+    const int dr = ring - cid;
+    if (idx == closest) return;
+    // the walk is monotone in the ring id: above `closest` it only meets rings >= cid, below it rings <= cid
+    if ((idx > closest && dr < 0) || (idx < closest && dr > 0)) return;
     const float d = (p.x - sel.x) * (p.x - sel.x) + (p.y - sel.y) * (p.y - sel.y) + (p.z - sel.z) * (p.z - sel.z);
-    if (d < 25.0f) b = best_min(b, Best{d, j - ub, j});
+    if (!(d < 25.0f)) return;
+    const int key = idx > closest ? (idx - closest) : ((closest - idx) + (1 << 30));
+    const Best c{d, key, idx};
+    if (dr == 0) bA = best_min(bA, c); else bB = best_min(bB, c);
+  };
+  // phase 1: +-2 buckets of rings cid-2 .. cid+2.  lane = ring slot (0..4) * 4 + part
+  {
+    const int slot = ln >> 2, part = ln & 3, ring = cid - 2 + slot;
+    unsigned b = 0, e = 0;
+    if (slot < 5 && part < 2 && ring >= 0 && ring < LVO_AZ_RINGS && (ring != cid || needA)) az_bounds(g, ring, bq - 2, bq + 2, part, b, e);
+    warp_scan_ranges<20>(b, e, [&](unsigned t, int r) { consider(t, cid - 2 + (r >> 2)); });
   }
-  const int ulen = max(ue - ub, 0);
-  for (int j = de - 1 - (int)ln; j >= db; j -= 32) {
-    const float4 p = C[j];
-    const float d = (p.x - sel.x) * (p.x - sel.x) + (p.y - sel.y) * (p.y - sel.y) + (p.z - sel.z) * (p.z - sel.z);
-    if (d < 25.0f) b = best_min(b, Best{d, ulen + (de - 1 - j), j});
+  bA = warp_best(bA); bB = warp_best(bB);
+  // phase 2: the rest of the window implied by the best distances so far (or by the 5 m gate)
+  {
+    const int hA = needA ? az_halfwidth(bA.d, rho) : 0, hB = az_halfwidth(bB.d, rho);
+    const int slot = ln >> 2, sp = ln & 3, ring = cid - 2 + slot;  // sp: side (bit 1), part (bit 0)
+    unsigned b = 0, e = 0;
+    if (slot < 5 && ring >= 0 && ring < LVO_AZ_RINGS && (ring != cid || needA)) {
+      const int h = ring == cid ? hA : hB;
+      if (h > 2) {
+        if (2 * h + 1 >= LVO_AZ_BUCKETS) { if (sp == 0) az_bounds(g, ring, 0, LVO_AZ_BUCKETS - 1, 0, b, e); }
+        else if ((sp >> 1) == 0) az_bounds(g, ring, bq - h, bq - 3, sp & 1, b, e);
+        else az_bounds(g, ring, bq + 3, bq + h, sp & 1, b, e);
+      }
+    }
+    warp_scan_ranges<20>(b, e, [&](unsigned t, int r) { consider(t, cid - 2 + (r >> 2)); });
   }
-  b = warp_best(b);
-  return b.j;
+  bA = warp_best(bA); bB = warp_best(bB);
+  outA = bA.j; outB = bB.j;
 }
 
-__global__ void __launch_bounds__(256) k_odo_assoc(OdoArgs a) {
+__global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
   const int lane = blockIdx.y;
   LaneState& s = a.ls[lane];
   if (!s.odo_inited) return;
@@ -77,51 +134,46 @@ __global__ void __launch_bounds__(256) k_odo_assoc(OdoArgs a) {
   const double* q = s.para_q; const double* t = s.para_t;
   const float4* CL = a.corner_last + (size_t)lane * a.cap_lsharp;
   const float4* SL = a.surf_last + (size_t)lane * a.P;
-  const GridView gc = grid_view(a.grid, 2 * lane), gsf = grid_view(a.grid, 2 * lane + 1);
+  const GridView gcf = grid_view(a.grid, 6 * lane), gsf = grid_view(a.grid, 6 * lane + 1);
+  const GridView gca = grid_view(a.grid, 6 * lane + 2), gsa = grid_view(a.grid, 6 * lane + 3);
+  const GridView gcc = grid_view(a.grid, 6 * lane + 4), gsc = grid_view(a.grid, 6 * lane + 5);
   int ncorr_c = 0, ncorr_p = 0;
   for (int f = wid; f < ns + nf; f += nw) {
     const bool corner = f < ns;
     const float4 pt = corner ? a.sharp[(size_t)lane * a.cap_sharp + f] : a.flat[(size_t)lane * a.cap_flat + (f - ns)];
     const float4 sel = transform_point(q, t, pt);  // TransformToStart
-    TopK<1> tk;
-    const bool ok = warp_knn<1>(corner ? gc : gsf, sel.x, sel.y, sel.z, 25.0f, tk);
+    float bd; int closest;
+    const bool ok = warp_nn1_two_level(corner ? gcf : gsf, corner ? gcc : gsc, sel.x, sel.y, sel.z, 25.0f, bd, closest);
     LvoFactor fac;
     fac.type = -1; fac.pad = 0; fac.d = 0;
     int i1 = -1, i2 = -1, i3 = -1;
     if (ok) {
       const float4* C = corner ? CL : SL;
-      const int* rf = corner ? s.corner_ring_first : s.surf_ring_first;
-      const int closest = tk.id[0];
-      int cid = int(C[closest].w);
-      cid = min(max(cid, 0), LVO_MAX_RINGS - 1);
-      const int r_lo2 = rf[max(cid - 2, 0)], r_c = rf[cid], r_c1 = rf[cid + 1], r_hi = rf[min(cid + 3, LVO_MAX_RINGS + 1)];
-      // rings cid+1, cid+2 walked upwards, then cid-1, cid-2 walked downwards (:395-440 / the `> closestPointScanID` arms of :481-532)
-      const int other = walk_min(C, r_c1, r_hi, r_lo2, r_c, sel, ln);
+      const float4 pj = C[closest];
+      const int cid = ring_clamped(pj.w);
+      int same = -1, other = -1;
+      ring_search(corner ? gca : gsa, sel, closest, cid, !corner, same, other);
       if (corner) {
         if (other >= 0) {
           i1 = closest; i2 = other;
-          const float4 pa = C[closest], pb = C[other];
+          const float4 pb = C[other];
           fac.type = 0;
           fac.c[0] = pt.x; fac.c[1] = pt.y; fac.c[2] = pt.z;
-          fac.a[0] = pa.x; fac.a[1] = pa.y; fac.a[2] = pa.z;
+          fac.a[0] = pj.x; fac.a[1] = pj.y; fac.a[2] = pj.z;
           fac.b[0] = pb.x; fac.b[1] = pb.y; fac.b[2] = pb.z;
         }
-      } else {
-        // same ring: upwards from closest+1 to the end of the ring, then downwards from closest-1 (:493-497, :520-524)
-        const int same = walk_min(C, closest + 1, r_c1, r_c, closest, sel, ln);
-        if (same >= 0 && other >= 0) {
-          i1 = closest; i2 = same; i3 = other;
-          const float4 pj = C[closest], pl = C[same], pm = C[other];
-          // LidarPlaneFactor constructor, lidarFactor.hpp:64-65
-          const d3 jl{(double)pj.x - (double)pl.x, (double)pj.y - (double)pl.y, (double)pj.z - (double)pl.z};
-          const d3 jm{(double)pj.x - (double)pm.x, (double)pj.y - (double)pm.y, (double)pj.z - (double)pm.z};
-          d3 n = d3cross(jl, jm);
-          const double nn = sqrt(n.x * n.x + n.y * n.y + n.z * n.z);
-          fac.type = 1;
-          fac.c[0] = pt.x; fac.c[1] = pt.y; fac.c[2] = pt.z;
-          fac.a[0] = pj.x; fac.a[1] = pj.y; fac.a[2] = pj.z;
-          fac.b[0] = n.x / nn; fac.b[1] = n.y / nn; fac.b[2] = n.z / nn;
-        }
+      } else if (same >= 0 && other >= 0) {
+        i1 = closest; i2 = same; i3 = other;
+        const float4 pl = C[same], pm = C[other];
+        // LidarPlaneFactor constructor, lidarFactor.hpp:64-65
+        const d3 jl{(double)pj.x - (double)pl.x, (double)pj.y - (double)pl.y, (double)pj.z - (double)pl.z};
+        const d3 jm{(double)pj.x - (double)pm.x, (double)pj.y - (double)pm.y, (double)pj.z - (double)pm.z};
+        d3 n = d3cross(jl, jm);
+        const double nn = sqrt(n.x * n.x + n.y * n.y + n.z * n.z);
+        fac.type = 1;
+        fac.c[0] = pt.x; fac.c[1] = pt.y; fac.c[2] = pt.z;
+        fac.a[0] = pj.x; fac.a[1] = pj.y; fac.a[2] = pj.z;
+        fac.b[0] = n.x / nn; fac.b[1] = n.y / nn; fac.b[2] = n.z / nn;
       }
     }
     if (ln == 0) {
@@ -187,13 +239,13 @@ static inline void lvo_launch_odometry(cudaStream_t st, OdoArgs a, const SolveAr
   k_odo_begin<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a);
   if (launches) *launches += 1;
   const int nfeat_cap = a.cap_sharp + a.cap_flat;
-  dim3 ga(max(1, min(lvo_div_up(nfeat_cap, 8), 148)), lanes);
+  dim3 ga(max(1, lvo_div_up(nfeat_cap, 8)), lanes);
   for (int o = 0; o < outer_iters; ++o) {
     a.outer = o;
     k_odo_assoc<<<ga, 256, 0, st>>>(a);
     SolveArgs sa = solve_proto;
     sa.which = 0; sa.outer = o; sa.factors = a.factors; sa.factor_cap = a.factor_cap;
-    k_lm_solve<<<lanes, LVO_LM_THREADS, 0, st>>>(sa);
+    lvo_launch_lm(st, sa, lanes);
     if (launches) *launches += 2;
   }
   k_odo_integrate<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a, outer_iters);

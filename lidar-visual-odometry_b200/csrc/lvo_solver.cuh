@@ -13,14 +13,20 @@
 //     discarded when a tolerance fires, rejected and invalid steps counted as iterations — A19) run by thread 0 in
 //     double.  The damped 6x6 system is solved from the normal equations (Cholesky) instead of a QR of the stacked
 //     Jacobian: same minimiser, difference O(cond * eps), far below the 1e-4 m / 1e-5 rad pose tolerance.
-// One CTA per lane runs the WHOLE inner loop (<= max_iters evaluations of all factors) without returning to the
-// host; each LM iteration costs one pass over the factors because cost, J^T W J and J^T r at the candidate are
-// accumulated together (if the step is accepted they are the next iteration's system).
+// One thread-block CLUSTER (up to 8 CTAs, portable size) per lane runs the WHOLE inner loop (<= max_iters evaluations of all
+// factors) without returning to the host: every CTA reduces its slice of the factors to 28 doubles in its own shared
+// memory, cluster.sync(), CTA 0 adds the 8 partials in rank order through distributed shared memory, its thread 0 takes
+// the trust-region decision and writes the next evaluation point into every CTA's shared memory, cluster.sync().
+// Each LM iteration costs one pass over the factors because cost, J^T W J and J^T r at the candidate are accumulated
+// together (if the step is accepted they are the next iteration's system).
 #pragma once
 #include "lvo_internal.h"
 #include <float.h>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 #define LVO_LM_THREADS 256
+#define LVO_LM_CLUSTER_MAX 8   // CTAs per lane (1, 2, 4 or 8): one thread-block cluster, partial sums exchanged through DSMEM
 #define LVO_NACC 28  // 21 + 6 + 1
 
 // ---- small dense routines (double) ---------------------------------------------------------------------------
@@ -97,22 +103,41 @@ __device__ inline bool lsq_qr_5x3(double A[15], double b[5], double y[3]) {
 }
 
 // Cholesky solve of a 6x6 SPD system (A full row-major, destroyed).  false if not positive definite.
-__device__ inline bool chol6_solve(double A[36], const double b[6], double y[6]) {
+// Fully unrolled and division-free apart from one reciprocal square root per pivot: this runs on ONE thread while the
+// rest of the cluster waits, so its dependent-latency chain is the critical path of every LM iteration.
+__device__ __forceinline__ bool chol6_solve(double A[36], const double b[6], double y[6]) {
+  double inv[6];
+#pragma unroll
   for (int j = 0; j < 6; ++j) {
     double d = A[j * 6 + j];
+#pragma unroll
     for (int k = 0; k < j; ++k) d -= A[j * 6 + k] * A[j * 6 + k];
     if (!(d > 0.0)) return false;
-    d = sqrt(d);
-    A[j * 6 + j] = d;
+    const double r = rsqrt(d);
+    inv[j] = r;
+#pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       double s = A[i * 6 + j];
+#pragma unroll
       for (int k = 0; k < j; ++k) s -= A[i * 6 + k] * A[j * 6 + k];
-      A[i * 6 + j] = s / d;
+      A[i * 6 + j] = s * r;
     }
   }
   double z[6];
-  for (int i = 0; i < 6; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= A[i * 6 + k] * z[k]; z[i] = s / A[i * 6 + i]; }
-  for (int i = 5; i >= 0; --i) { double s = z[i]; for (int k = i + 1; k < 6; ++k) s -= A[k * 6 + i] * y[k]; y[i] = s / A[i * 6 + i]; }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double s = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s -= A[i * 6 + k] * z[k];
+    z[i] = s * inv[i];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double s = z[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) s -= A[k * 6 + i] * y[k];
+    y[i] = s * inv[i];
+  }
   return true;
 }
 
@@ -199,16 +224,19 @@ struct SolveArgs {
 
 struct LmShared {
   double red[LVO_LM_THREADS / 32][LVO_NACC];
-  double sum[LVO_NACC];   // reduced accumulators of the last evaluation
-  double xeval[7];        // point to evaluate next
-  int ctrl;               // 0 = evaluate xeval, 1 = finished
+  double partial[LVO_NACC];  // this CTA's partial sums
+  double sum[LVO_NACC];      // (CTA 0) reduced accumulators of the last evaluation
+  double xeval[7];           // point to evaluate next
+  int ctrl;                  // 0 = evaluate xeval, 1 = finished
 };
 
-__device__ __forceinline__ void lm_evaluate(const SolveArgs& a, const LvoFactor* F, int nslots, const double* x, LmShared& sh) {
+// All CTAs of the cluster call this; afterwards CTA 0's sh.sum holds the cluster-wide sums (fixed summation tree).
+__device__ __forceinline__ void lm_evaluate(const SolveArgs& a, const LvoFactor* F, int nslots, const double* x, LmShared& sh, cg::cluster_group& cluster) {
+  const unsigned crank = cluster.block_rank(), csize = cluster.num_blocks();
   double acc[LVO_NACC];
 #pragma unroll
   for (int i = 0; i < LVO_NACC; ++i) acc[i] = 0.0;
-  for (int s = threadIdx.x; s < nslots; s += LVO_LM_THREADS) {
+  for (int s = crank * LVO_LM_THREADS + threadIdx.x; s < nslots; s += LVO_LM_THREADS * csize) {
     const LvoFactor f = F[s];
     if (f.type >= 0) accumulate_factor(f, x, a.huber, acc);
   }
@@ -225,9 +253,27 @@ __device__ __forceinline__ void lm_evaluate(const SolveArgs& a, const LvoFactor*
     double v = 0;
 #pragma unroll
     for (int ww = 0; ww < LVO_LM_THREADS / 32; ++ww) v += sh.red[ww][threadIdx.x];
-    sh.sum[threadIdx.x] = v;
+    sh.partial[threadIdx.x] = v;
   }
-  __syncthreads();
+  cluster.sync();
+  if (crank == 0) {
+    if (threadIdx.x < LVO_NACC) {
+      double v = 0;
+#pragma unroll
+      for (unsigned r = 0; r < csize; ++r) v += cluster.map_shared_rank(&sh, r)->partial[threadIdx.x];
+      sh.sum[threadIdx.x] = v;
+    }
+    __syncthreads();
+  }
+}
+// CTA 0 thread 0: publish the next evaluation point / the stop flag to every CTA of the cluster
+__device__ __forceinline__ void lm_broadcast(LmShared& sh, cg::cluster_group& cluster, const double* xc, bool go) {
+  const unsigned csize = cluster.num_blocks();
+  for (unsigned r = 0; r < csize; ++r) {
+    LmShared* o = cluster.map_shared_rank(&sh, r);
+    if (go) for (int i = 0; i < 7; ++i) o->xeval[i] = xc[i];
+    o->ctrl = go ? 0 : 1;
+  }
 }
 
 // State of the trust-region loop, owned by thread 0.
@@ -297,10 +343,12 @@ __device__ inline bool lm_next_step(const SolveArgs& a, int lane, LmCtl& c) {
   }
 }
 
-__global__ void __launch_bounds__(LVO_LM_THREADS) k_lm_solve(SolveArgs a) {
+__global__ void __launch_bounds__(LVO_LM_THREADS, 2) k_lm_solve(SolveArgs a) {
   __shared__ LmShared sh;
-  __shared__ LmCtl ctl;  // only thread 0 touches it; shared to keep it out of thread 0's registers
-  const int lane = blockIdx.x;
+  __shared__ LmCtl ctl;  // only thread 0 of CTA 0 touches it; shared to keep it out of its registers
+  cg::cluster_group cluster = cg::this_cluster();
+  const bool lead = cluster.block_rank() == 0 && threadIdx.x == 0;
+  const int lane = blockIdx.x / cluster.num_blocks();
   LaneState& s = a.ls[lane];
   if (a.which == 0 ? (s.odo_inited == 0) : (s.map_too_small != 0)) return;
   const int nslots = a.which == 0 ? (s.n_sharp + s.n_flat) : (s.n_stack[0] + s.n_stack[1]);
@@ -308,8 +356,8 @@ __global__ void __launch_bounds__(LVO_LM_THREADS) k_lm_solve(SolveArgs a) {
   double* xg = a.which == 0 ? s.para_q : s.map_x;  // para_q[4], para_t[3] are contiguous
   if (threadIdx.x < 7) sh.xeval[threadIdx.x] = xg[threadIdx.x];
   __syncthreads();
-  lm_evaluate(a, F, nslots, sh.xeval, sh);
-  if (threadIdx.x == 0) {
+  lm_evaluate(a, F, nslots, sh.xeval, sh, cluster);
+  if (lead) {
     LmCtl& c = ctl;
     for (int i = 0; i < 7; ++i) c.x[i] = sh.xeval[i];
     for (int i = 0; i < 21; ++i) c.H[i] = sh.sum[i];
@@ -330,13 +378,12 @@ __global__ void __launch_bounds__(LVO_LM_THREADS) k_lm_solve(SolveArgs a) {
       lm_trace(a, lane, 0, c.x, c.cost, c.radius, 32 | (gconv ? 16 : 0));
       if (!gconv) go = lm_next_step(a, lane, c);
     }
-    if (go) for (int i = 0; i < 7; ++i) sh.xeval[i] = c.xc[i];
-    sh.ctrl = go ? 0 : 1;
+    lm_broadcast(sh, cluster, c.xc, go);
   }
-  __syncthreads();
+  cluster.sync();
   while (sh.ctrl == 0) {
-    lm_evaluate(a, F, nslots, sh.xeval, sh);
-    if (threadIdx.x == 0) {
+    lm_evaluate(a, F, nslots, sh.xeval, sh, cluster);
+    if (lead) {
       LmCtl& c = ctl;
       const double new_cost = sh.sum[27];
       bool go = false;
@@ -370,15 +417,31 @@ __global__ void __launch_bounds__(LVO_LM_THREADS) k_lm_solve(SolveArgs a) {
         if (c.radius < 1e-32) go = false;
         if (go) go = lm_next_step(a, lane, c);
       }
-      if (go) for (int i = 0; i < 7; ++i) sh.xeval[i] = c.xc[i];
-      sh.ctrl = go ? 0 : 1;
+      lm_broadcast(sh, cluster, c.xc, go);
     }
-    __syncthreads();
+    cluster.sync();
   }
-  if (threadIdx.x == 0) {
+  if (lead) {
     LmCtl& c = ctl;
     for (int i = 0; i < 7; ++i) xg[i] = c.x[i];
     if (a.which == 0) { s.stats.odo_lm_iters[a.outer] = c.iter; s.stats.odo_final_cost[a.outer] = c.nfactors ? c.cost : 0.0; }
     else { s.stats.map_lm_iters[a.outer] = c.iter; s.stats.map_final_cost[a.outer] = c.nfactors ? c.cost : 0.0; }
   }
+}
+
+// one cluster per lane; the cluster size is the largest of 8, 4, 2, 1 that keeps all lanes resident in one wave
+// (2 CTAs per SM x 148 SMs), so that few lanes get short latency and many lanes get full throughput
+static inline void lvo_launch_lm(cudaStream_t st, const SolveArgs& sa, int lanes) {
+  int csize = LVO_LM_CLUSTER_MAX;
+  while (csize > 1 && lanes * csize > 296) csize >>= 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(lanes * csize, 1, 1);
+  cfg.blockDim = dim3(LVO_LM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, k_lm_solve, sa);
 }
