@@ -92,6 +92,22 @@ def lane_plan(lanes, n_seq):
     return [(l % n_seq, 5 * (l // n_seq)) for l in range(lanes)]
 
 
+def rank_sequence_base(rank):
+    """Sequence ids of a rank: distinct data per rank, no overlap (8 sequences per rank)."""
+    return 8 * rank
+
+
+def max_over_ranks(values, world, device="cuda"):
+    """The only cross-rank exchange of the bench: element-wise max of per-rank timings."""
+    if world <= 1:
+        return [float(v) for v in values]
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(values, dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
 def run_reference(args, rank, world):
     """CPU oracle with all host threads: one independent sequence per thread."""
     if rank != 0:
@@ -170,7 +186,7 @@ def main():
     synth = Synth()
     jobs = [(s, f) for s in range(n_seq) for f in range(total + max_off)]
     with ThreadPoolExecutor(max_workers=host_threads) as ex:
-        res = list(ex.map(lambda j: synth.sweep(64, 8 * rank + j[0], j[1])[0], jobs))
+        res = list(ex.map(lambda j: synth.sweep(64, rank_sequence_base(rank) + j[0], j[1])[0], jobs))
     sweeps = {j: r for j, r in zip(jobs, res)}
     t_gen = time.perf_counter() - t_gen
 
@@ -248,10 +264,7 @@ def main():
     ctx_d.close()
 
     # max over ranks
-    if world > 1:
-        tt = torch.tensor([ms_d, ms_e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_d, ms_e = float(tt[0]), float(tt[1])
+    ms_d, ms_e = max_over_ranks([ms_d, ms_e], world)
     scans = lanes * args.steps * world
     value = scans / (ms_d * 1e-3)
     e2e = scans / (ms_e * 1e-3)

@@ -29,7 +29,7 @@ LVO_HD double lvo_atan_tab(int k) {
     case 4: return 0.46364760900080611621;
     case 5: return 0.55859931534356243597;
     case 6: return 0.64350110879328438680;
-    case 7: return 0.71883000399876212297;
+    case 7: return 0.71882999962162450;
     default: return 0.78539816339744830962;
   }
 }

@@ -1,0 +1,302 @@
+"""CPU tests (no GPU): the oracle against independent implementations (numpy / scipy / glibc), against the reference's
+own functors (oracle/_ref: src/lidarFactor.hpp + vendored Eigen), against ground truth, and against the golden fixture."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle_py import ROOT, Oracle, Synth
+
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "liblvo_oracle_ref.so")
+GOLD = os.path.join(ROOT, "tests", "golden", "vlp16_seq1.npz")
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle()
+
+
+@pytest.fixture(scope="module")
+def feats():
+    s, o = Synth(), Oracle()
+    return o.extract(s.sweep(64, 0, 0)[0])
+
+
+# ---- lvo_math.h ----------------------------------------------------------------------------------------------------
+def test_atan_within_one_float_ulp_of_glibc(orc):
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.normal(0, 1, 4000), rng.normal(0, 100, 2000), [0.0, 1.0, -1.0, 1e-30, 1e30, 0.125, 0.0625 * 9]]).astype(np.float32)
+    got = np.array([orc.lib.lvo_oracle_atanf(float(v)) for v in x], np.float32)
+    ref = np.arctan(x.astype(np.float64))
+    ulp = np.spacing(np.abs(ref).astype(np.float32)).astype(np.float64)
+    assert np.all(np.abs(got.astype(np.float64) - ref) <= 0.5000001 * ulp + 1e-45)  # correctly rounded from a ~1e-16-accurate double
+    assert np.all(np.abs(got - np.arctan(x)) <= np.spacing(np.abs(got)))       # <= 1 ulp from glibc's atanf
+
+
+def test_atan2_quadrants_and_accuracy(orc):
+    rng = np.random.default_rng(1)
+    y = rng.normal(0, 10, 5000).astype(np.float32)
+    x = rng.normal(0, 10, 5000).astype(np.float32)
+    got = np.array([orc.lib.lvo_oracle_atan2f(float(a), float(b)) for a, b in zip(y, x)], np.float32)
+    ref = np.arctan2(y.astype(np.float64), x.astype(np.float64))
+    assert np.all(np.abs(got.astype(np.float64) - ref) <= 0.5000001 * np.spacing(np.abs(ref).astype(np.float32)).astype(np.float64))
+    for yy, xx in [(0.0, 1.0), (0.0, -1.0), (1.0, 0.0), (-1.0, 0.0), (1.0, 1.0), (-1.0, -1.0), (1e-20, -1.0)]:
+        assert abs(orc.lib.lvo_oracle_atan2f(yy, xx) - np.float32(np.arctan2(yy, xx))) <= np.spacing(np.float32(4.0))
+
+
+# ---- pcl::VoxelGrid restatement -----------------------------------------------------------------------------------------
+def voxel_numpy(p, leaf):
+    """Independent numpy statement of the same filter (float32 arithmetic, stable order, sequential sums)."""
+    p = np.asarray(p, np.float32)
+    inv = np.float32(1.0) / np.float32(leaf)
+    mn, mx = p[:, :3].min(0), p[:, :3].max(0)
+    minb = np.floor(mn * inv).astype(np.int64)
+    maxb = np.floor(mx * inv).astype(np.int64)
+    div = maxb - minb + 1
+    ijk = (np.floor(p[:, :3] * inv) - minb.astype(np.float32)).astype(np.int64)
+    idx = ijk[:, 0] + ijk[:, 1] * div[0] + ijk[:, 2] * div[0] * div[1]
+    order = np.argsort(idx, kind="stable")
+    out = []
+    i = 0
+    while i < len(order):
+        j = i
+        acc = np.zeros(4, np.float32)
+        while j < len(order) and idx[order[j]] == idx[order[i]]:
+            acc = acc + p[order[j]]
+            j += 1
+        out.append(acc / np.float32(j - i))
+        i = j
+    return np.array(out, np.float32), idx
+
+
+@pytest.mark.parametrize("leaf", [0.2, 0.4, 0.8])
+def test_voxel_grid_matches_numpy_statement(orc, feats, leaf):
+    cloud = feats["less_sharp"]
+    got, idx, order = orc.voxel_grid(cloud, leaf)
+    ref, ridx = voxel_numpy(cloud, leaf)
+    assert np.array_equal(idx, ridx) and np.array_equal(_bits(got), _bits(ref))
+    assert np.all(np.diff(idx[order]) >= 0)  # output order = ascending voxel index
+    # idempotence: a filtered cloud has one point per voxel of the same lattice only approximately, but never grows
+    again, _, _ = orc.voxel_grid(got, leaf)
+    assert len(again) <= len(got)
+
+
+def test_voxel_grid_known_answer_and_edges(orc):
+    g = np.load(GOLD)
+    got, idx, _ = orc.voxel_grid(g["tiny"], 0.2)
+    assert np.array_equal(idx, g["tiny_voxel_idx"]) and np.array_equal(_bits(got), _bits(g["tiny_voxel"]))
+    # hand check: points 0 and 1 share voxel (x in [0, 0.2)), ordered after the voxel at x < 0
+    assert len(got) == 4 and np.allclose(got[1], [0.1, 0.05, 0.05, 2.0], atol=1e-6)
+    assert len(orc.voxel_grid(np.zeros((0, 4), np.float32), 0.4)[0]) == 0
+    rng = np.random.default_rng(2)
+    huge = (rng.random((500, 4)) * 4000 - 2000).astype(np.float32)
+    out, _, _ = orc.voxel_grid(huge, 0.01)  # dx*dy*dz > INT_MAX -> unchanged
+    assert np.array_equal(_bits(out), _bits(huge))
+
+
+# ---- kNN -------------------------------------------------------------------------------------------------------------
+def test_kdtree_equals_brute_force_and_scipy(orc, feats):
+    from scipy.spatial import cKDTree
+    cloud = orc.voxel_grid(feats["less_flat"], 0.8)[0]
+    q = cloud[::3] + np.array([0.07, -0.02, 0.03, 0], np.float32)
+    i_b, d_b = orc.knn(cloud, q, 5, 1.0, method=0)
+    i_k, d_k = orc.knn(cloud, q, 5, 1.0, method=1)
+    assert np.array_equal(i_b, i_k) and np.array_equal(_bits(d_b), _bits(d_k))
+    dd, ii = cKDTree(cloud[:, :3].astype(np.float64)).query(q[:, :3].astype(np.float64), k=5)
+    ok = i_b[:, 0] >= 0
+    assert ok.mean() > 0.3
+    same = np.array([set(a) == set(b) for a, b in zip(i_b[ok], ii[ok])])
+    assert same.mean() > 0.999  # float-vs-double distance ranking can differ only on near-ties
+    i1, _ = orc.knn(feats["less_flat"], feats["flat"], 1, 25.0, method=1)
+    i0, _ = orc.knn(feats["less_flat"], feats["flat"], 1, 25.0, method=0)
+    assert np.array_equal(i0, i1)
+
+
+def test_knn_tie_break_is_distance_then_index(orc):
+    cloud = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [-1, 0, 0, 0], [0, -1, 0, 0], [0, 0, 1, 0], [0, 0, -1, 0]], np.float32) * 0.5
+    i, d = orc.knn(cloud, np.zeros((1, 4), np.float32), 5, 1.0, method=1)
+    assert list(i[0]) == [0, 1, 2, 3, 4] and np.all(d[0] == 0.25)
+
+
+# ---- dense routines ---------------------------------------------------------------------------------------------------
+def test_eigen_and_plane_fit_vs_numpy(orc):
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        a = rng.normal(size=(5, 3)) * [3, 0.3, 0.05]
+        m = a.T @ a
+        w, v = np.zeros(3), np.zeros(9)
+        orc.lib.lvo_oracle_sym_eigen3(np.ascontiguousarray(m).ctypes.data, w.ctypes.data, v.ctypes.data)
+        rw, rv = np.linalg.eigh(m)
+        assert np.allclose(w, rw, rtol=1e-10, atol=1e-12)
+        assert abs(abs(v.reshape(3, 3)[:, 2] @ rv[:, 2]) - 1) < 1e-9
+        pts = rng.normal(size=(5, 3)) + [0, 0, 5]
+        n = np.zeros(3)
+        orc.lib.lvo_oracle_plane_fit5(np.ascontiguousarray(pts).ctypes.data, n.ctypes.data)
+        assert np.allclose(n, np.linalg.lstsq(pts, -np.ones(5), rcond=None)[0], rtol=1e-9, atol=1e-12)
+
+
+# ---- residual functors and the LM loop ----------------------------------------------------------------------------------
+def _random_factors(rng, n, pose):
+    """Factors consistent with a ground-truth pose: points on lines / planes of a random scene."""
+    from scipy.spatial.transform import Rotation as R
+    rot = R.from_quat(pose[:4])
+    F = np.zeros((n, 14))
+    for i in range(n):
+        c = rng.normal(size=3) * 10
+        w = rot.apply(c) + pose[4:]
+        t = i % 3
+        F[i, 0] = t
+        F[i, 1:4] = c
+        if t == 0:
+            d = rng.normal(size=3); d /= np.linalg.norm(d)
+            F[i, 4:7] = w + 0.1 * d + rng.normal(size=3) * 0.01
+            F[i, 7:10] = w - 0.1 * d + rng.normal(size=3) * 0.01
+        elif t == 1:
+            nrm = rng.normal(size=3); nrm /= np.linalg.norm(nrm)
+            u = np.cross(nrm, rng.normal(size=3)); u /= np.linalg.norm(u)
+            v = np.cross(nrm, u)
+            F[i, 4:7] = w + rng.normal() * 0.01 * nrm
+            F[i, 7:10] = w + u
+            F[i, 10:13] = w + v
+        else:
+            nrm = rng.normal(size=3); nrm /= np.linalg.norm(nrm)
+            F[i, 4:7] = nrm
+            F[i, 13] = -nrm @ w + rng.normal() * 0.01
+    return F
+
+
+def test_analytic_jacobian_matches_finite_differences(orc):
+    rng = np.random.default_rng(4)
+    x = np.array([0.02, -0.03, 0.05, 0, 0.3, -0.2, 0.1]); x[3] = np.sqrt(1 - x[:3] @ x[:3])
+    F = _random_factors(rng, 9, x)
+    for f in F:
+        r, J = orc.eval_factor(f, x)
+        for c in range(6):
+            d = np.zeros(6); d[c] = 1e-6
+            # x (+) delta with Ceres' EigenQuaternionParameterization: q_delta * q, q_delta = (sin|d| d/|d|, cos|d|)
+            from scipy.spatial.transform import Rotation as R
+            qd = np.r_[np.sin(np.linalg.norm(d[:3])) * d[:3] / max(np.linalg.norm(d[:3]), 1e-300), np.cos(np.linalg.norm(d[:3]))]
+            qn = (R.from_quat(qd) * R.from_quat(x[:4])).as_quat()
+            xp = np.r_[qn, x[4:] + d[3:]]
+            rp, _ = orc.eval_factor(f, xp)
+            assert np.allclose((rp - r) / 1e-6, J[:, c], atol=2e-4 * max(1.0, np.abs(J).max()))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref not built (needs /root/reference)")
+def test_restatement_matches_the_references_own_functors():
+    """oracle/_ref evaluates src/lidarFactor.hpp (unmodified) with forward-mode autodiff and uses Eigen 3.3.7."""
+    a, b = Oracle(), Oracle(reference_build=True)
+    assert b.lib.lvo_oracle_is_reference_build() == 1 and a.lib.lvo_oracle_is_reference_build() == 0
+    rng = np.random.default_rng(5)
+    x = np.array([0.1, -0.2, 0.05, 0, 1.0, -2.0, 0.5]); x[3] = np.sqrt(1 - x[:3] @ x[:3])
+    F = _random_factors(rng, 30, x)
+    for f in F:
+        ra, Ja = a.eval_factor(f, x)
+        rb, Jb = b.eval_factor(f, x)
+        assert np.allclose(ra, rb, rtol=1e-12, atol=1e-13) and np.allclose(Ja, Jb, rtol=1e-10, atol=1e-11)
+    x0 = np.array([0, 0, 0, 1, 0, 0, 0.0])
+    xa, ta = a.solve(F, x0)
+    xb, tb = b.solve(F, x0)
+    assert np.array_equal(ta[:, 9], tb[:, 9]) and np.allclose(xa, xb, atol=1e-9) and np.allclose(ta[:, 7], tb[:, 7], rtol=1e-9)
+    # whole pipeline, 4 frames
+    s = Synth()
+    for k in range(4):
+        pts = s.sweep(64, 0, k)[0]
+        _, oa, ma = a.step(pts)
+        _, ob, mb = b.step(pts)
+        assert np.allclose(oa, ob, atol=1e-8) and np.allclose(ma, mb, atol=1e-8), k
+
+
+def test_lm_agrees_with_scipy_huber_least_squares(orc):
+    from scipy.optimize import least_squares
+    from scipy.spatial.transform import Rotation as R
+    rng = np.random.default_rng(6)
+    truth = np.r_[R.from_rotvec([0.02, -0.01, 0.03]).as_quat(), [0.5, -0.3, 0.1]]
+    F = _random_factors(rng, 300, truth)
+    x = np.array([0, 0, 0, 1, 0, 0, 0.0])
+    for _ in range(6):  # six restarts of <= 4 iterations, as the outer loop does
+        x, tr = orc.solve(F, x)
+    assert np.linalg.norm(x[4:] - truth[4:]) < 0.01 and 2 * np.arccos(min(1, abs(x[:4] @ truth[:4]))) < 0.005
+
+    def fun(p):
+        xx = np.r_[R.from_rotvec(p[:3]).as_quat(), p[3:]]
+        out = []
+        for f in F:
+            r, _ = orc.eval_factor(f, xx)
+            s = r @ r
+            rho = s if s <= 0.01 else 0.2 * np.sqrt(s) - 0.01   # Huber(0.1) per residual block
+            out.append(np.sqrt(rho))
+        return np.array(out)
+    sol = least_squares(fun, np.zeros(6), method="trf", xtol=1e-12, ftol=1e-12)
+    xs = np.r_[R.from_rotvec(sol.x[:3]).as_quat(), sol.x[3:]]
+    assert np.linalg.norm(x[4:] - xs[4:]) < 2e-3 and 2 * np.arccos(min(1, abs(x[:4] @ xs[:4]))) < 1e-3
+    assert tr[-1, 7] <= 0.5 * sol.cost * 2 * 1.001 + 1e-9  # our cost (1/2 sum rho) is not above scipy's optimum
+
+
+def test_lm_control_flow_flags(orc):
+    rng = np.random.default_rng(7)
+    truth = np.array([0, 0, 0, 1, 0.2, 0, 0.0])
+    F = _random_factors(rng, 100, truth)
+    x, tr = orc.solve(F, np.array([0, 0, 0, 1, 0, 0, 0.0]))
+    assert int(tr[0, 9]) & 32 and all(int(f) & 1 for f in tr[1:, 9])   # row 0 = initial evaluation, then valid steps
+    assert np.all(np.diff(tr[:, 7]) <= 1e-12)                           # monotone cost
+    x2, tr2 = orc.solve(np.zeros((0, 14)), truth)
+    assert np.array_equal(x2, truth) and len(tr2) == 1
+
+
+# ---- the whole path ---------------------------------------------------------------------------------------------------------
+def test_pipeline_tracks_ground_truth():
+    s, o = Synth(), Oracle()
+    for k in range(8):
+        pts, gt = s.sweep(64, 1, k)
+        st, odo, mp = o.step(pts)
+        assert np.linalg.norm(mp[4:] - gt[4:]) < 0.15, (k, mp, gt)
+    assert np.linalg.norm(gt[4:]) > 6.0
+
+
+def test_extraction_invariants(feats):
+    f = feats
+    rings = np.floor(f["full"][:, 3]).astype(int)
+    assert np.all(np.diff(rings) >= 0) and rings.min() >= 0 and rings.max() <= 50       # ring-ordered, rings 0..50 only
+    rel = f["full"][:, 3] - rings
+    assert rel.min() >= -1e-6 and rel.max() <= 0.1001
+    assert len(f["sharp"]) <= 2 * 6 * 51 and len(f["less_sharp"]) <= 20 * 6 * 51 and len(f["flat"]) <= 4 * 6 * 51
+    assert set(np.unique(f["label"])) <= {-1, 0, 1, 2}
+    assert (f["label"] == 2).sum() == len(f["sharp"]) and (f["label"] >= 1).sum() == len(f["less_sharp"]) and (f["label"] == -1).sum() == len(f["flat"])
+    # every sharp point is also the head of its sector in the less-sharp list
+    ls = {tuple(p) for p in f["less_sharp"].view(np.uint32).tolist()}
+    assert all(tuple(p) in ls for p in f["sharp"].view(np.uint32).tolist())
+    for start, end in zip(f["scan_start"], f["scan_end"]):
+        if end - start >= 6:
+            for j in range(6):
+                sp, ep = start + (end - start) * j // 6, start + (end - start) * (j + 1) // 6 - 1
+                idx = f["sort_ind"][sp:ep + 1]
+                c = f["curvature"][idx]
+                assert np.all(np.diff(c) >= 0) and sorted(idx) == list(range(sp, ep + 1))
+
+
+def test_oracle_reproduces_golden_fixture():
+    g = np.load(GOLD)
+    o = Oracle(16, 0.3, 0.2, 0.4)
+    for k in range(3):
+        pts = np.concatenate([g[f"sweep{k}"], np.zeros((len(g[f"sweep{k}"]), 1), np.float32)], 1)
+        f = o.extract(pts)
+        for name in ("full", "sharp", "less_sharp", "flat", "less_flat"):
+            assert len(f[name]) == int(g[f"f{k}_{name}_n"]) and np.array_equal(sha(f[name]), g[f"f{k}_{name}_sha"]), (k, name)
+        assert np.array_equal(sha(f["label"]), g[f"f{k}_label_sha"]) and np.array_equal(sha(f["curvature"]), g[f"f{k}_curvature_sha"])
+        st, rel, w = o.odometry(f["sharp"], f["less_sharp"], f["flat"], f["less_flat"])
+        assert st == int(g[f"odo{k}_status"]) and np.allclose(rel, g[f"odo{k}_rel"], atol=1e-12) and np.allclose(w, g[f"odo{k}_world"], atol=1e-12)
+        if k > 0:
+            assert np.array_equal(o.odometry_log(0)["corner_corr"], g[f"odo{k}_corner_corr0"])
+        st, pose, _ = o.mapping(f["less_sharp"], f["less_flat"], f["full"], w)
+        assert st == int(g[f"map{k}_status"]) and np.allclose(pose, g[f"map{k}_pose"], atol=1e-12)
+        assert np.array_equal(sha(o.mapping_info()["corner_stack"]), g[f"map{k}_corner_stack_sha"])
