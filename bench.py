@@ -108,6 +108,46 @@ def max_over_ranks(values, world, device="cuda"):
     return [float(v) for v in t]
 
 
+def knn_throughput(L, frames, reps, device):
+    """SURVEY §8d throughput mode of the graded kernel: `frames` x (corner, surf) 5-NN problems of config-3 size
+    (~100 k corner + ~390 k surf map points, ~8 k queries per frame) in ONE launch, >= 1 GiB of map data, cold L2."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    ax = torch.arange(-125.0, 125.0, 0.4, device="cuda")
+    gx, gy = torch.meshgrid(ax, ax, indexing="ij")
+    n_s = gx.numel()
+    surf = torch.stack([gx.reshape(-1), gy.reshape(-1), torch.full((n_s,), -1.73, device="cuda"), torch.zeros(n_s, device="cuda")], 1)
+    surf[:, :2] += (torch.rand(n_s, 2, device="cuda", generator=g) - 0.5) * 0.3
+    surf[:, 2] += torch.randn(n_s, device="cuda", generator=g) * 0.02
+    nl = 4000
+    lx = (torch.rand(nl, 2, device="cuda", generator=g) - 0.5) * 250.0
+    lz = torch.arange(-1.7, 8.3, 0.4, device="cuda")
+    corner = torch.cat([lx[:, None, :].expand(nl, len(lz), 2), lz[None, :, None].expand(nl, len(lz), 1), torch.zeros(nl, len(lz), 1, device="cuda")], 2).reshape(-1, 4).contiguous()
+    r = torch.rand(3000, device="cuda", generator=g).sqrt() * 40.0
+    th = torch.rand(3000, device="cuda", generator=g) * 6.2831853
+    q_s = torch.stack([r * torch.cos(th), r * torch.sin(th), torch.full((3000,), -1.70, device="cuda"), torch.zeros(3000, device="cuda")], 1)
+    near = corner[(corner[:, 0].abs() < 60) & (corner[:, 1].abs() < 60)]
+    q_c = near[torch.randint(0, len(near), (5000,), device="cuda", generator=g)].clone()
+    q_c[:, :3] += torch.randn(5000, 3, device="cuda", generator=g) * 0.1
+    maps, queries, mc, qc = [], [], [], []
+    for f in range(frames):
+        off = torch.tensor([0.013 * f, -0.007 * f, 0.0, 0.0], device="cuda")
+        for m, q in ((corner, q_c), (surf, q_s)):
+            maps.append(m + off); queries.append(q + off); mc.append(len(m)); qc.append(len(q))
+    maps = torch.cat(maps).contiguous(); queries = torch.cat(queries).contiguous()
+    ind = torch.empty((len(queries), 5), dtype=torch.int32, device="cuda")
+    sq = torch.empty((len(queries), 5), dtype=torch.float32, device="cuda")
+    ctx = L.Lvo(lanes=1, device=device, max_points=65536, max_map_corner=1 << 16, max_map_surf=1 << 16)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ms = ctx.knn5_throughput(maps.data_ptr(), mc, queries.data_ptr(), qc, reps, ind.data_ptr(), sq.data_ptr())
+    ctx.close()
+    alg = 16.0 * sum(mc) + 56.0 * sum(qc)
+    found = float((ind[:, 0] >= 0).float().mean())
+    return {"problems": len(mc), "map_points_total": int(sum(mc)), "queries_total": int(sum(qc)), "map_bytes": 16 * int(sum(mc)), "kernel_ms": ms,
+            "algorithmic_bytes_per_launch": alg, "achieved_gbs": alg / 1e9 / (ms * 1e-3), "queries_with_5_neighbours": found, "reps": reps}
+
+
 def run_reference(args, rank, world):
     """CPU oracle with all host threads: one independent sequence per thread."""
     if rank != 0:
@@ -155,6 +195,8 @@ def main():
     ap.add_argument("--cpu-sample-frames", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: only the device-resident arm")
+    ap.add_argument("--knn-frames", type=int, default=128, help="throughput-mode 5-NN: number of config-3 frames in one launch (0 = skip)")
+    ap.add_argument("--only-knn", action="store_true", help="profiling aid: only the throughput-mode 5-NN measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -174,6 +216,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L = load_pkg()
+    if args.only_knn:
+        print(json.dumps({"knn_throughput": knn_throughput(L, args.knn_frames, 5, local_rank)}), flush=True)
+        return
     lanes = args.lanes
     total = args.warmup + args.steps
     n_seq = min(lanes, 8)
@@ -271,6 +316,12 @@ def main():
     peak, peak_src = measured_peak_gbs()
     achieved = (knn_bytes / 1e9) / (knn_ms * 1e-3) if knn_ms > 0 else 0.0
 
+    knn_tp = None
+    if rank == 0 and world == 1 and args.knn_frames > 0:
+        del dev
+        torch.cuda.empty_cache()
+        knn_tp = knn_throughput(L, args.knn_frames, 5, local_rank)
+        knn_tp["frac"] = knn_tp["achieved_gbs"] / peak
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle_py import Oracle
@@ -298,7 +349,7 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": "k_map_knn (5-NN grid search, thread per query)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src, "launches": knn_launches,
                              "avg_launch_us": 1e3 * knn_ms / max(knn_launches, 1), "algorithmic_bytes_per_launch": knn_bytes / max(knn_launches, 1)},
-                "cpu_baseline": cpu, "clocks": clocks,
+                "knn_throughput": knn_tp, "cpu_baseline": cpu, "clocks": clocks,
                 "host": {"wall_ms_per_step_dev": 1e3 * wall_d / args.steps, "wall_ms_per_step_e2e": 1e3 * wall_e / args.steps, "gen_s": t_gen, "cores": host_threads}}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -286,6 +286,16 @@ class Lvo:
             return raw.view(np.int32).reshape(O, -1).copy()
         raise KeyError(what)
 
+    def knn5_throughput(self, d_maps_ptr, map_counts, d_queries_ptr, query_counts, reps, d_ind_ptr, d_sq_ptr):
+        """S problems in one launch (device pointers in, device outputs); returns average kernel milliseconds."""
+        S = len(map_counts)
+        mc = (C.c_int * S)(*[int(x) for x in map_counts])
+        qc = (C.c_int * S)(*[int(x) for x in query_counts])
+        ms = C.c_float(0)
+        self._check(self.lib.lvo_knn5_throughput(self.h, C.c_void_p(d_maps_ptr), mc, C.c_void_p(d_queries_ptr), qc, S, reps, C.c_void_p(d_ind_ptr),
+                                                 C.c_void_p(d_sq_ptr), C.byref(ms)))
+        return ms.value
+
     # ---- stand-alone operators
     def voxel_downsample(self, pts, leaf):
         v, keep = view_of(pts)

@@ -435,3 +435,21 @@ __global__ void k_knn_queries(GridSet gs, const float4* __restrict__ q, int nq, 
     }
   }
 }
+
+// Throughput form: S independent (map, query set) problems in ONE launch, blockIdx.y = problem.
+// One thread per query; q_off[p] is the offset of problem p's queries in the concatenated query / output arrays.
+__global__ void __launch_bounds__(128) k_knn5_batch(GridSet gs, const float4* __restrict__ q, const unsigned* __restrict__ q_off, float max_sq,
+                                                    int* __restrict__ ind, float* __restrict__ sq) {
+  const int p = blockIdx.y;
+  const GridView g = grid_view(gs, p);
+  const unsigned b = q_off[p], n = q_off[p + 1] - b;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 v = __ldg(q + b + i);
+    TopK<5> tk;
+    const bool ok = thread_knn<5>(g, v.x, v.y, v.z, max_sq, tk);
+    int* o = ind + (size_t)(b + i) * 5;
+    float* d = sq + (size_t)(b + i) * 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { o[k] = ok ? tk.id[k] : -1; d[k] = ok ? tk.d[k] : INFINITY; }
+  }
+}

@@ -91,3 +91,28 @@ def test_knn_ties_and_edges(ctx):
     assert (got_i == -1).all()
     got_i, _ = ctx.knn(cloud[:3], q, 5, 1.0)
     assert (got_i == -1).all()
+
+
+def test_knn5_throughput_entry_matches_oracle(lvo_mod):
+    """lvo_knn5_throughput: several independent (map, query) problems in one launch; every problem checked against the oracle."""
+    import torch
+    O = Oracle()
+    rng = np.random.default_rng(11)
+    maps, queries, mc, qc = [], [], [], []
+    for p in range(5):
+        m = np.concatenate([(rng.random((4000 + 500 * p, 3)) * [30, 30, 3] + [10 * p, -5, 0]).astype(np.float32), np.zeros((4000 + 500 * p, 1), np.float32)], 1)
+        q = m[rng.choice(len(m), 700, replace=False)] + np.array([0.1, 0.05, -0.02, 0], np.float32)
+        maps.append(m); queries.append(q); mc.append(len(m)); qc.append(len(q))
+    dm, dq = torch.from_numpy(np.concatenate(maps)).cuda(), torch.from_numpy(np.concatenate(queries)).cuda()
+    ind = torch.empty((len(dq), 5), dtype=torch.int32, device="cuda")
+    sq = torch.empty((len(dq), 5), dtype=torch.float32, device="cuda")
+    ctx = lvo_mod.Lvo(max_points=1 << 16, max_map_corner=1 << 16, max_map_surf=1 << 16)
+    ms = ctx.knn5_throughput(dm.data_ptr(), mc, dq.data_ptr(), qc, 2, ind.data_ptr(), sq.data_ptr())
+    assert ms > 0
+    got_i, got_d = ind.cpu().numpy(), sq.cpu().numpy()
+    o = 0
+    for m, q in zip(maps, queries):
+        ref_i, ref_d = O.knn(m, q, 5, 1.0, method=0)
+        assert np.array_equal(got_i[o:o + len(q)], ref_i) and np.array_equal(_bits(got_d[o:o + len(q)]), _bits(ref_d))
+        o += len(q)
+    ctx.close()
