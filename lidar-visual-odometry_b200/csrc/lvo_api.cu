@@ -115,23 +115,26 @@ __global__ void k_init_lanes(LaneState* ls, int lanes) {
   s.para_q[3] = 1.0; s.q_w[3] = 1.0; s.map_x[3] = 1.0; s.q_wmap_wodom[3] = 1.0; s.q_wodom[3] = 1.0;
   s.cen[0] = 10; s.cen[1] = 10; s.cen[2] = 5;  // laserMapping.cpp:74-76
 }
-// which == 0: odometry, 6 problems per lane (corner / surf fine xyz, corner / surf ring-azimuth, corner / surf coarse xyz);
+// which == 0: odometry, 8 problems per lane (corner / surf fine xyz, ring-azimuth, middle xyz, coarse xyz);
 // which == 1: mapping, 2 problems per lane (corner / surf FromMap)
 __global__ void k_setup_grid_problems(GridProblem* prob, int nprob, const float4* base0, size_t stride0, const float4* base1, size_t stride1,
                                       LaneState* ls, int which, float cell) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nprob) return;
-  const int per = which == 0 ? 6 : 2;
+  const int per = which == 0 ? 8 : 2;
   const int lane = p / per, t = p & 1;
   prob[p].pts = (t ? base1 + (size_t)lane * stride1 : base0 + (size_t)lane * stride0);
   if (which == 0) prob[p].d_n = t ? &ls[lane].n_surf_last : &ls[lane].n_corner_last;
   else prob[p].d_n = &ls[lane].from_off[t][LVO_MAX_VALID];
   const int k = p % per;
-  prob[p].want_cell = (which == 0 && k >= 4) ? 4.0f * cell : cell;   // odometry: fine + coarse xyz grids
+  // odometry: fine grid 0.5 x 0.5 x 2 m for the surf cloud (dense in x-y, sparse in z), 1 x 1 x 2 m for the corner cloud,
+  // middle grids 2 m, coarse grids 8 m
+  prob[p].want_cell = which == 0 ? (k >= 6 ? 8.0f : (k >= 4 ? 2.0f : (k == 1 ? 0.5f : 1.0f))) : cell;
+  prob[p].want_cell_z = which == 0 ? (k >= 6 ? 8.0f : 2.0f) : 0.f;
   prob[p].mode = (which == 0 && (k == 2 || k == 3)) ? 1 : 0;
 }
 __global__ void k_setup_one_problem(GridProblem* prob, const float4* pts, const int* d_n, float cell) {
-  prob[0].pts = pts; prob[0].d_n = d_n; prob[0].want_cell = cell; prob[0].mode = 0;
+  prob[0].pts = pts; prob[0].d_n = d_n; prob[0].want_cell = cell; prob[0].want_cell_z = 0.f; prob[0].mode = 0;
 }
 __global__ void k_vx_single_setup(VoxelEngine e, int n, float leaf) {
   if (blockIdx.x == 0 && threadIdx.x == 0) { *e.d_n = n; *e.d_nsegs = 1; e.seg_leaf[0] = leaf; }
@@ -296,8 +299,8 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
   LVO_TRY(dalloc(c, &od.factors, (size_t)L * od.factor_cap));
   LVO_TRY(dalloc(c, &od.corner_corr, (size_t)L * LVO_MAX_OUTER * c->cap_sharp * 2));
   LVO_TRY(dalloc(c, &od.plane_corr, (size_t)L * LVO_MAX_OUTER * c->cap_flat * 3));
-  LVO_TRY(alloc_grid(c, &od.grid, 6 * L, 1 << 21, (size_t)3 * L * (c->cap_lsharp + P), P));
-  k_setup_grid_problems<<<lvo_div_up(6 * L, 64), 64, 0, c->st>>>(od.grid.prob, 6 * L, od.corner_last, (size_t)c->cap_lsharp, od.surf_last, (size_t)P, c->d_ls, 0, 1.0f);
+  LVO_TRY(alloc_grid(c, &od.grid, 8 * L, 1 << 22, (size_t)4 * L * (c->cap_lsharp + P), P));
+  k_setup_grid_problems<<<lvo_div_up(8 * L, 64), 64, 0, c->st>>>(od.grid.prob, 8 * L, od.corner_last, (size_t)c->cap_lsharp, od.surf_last, (size_t)P, c->d_ls, 0, 1.0f);
 
   // ---- mapping
   MapArgs& mp = c->map;
@@ -706,7 +709,7 @@ int lvo_knn(lvo_ctx* c, lvo_cloud_view cloud, lvo_cloud_view queries, int K, flo
 __global__ void k_setup_batch_problems(GridProblem* prob, int S, const float4* maps, const unsigned* m_off, const int* m_cnt, float cell) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= S) return;
-  prob[p].pts = maps + m_off[p]; prob[p].d_n = m_cnt + p; prob[p].want_cell = cell; prob[p].mode = 0;
+  prob[p].pts = maps + m_off[p]; prob[p].d_n = m_cnt + p; prob[p].want_cell = cell; prob[p].want_cell_z = 0.f; prob[p].mode = 0;
 }
 
 int lvo_knn5_throughput(lvo_ctx* c, const lvo_point* d_maps, const int* map_counts, const lvo_point* d_queries, const int* query_counts, int S, int reps,

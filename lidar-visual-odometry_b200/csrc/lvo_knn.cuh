@@ -26,10 +26,12 @@
 struct GridProblem {   // device-resident descriptor
   const float4* pts;   // source cloud
   const int* d_n;      // its size (device)
-  float want_cell;     // requested cell size (power of two)
+  float want_cell;     // requested cell size in x and y (power of two)
+  float want_cell_z;   // requested cell size in z (power of two; 0 = same as want_cell)
   int mode;            // 0: uniform xyz grid; 1: (ring, azimuth) grid — cell = ring * LVO_AZ_BUCKETS + azimuth bucket
   // filled by k_grid_setup
-  float cell, inv_cell;
+  float cell, inv_cell;      // x / y cell size (the smallest one: all search bounds use it)
+  float inv_cell_z;
   int org[3], dim[3];
   int ncells;
   unsigned table_off;  // offset of this problem's cells in the shared table
@@ -53,13 +55,13 @@ struct GridSet {
 
 struct GridView {  // what a search needs
   const float4* pts; const int* ids; const unsigned* cell_start;
-  float cell, inv_cell; int org[3], dim[3];
+  float cell, inv_cell, inv_cell_z; int org[3], dim[3];   // cell = the smallest cell edge (x / y); z cells may be taller
 };
 __device__ __forceinline__ GridView grid_view(const GridSet& g, int p) {
   const GridProblem& q = g.prob[p];
   GridView v;
   v.pts = g.sorted_pts; v.ids = g.sorted_id; v.cell_start = g.table + q.table_off;
-  v.cell = q.cell; v.inv_cell = q.inv_cell;
+  v.cell = q.cell; v.inv_cell = q.inv_cell; v.inv_cell_z = q.inv_cell_z;
   for (int c = 0; c < 3; ++c) { v.org[c] = q.org[c]; v.dim[c] = q.dim[c]; }
   return v;
 }
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(256) k_grid_setup(GridSet g) {
     unsigned my_cells = 0, my_pts = 0;
     if (p < g.nprob) {
       GridProblem& q = g.prob[p];
-      float cell = q.want_cell;
+      float cell = q.want_cell, cellz = q.want_cell_z > 0.f ? q.want_cell_z : q.want_cell;
       int org[3] = {0, 0, 0}, dim[3] = {0, 0, 0};
       long long nc = 0;
       if (q.mode == 1) {
@@ -114,18 +116,19 @@ __global__ void __launch_bounds__(256) k_grid_setup(GridSet g) {
         nc = (long long)LVO_AZ_BUCKETS * LVO_AZ_RINGS;
       } else if (q.n > 0) {
         for (int it = 0; it < 40; ++it) {
-          const float inv = 1.0f / cell;
           nc = 1;
           for (int c = 0; c < 3; ++c) {
+            const float inv = 1.0f / (c == 2 ? cellz : cell);
             const int lo = cell_coord(ord2f_k(q.bb_mn[c]), inv), hi = cell_coord(ord2f_k(q.bb_mx[c]), inv);
             org[c] = lo; dim[c] = hi - lo + 1;
             nc *= (long long)dim[c];
           }
           if (nc <= (long long)g.cells_cap_per_problem) break;
           cell *= 2.0f;
+          if (cellz < cell) cellz = cell;
         }
       }
-      q.cell = cell; q.inv_cell = 1.0f / cell;
+      q.cell = cell; q.inv_cell = 1.0f / cell; q.inv_cell_z = 1.0f / cellz;
       for (int c = 0; c < 3; ++c) { q.org[c] = org[c]; q.dim[c] = dim[c]; }
       q.ncells = (int)nc;
       my_cells = (unsigned)nc; my_pts = (unsigned)q.n;
@@ -151,7 +154,7 @@ __device__ __forceinline__ int az_bucket(float x, float y) {
 __device__ __forceinline__ int ring_clamped(float intensity) { return min(max(int(intensity), 0), LVO_AZ_RINGS - 1); }
 __device__ __forceinline__ int grid_cell_of(const GridProblem& q, float4 v) {
   if (q.mode == 1) return ring_clamped(v.w) * LVO_AZ_BUCKETS + az_bucket(v.x, v.y);
-  const int cx = cell_coord(v.x, q.inv_cell) - q.org[0], cy = cell_coord(v.y, q.inv_cell) - q.org[1], cz = cell_coord(v.z, q.inv_cell) - q.org[2];
+  const int cx = cell_coord(v.x, q.inv_cell) - q.org[0], cy = cell_coord(v.y, q.inv_cell) - q.org[1], cz = cell_coord(v.z, q.inv_cell_z) - q.org[2];
   return (cz * q.dim[1] + cy) * q.dim[0] + cx;
 }
 __global__ void k_grid_count(GridSet g) {
@@ -170,8 +173,7 @@ __global__ void k_grid_fill(GridSet g) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 v = q.pts[i];
     const unsigned dst = g.table[q.table_off + grid_cell_of(q, v)] + (unsigned)g.rank[po + i];
-    g.sorted_pts[dst] = v;
-    g.sorted_id[dst] = i;
+    g.sorted_pts[dst] = make_float4(v.x, v.y, v.z, __int_as_float(i));  // w carries the original index: one 16-byte load per candidate
   }
 }
 
@@ -183,7 +185,8 @@ static inline void lvo_grid_build(cudaStream_t st, const GridSet& g, long long* 
   k_grid_setup<<<1, 256, 0, st>>>(g);
   k_grid_zero<<<1184, 256, 0, st>>>(g);
   k_grid_count<<<gp, 256, 0, st>>>(g);
-  lvo_scan_exclusive(st, g.table, g.d_table_len, g.nprob * g.cells_cap_per_problem + 1, nullptr, g.scan, launches);
+  const long long table_cap = (long long)g.nprob * g.cells_cap_per_problem + 1;
+  lvo_scan_exclusive(st, g.table, g.d_table_len, (int)(table_cap < 0x7fffffffLL ? table_cap : 0x7fffffffLL), nullptr, g.scan, launches);
   k_grid_fill<<<gp, 256, 0, st>>>(g);
   if (launches) *launches += 6;
 }
@@ -222,7 +225,7 @@ __device__ __forceinline__ void scan_row(const GridView& g, int cz, int cy, int 
   const unsigned b = g.cell_start[rowbase + x0], e = g.cell_start[rowbase + x1 + 1];
   for (unsigned t = b + ln; t < e; t += 32) {
     const float4 p = g.pts[t];
-    tk.insert(sqdist3(p, qx, qy, qz), g.ids[t]);
+    tk.insert(sqdist3(p, qx, qy, qz), __float_as_int(p.w));
   }
 }
 
@@ -257,7 +260,7 @@ __device__ __forceinline__ bool warp_knn(const GridView& g, float qx, float qy, 
   const unsigned ln = threadIdx.x & 31;
   tk.init();
   if (g.dim[0] <= 0) return false;
-  const int cx = cell_coord(qx, g.inv_cell) - g.org[0], cy = cell_coord(qy, g.inv_cell) - g.org[1], cz = cell_coord(qz, g.inv_cell) - g.org[2];
+  const int cx = cell_coord(qx, g.inv_cell) - g.org[0], cy = cell_coord(qy, g.inv_cell) - g.org[1], cz = cell_coord(qz, g.inv_cell_z) - g.org[2];
   // number of rings that can hold a point inside the gate: points of ring r have d > (r-1)*cell
   int R = (int)ceilf(sqrtf(max_sq) * g.inv_cell);
   if (R < 1) R = 1;
@@ -293,14 +296,14 @@ __device__ __forceinline__ void thread_scan_row(const GridView& g, int cz, int c
   const unsigned b = __ldg(g.cell_start + rowbase + x0), e = __ldg(g.cell_start + rowbase + x1 + 1);
   for (unsigned t = b; t < e; ++t) {
     const float4 p = __ldg(g.pts + t);
-    tk.insert(sqdist3(p, qx, qy, qz), __ldg(g.ids + t));
+    tk.insert(sqdist3(p, qx, qy, qz), __float_as_int(p.w));
   }
 }
 template <int K>
 __device__ __forceinline__ bool thread_knn(const GridView& g, float qx, float qy, float qz, float max_sq, TopK<K>& tk) {
   tk.init();
   if (g.dim[0] <= 0) return false;
-  const int cx = cell_coord(qx, g.inv_cell) - g.org[0], cy = cell_coord(qy, g.inv_cell) - g.org[1], cz = cell_coord(qz, g.inv_cell) - g.org[2];
+  const int cx = cell_coord(qx, g.inv_cell) - g.org[0], cy = cell_coord(qy, g.inv_cell) - g.org[1], cz = cell_coord(qz, g.inv_cell_z) - g.org[2];
   int R = (int)ceilf(sqrtf(max_sq) * g.inv_cell);
   if (R < 1) R = 1;
   // rings 0 and 1: fetch the 9 row ranges first (independent loads), then stream the candidates
@@ -319,7 +322,7 @@ __device__ __forceinline__ bool thread_knn(const GridView& g, float qx, float qy
   for (int k = 0; k < 9; ++k)
     for (unsigned t = rb[k]; t < re[k]; ++t) {
       const float4 p = __ldg(g.pts + t);
-      tk.insert(sqdist3(p, qx, qy, qz), __ldg(g.ids + t));
+      tk.insert(sqdist3(p, qx, qy, qz), __float_as_int(p.w));
     }
   for (int r = 2; r <= R; ++r) {
     const float bound = (float)(r - 1) * g.cell;
@@ -354,6 +357,65 @@ __device__ __forceinline__ void warp_scan_ranges(unsigned b, unsigned e, F&& f) 
     if (k < total) f(rb + (k - (ri - rl)), r);
   }
 }
+// ---------------------------------------------------------------------------------------------------------------
+// 8-lane tiles: four queries per warp.  Every primitive below is executed by all 32 lanes (full-mask shuffles with
+// width 8); a tile that has nothing to do passes empty ranges.  This shares all per-query overhead (bounds, prefix
+// sums, reductions, control flow) between four queries, which is what the latency-bound association kernels need.
+// ---------------------------------------------------------------------------------------------------------------
+#define LVO_TW 8
+__device__ __forceinline__ unsigned tile_lane() { return threadIdx.x & (LVO_TW - 1); }
+__device__ __forceinline__ unsigned tile_incl_scan(unsigned v) {
+  const unsigned tl = tile_lane();
+#pragma unroll
+  for (int o = 1; o < LVO_TW; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, v, o, LVO_TW);
+    if (tl >= (unsigned)o) v += t;
+  }
+  return v;
+}
+// lane j of the tile holds range [b, e) (possibly empty); f(t, r) is called for candidate t of range r
+// f(p, r): candidate point p (w = original index) of range r.  Software-pipelined: the candidate of step k+1 is
+// fetched before step k is processed, so two loads per lane are in flight.
+template <class F>
+__device__ __forceinline__ void tile_scan_ranges(const float4* __restrict__ pts, unsigned b, unsigned e, F&& f) {
+  const unsigned tl = tile_lane();
+  const unsigned len = e > b ? e - b : 0u;
+  const unsigned incl = tile_incl_scan(len);
+  const unsigned total = __shfl_sync(0xffffffffu, incl, LVO_TW - 1, LVO_TW);
+  auto locate = [&](unsigned k, int& r) -> unsigned {
+    r = 0;
+#pragma unroll
+    for (int j = 0; j < LVO_TW - 1; ++j) r += (k >= __shfl_sync(0xffffffffu, incl, j, LVO_TW)) ? 1 : 0;
+    const unsigned rb = __shfl_sync(0xffffffffu, b, r, LVO_TW), ri = __shfl_sync(0xffffffffu, incl, r, LVO_TW), rl = __shfl_sync(0xffffffffu, len, r, LVO_TW);
+    return rb + (k - (ri - rl));
+  };
+  if (!__any_sync(0xffffffffu, total > 0)) return;
+  int r_cur, r_nxt = 0;
+  unsigned t = locate(tl, r_cur);
+  bool v_cur = tl < total;
+  float4 p_cur = make_float4(0.f, 0.f, 0.f, 0.f), p_nxt = p_cur;
+  if (v_cur) p_cur = __ldg(pts + t);
+  for (unsigned k0 = 0; __any_sync(0xffffffffu, k0 < total); k0 += LVO_TW) {
+    const unsigned kn = k0 + LVO_TW + tl;
+    const bool v_nxt = kn < total;
+    if (__any_sync(0xffffffffu, k0 + LVO_TW < total)) {
+      const unsigned tn = locate(kn, r_nxt);
+      if (v_nxt) p_nxt = __ldg(pts + tn);
+    }
+    if (v_cur) f(p_cur, r_cur);
+    p_cur = p_nxt; r_cur = r_nxt; v_cur = v_nxt;
+  }
+}
+// (d, key) lexicographic minimum over the tile, payload j
+__device__ __forceinline__ void tile_min3(float& d, int& key, int& j) {
+#pragma unroll
+  for (int o = LVO_TW / 2; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, d, o, LVO_TW);
+    const int ok = __shfl_xor_sync(0xffffffffu, key, o, LVO_TW), oj = __shfl_xor_sync(0xffffffffu, j, o, LVO_TW);
+    if (od < d || (od == d && ok < key)) { d = od; key = ok; j = oj; }
+  }
+}
+
 // bounds of the x-row (cz, cy, x0..x1) of a grid, empty when outside
 __device__ __forceinline__ void row_bounds(const GridView& g, int cz, int cy, int x0, int x1, unsigned& b, unsigned& e) {
   b = e = 0;
@@ -371,22 +433,19 @@ __device__ __forceinline__ bool warp_nn1_two_level(const GridView& gf, const Gri
   float d = FLT_MAX; int id = INT_MAX;
   auto consider = [&](const GridView& g, unsigned t) {
     const float4 p = __ldg(g.pts + t);
-    const int i = __ldg(g.ids + t);
+    const int i = __float_as_int(p.w);
     const float dd = sqdist3(p, qx, qy, qz);
     if (dd < d || (dd == d && i < id)) { d = dd; id = i; }
   };
-  auto reduce = [&]() {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float od = __shfl_xor_sync(0xffffffffu, d, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, id, o);
-      if (od < d || (od == d && oi < id)) { d = od; id = oi; }
-    }
+  auto reduce = [&]() {  // (d, id) lexicographic minimum over the warp with two REDUX instructions (d >= 0: bit order = value order)
+    const unsigned md = __reduce_min_sync(0xffffffffu, __float_as_uint(d));
+    const unsigned mi = __reduce_min_sync(0xffffffffu, __float_as_uint(d) == md ? (unsigned)id : 0xffffffffu);
+    d = __uint_as_float(md); id = (int)mi;
   };
   for (int level = 0; level < 2; ++level) {
     const GridView& g = level ? gc : gf;
     if (g.dim[0] <= 0) continue;
-    const int cx = cell_coord(qx, g.inv_cell) - g.org[0], cy = cell_coord(qy, g.inv_cell) - g.org[1], cz = cell_coord(qz, g.inv_cell) - g.org[2];
+    const int cx = cell_coord(qx, g.inv_cell) - g.org[0], cy = cell_coord(qy, g.inv_cell) - g.org[1], cz = cell_coord(qz, g.inv_cell_z) - g.org[2];
     unsigned b = 0, e = 0;
     if (ln < 9) row_bounds(g, cz + (int)ln / 3 - 1, cy + (int)ln % 3 - 1, cx - 1, cx + 1, b, e);
     warp_scan_ranges<9>(b, e, [&](unsigned t, int) { consider(g, t); });

@@ -2,7 +2,7 @@
 // (DISTORTION 0, :67).
 //
 //   k_odo_begin      first-frame handling (:355-358), per-outer-iteration counter reset
-//   k_odo_assoc      one warp per feature: TransformToStart (:154-172, s = 1), 1-NN in the previous sweep's
+//   k_odo_assoc      one 8-lane tile per feature (4 features per warp): TransformToStart (:154-172, s = 1), 1-NN in the previous sweep's
 //                    less-sharp / less-flat cloud on the uniform grid with the d^2 < 25 gate (:386-389, :470-473),
 //                    then the adjacent-ring searches of :395-440 / :481-532 as ring-filtered nearest-neighbour searches
 //                    on the same grid (the clouds are ring-ordered by construction), with the reference's walk order
@@ -24,7 +24,7 @@ struct OdoArgs {
   int cap_sharp, cap_lsharp, cap_flat, P;
   // previous sweep
   float4* corner_last; float4* surf_last;  // [lanes][cap_lsharp], [lanes][P]
-  GridSet grid;                            // problems 6*lane + {0 corner fine xyz, 1 surf fine xyz, 2 corner (ring,azimuth), 3 surf (ring,azimuth), 4 corner coarse xyz, 5 surf coarse xyz}
+  GridSet grid;                            // problems 8*lane + {0/1 corner/surf fine xyz, 2/3 corner/surf (ring,azimuth), 4/5 corner/surf middle xyz, 6/7 corner/surf coarse xyz}
   LvoFactor* factors; int factor_cap;
   int* corner_corr;  // [lanes][LVO_MAX_OUTER][cap_sharp][2]   probes
   int* plane_corr;   // [lanes][LVO_MAX_OUTER][cap_flat][3]
@@ -40,14 +40,16 @@ __global__ void k_odo_begin(OdoArgs a) {
 
 struct Best { float d; int pos; int j; };
 __device__ __forceinline__ Best best_min(Best a, Best b) { return (b.d < a.d || (b.d == a.d && b.pos < a.pos)) ? b : a; }
+// (d, pos) lexicographic minimum over the warp: two REDUX + ballot + shuffle (d >= 0 so its bit pattern orders like its value)
 __device__ __forceinline__ Best warp_best(Best v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    Best w;
-    w.d = __shfl_xor_sync(0xffffffffu, v.d, o); w.pos = __shfl_xor_sync(0xffffffffu, v.pos, o); w.j = __shfl_xor_sync(0xffffffffu, v.j, o);
-    v = best_min(v, w);
-  }
-  return v;
+  const unsigned md = __reduce_min_sync(0xffffffffu, __float_as_uint(v.d));
+  const bool dmin = __float_as_uint(v.d) == md;
+  const unsigned mp = __reduce_min_sync(0xffffffffu, dmin ? (unsigned)v.pos : 0xffffffffu);
+  const unsigned who = __ballot_sync(0xffffffffu, dmin && (unsigned)v.pos == mp);
+  const int src = __ffs(who) - 1;
+  Best r;
+  r.d = __uint_as_float(md); r.pos = (int)mp; r.j = __shfl_sync(0xffffffffu, v.j, src);
+  return r;
 }
 
 // The adjacent-ring searches of :395-440 / :481-532.  The reference walks the ring-ordered cloud upwards from the
@@ -78,81 +80,147 @@ __device__ __forceinline__ int az_halfwidth(float d2, float rho) {
   const float w = asinf(d / rho);
   return (int)ceilf(w * ((float)LVO_AZ_BUCKETS / 6.28318548f)) + 2;
 }
-// one warp per feature
-__device__ __forceinline__ void ring_search(const GridView& g, float4 sel, int closest, int cid, bool needA, int& outA, int& outB) {
-  const int ln = threadIdx.x & 31;
-  Best bA{25.0f, INT_MAX, -1}, bB{25.0f, INT_MAX, -1};
-  const int bq = az_bucket(sel.x, sel.y);
-  const float rho = sqrtf(sel.x * sel.x + sel.y * sel.y);
-  auto consider = [&](unsigned t, int ring) {
-    const float4 p = __ldg(g.pts + t);
-    const int idx = __ldg(g.ids + t);
-    const int dr = ring - cid;
-    if (idx == closest) return;
-    // the walk is monotone in the ring id: above `closest` it only meets rings >= cid, below it rings <= cid
-    if ((idx > closest && dr < 0) || (idx < closest && dr > 0)) return;
-    const float d = (p.x - sel.x) * (p.x - sel.x) + (p.y - sel.y) * (p.y - sel.y) + (p.z - sel.z) * (p.z - sel.z);
-    if (!(d < 25.0f)) return;
-    const int key = idx > closest ? (idx - closest) : ((closest - idx) + (1 << 30));
-    const Best c{d, key, idx};
-    if (dr == 0) bA = best_min(bA, c); else bB = best_min(bB, c);
+// ---- one 8-lane tile per feature (four features per warp); every call below is made by all 32 lanes --------------------
+// rows 3k .. 3k+2 (k = part) of the 3x3 row block around (cx, cy, cz): lanes 0..2 of the tile fetch the bounds
+__device__ __forceinline__ void tile_block_nn1(const GridView& g, bool active, float4 sel, float& d, int& id) {
+  const int tl = (int)tile_lane();
+  const int cx = cell_coord(sel.x, g.inv_cell) - g.org[0], cy = cell_coord(sel.y, g.inv_cell) - g.org[1], cz = cell_coord(sel.z, g.inv_cell_z) - g.org[2];
+  auto consider = [&](float4 p, int) {
+    const int i = __float_as_int(p.w);
+    const float dd = sqdist3(p, sel.x, sel.y, sel.z);
+    if (dd < d || (dd == d && i < id)) { d = dd; id = i; }
   };
-  // phase 1: +-2 buckets of rings cid-2 .. cid+2.  lane = ring slot (0..4) * 4 + part
-  {
-    const int slot = ln >> 2, part = ln & 3, ring = cid - 2 + slot;
+  unsigned b = 0, e = 0;
+  if (active && g.dim[0] > 0) row_bounds(g, cz + tl / 3 - 1, cy + tl % 3 - 1, cx - 1, cx + 1, b, e);   // rows 0..7
+  tile_scan_ranges(g.pts, b, e, consider);
+  b = e = 0;
+  if (active && g.dim[0] > 0 && tl == 0) row_bounds(g, cz + 1, cy + 1, cx - 1, cx + 1, b, e);            // row 8
+  tile_scan_ranges(g.pts, b, e, consider);
+}
+// shell r >= 2 of the coarse grid, 8 ranges at a time
+__device__ __forceinline__ void tile_shell_nn1(const GridView& g, bool active, float4 sel, int r, float& d, int& id) {
+  const int tl = (int)tile_lane();
+  const int cx = cell_coord(sel.x, g.inv_cell) - g.org[0], cy = cell_coord(sel.y, g.inv_cell) - g.org[1], cz = cell_coord(sel.z, g.inv_cell_z) - g.org[2];
+  auto consider = [&](float4 p, int) {
+    const int i = __float_as_int(p.w);
+    const float dd = sqdist3(p, sel.x, sel.y, sel.z);
+    if (dd < d || (dd == d && i < id)) { d = dd; id = i; }
+  };
+  const int side = 2 * r + 1, nrows = side * side;
+  for (int base = 0; base < nrows; base += 4) {   // 4 rows per step: lanes 0..3 left / full part, lanes 4..7 right part
+    const int row = base + (tl & 3);
     unsigned b = 0, e = 0;
-    if (slot < 5 && part < 2 && ring >= 0 && ring < LVO_AZ_RINGS && (ring != cid || needA)) az_bounds(g, ring, bq - 2, bq + 2, part, b, e);
-    warp_scan_ranges<20>(b, e, [&](unsigned t, int r) { consider(t, cid - 2 + (r >> 2)); });
-  }
-  bA = warp_best(bA); bB = warp_best(bB);
-  // phase 2: the rest of the window implied by the best distances so far (or by the 5 m gate)
-  {
-    const int hA = needA ? az_halfwidth(bA.d, rho) : 0, hB = az_halfwidth(bB.d, rho);
-    const int slot = ln >> 2, sp = ln & 3, ring = cid - 2 + slot;  // sp: side (bit 1), part (bit 0)
-    unsigned b = 0, e = 0;
-    if (slot < 5 && ring >= 0 && ring < LVO_AZ_RINGS && (ring != cid || needA)) {
-      const int h = ring == cid ? hA : hB;
-      if (h > 2) {
-        if (2 * h + 1 >= LVO_AZ_BUCKETS) { if (sp == 0) az_bounds(g, ring, 0, LVO_AZ_BUCKETS - 1, 0, b, e); }
-        else if ((sp >> 1) == 0) az_bounds(g, ring, bq - h, bq - 3, sp & 1, b, e);
-        else az_bounds(g, ring, bq + 3, bq + h, sp & 1, b, e);
-      }
+    if (active && row < nrows) {
+      const int dz = row / side - r, dy = row % side - r;
+      const bool edge = dz == -r || dz == r || dy == -r || dy == r;
+      if (edge) { if (tl < 4) row_bounds(g, cz + dz, cy + dy, cx - r, cx + r, b, e); }
+      else row_bounds(g, cz + dz, cy + dy, tl < 4 ? cx - r : cx + r, tl < 4 ? cx - r : cx + r, b, e);
     }
-    warp_scan_ranges<20>(b, e, [&](unsigned t, int r) { consider(t, cid - 2 + (r >> 2)); });
+    tile_scan_ranges(g.pts, b, e, consider);
   }
-  bA = warp_best(bA); bB = warp_best(bB);
-  outA = bA.j; outB = bB.j;
 }
 
 __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
+  __shared__ GridView gv[8];
   const int lane = blockIdx.y;
   LaneState& s = a.ls[lane];
   if (!s.odo_inited) return;
+  if (threadIdx.x < 8) gv[threadIdx.x] = grid_view(a.grid, 8 * lane + threadIdx.x);
+  __syncthreads();
   const int ns = s.n_sharp, nf = s.n_flat;
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  const unsigned ln = threadIdx.x & 31;
+  const int tl = (int)tile_lane();
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) / LVO_TW;   // one tile per feature
+  if (__all_sync(0xffffffffu, f >= ns + nf)) return;                // whole warp idle
+  const bool have = f < ns + nf;
+  const bool corner = f < ns;
   const double* q = s.para_q; const double* t = s.para_t;
-  const float4* CL = a.corner_last + (size_t)lane * a.cap_lsharp;
-  const float4* SL = a.surf_last + (size_t)lane * a.P;
-  const GridView gcf = grid_view(a.grid, 6 * lane), gsf = grid_view(a.grid, 6 * lane + 1);
-  const GridView gca = grid_view(a.grid, 6 * lane + 2), gsa = grid_view(a.grid, 6 * lane + 3);
-  const GridView gcc = grid_view(a.grid, 6 * lane + 4), gsc = grid_view(a.grid, 6 * lane + 5);
-  int ncorr_c = 0, ncorr_p = 0;
-  for (int f = wid; f < ns + nf; f += nw) {
-    const bool corner = f < ns;
-    const float4 pt = corner ? a.sharp[(size_t)lane * a.cap_sharp + f] : a.flat[(size_t)lane * a.cap_flat + (f - ns)];
-    const float4 sel = transform_point(q, t, pt);  // TransformToStart
-    float bd; int closest;
-    const bool ok = warp_nn1_two_level(corner ? gcf : gsf, corner ? gcc : gsc, sel.x, sel.y, sel.z, 25.0f, bd, closest);
+  const float4* C = corner ? a.corner_last + (size_t)lane * a.cap_lsharp : a.surf_last + (size_t)lane * a.P;
+  const GridView& gfine = gv[corner ? 0 : 1];
+  const GridView& gaz = gv[corner ? 2 : 3];
+  const GridView& gmid = gv[corner ? 4 : 5];
+  const GridView& gcoarse = gv[corner ? 6 : 7];
+  float4 pt = make_float4(0.f, 0.f, 0.f, 0.f), sel = pt;
+  if (have) {
+    pt = corner ? a.sharp[(size_t)lane * a.cap_sharp + f] : a.flat[(size_t)lane * a.cap_flat + (f - ns)];
+    sel = transform_point(q, t, pt);  // TransformToStart
+  }
+  // ---- closest point (laserOdometry.cpp:386 / :470, gate :389 / :473): the 27 cells around the query on the fine grid
+  // (0.5 m) settle it when the best squared distance is below cell^2; otherwise the middle grid (2 m), then the coarse
+  // grid (8 m, whose 27 cells cover the whole 5 m gate), then coarse shells if the cells had to be enlarged.
+  float d = FLT_MAX; int id = INT_MAX, key;
+  tile_block_nn1(gfine, have, sel, d, id);
+  key = id; tile_min3(d, key, id);
+  bool more = have && !(d < gfine.cell * gfine.cell);
+  if (__any_sync(0xffffffffu, more)) {
+    tile_block_nn1(gmid, more, sel, d, id);
+    key = id; tile_min3(d, key, id);
+    more = more && !(d < gmid.cell * gmid.cell);
+  }
+  if (__any_sync(0xffffffffu, more)) {
+    tile_block_nn1(gcoarse, more, sel, d, id);
+    key = id; tile_min3(d, key, id);
+    more = more && !(d < gcoarse.cell * gcoarse.cell);
+    const int R = (int)ceilf(5.0f * gcoarse.inv_cell);
+    for (int r = 2; r <= R; ++r) {
+      const float bound = (float)(r - 1) * gcoarse.cell;
+      more = more && !(d < bound * bound);
+      if (!__any_sync(0xffffffffu, more)) break;
+      tile_shell_nn1(gcoarse, more, sel, r, d, id);
+      key = id; tile_min3(d, key, id);
+    }
+  }
+  const bool ok = have && id != INT_MAX && (double)d < 25.0;
+  const int closest = ok ? id : 0;
+  float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ok) pj = C[closest];
+  const int cid = ring_clamped(pj.w);
+  // ---- adjacent-ring searches on the (ring, azimuth) grid
+  const bool needA = !corner;
+  Best bA{25.0f, INT_MAX, -1}, bB{25.0f, INT_MAX, -1};
+  const int bq = az_bucket(sel.x, sel.y);
+  const float rho = sqrtf(sel.x * sel.x + sel.y * sel.y);
+  auto consider = [&](float4 p, int r) {   // range r <-> ring cid - 2 + r
+    const int idx = __float_as_int(p.w);
+    const int dr = r - 2;
+    if (idx == closest) return;
+    // the walk is monotone in the ring id: above `closest` it only meets rings >= cid, below it rings <= cid
+    if ((idx > closest && dr < 0) || (idx < closest && dr > 0)) return;
+    const float dd = (p.x - sel.x) * (p.x - sel.x) + (p.y - sel.y) * (p.y - sel.y) + (p.z - sel.z) * (p.z - sel.z);
+    if (!(dd < 25.0f)) return;
+    const int k2 = idx > closest ? (idx - closest) : ((closest - idx) + (1 << 30));
+    const Best c{dd, k2, idx};
+    if (dr == 0) bA = best_min(bA, c); else bB = best_min(bB, c);
+  };
+  const int ring = cid - 2 + tl;   // lanes 0..4 of the tile own rings cid-2 .. cid+2
+  const bool ring_ok = ok && tl < 5 && ring >= 0 && ring < LVO_AZ_RINGS && (ring != cid || needA);
+  for (int part = 0; part < 2; ++part) {   // phase 1: +-2 buckets (part 1 only exists when the window wraps)
+    unsigned b = 0, e = 0;
+    if (ring_ok) az_bounds(gaz, ring, bq - 2, bq + 2, part, b, e);
+    tile_scan_ranges(gaz.pts, b, e, consider);
+  }
+  tile_min3(bA.d, bA.pos, bA.j); tile_min3(bB.d, bB.pos, bB.j);
+  {  // phase 2: the rest of the window implied by the best distances so far (or by the 5 m gate)
+    const int h = ring == cid ? (needA ? az_halfwidth(bA.d, rho) : 0) : az_halfwidth(bB.d, rho);
+    const bool whole = 2 * h + 1 >= LVO_AZ_BUCKETS;
+    for (int sp = 0; sp < 4; ++sp) {   // side (bit 1), part (bit 0)
+      unsigned b = 0, e = 0;
+      if (ring_ok && h > 2) {
+        if (whole) { if (sp == 0) az_bounds(gaz, ring, 0, LVO_AZ_BUCKETS - 1, 0, b, e); }
+        else if ((sp >> 1) == 0) az_bounds(gaz, ring, bq - h, bq - 3, sp & 1, b, e);
+        else az_bounds(gaz, ring, bq + 3, bq + h, sp & 1, b, e);
+      }
+      tile_scan_ranges(gaz.pts, b, e, consider);
+    }
+  }
+  tile_min3(bA.d, bA.pos, bA.j); tile_min3(bB.d, bB.pos, bB.j);
+  const int same = bA.j, other = bB.j;
+  // ---- factor record (tile leader)
+  bool made_c = false, made_p = false;
+  if (have && tl == 0) {
     LvoFactor fac;
     fac.type = -1; fac.pad = 0; fac.d = 0;
     int i1 = -1, i2 = -1, i3 = -1;
     if (ok) {
-      const float4* C = corner ? CL : SL;
-      const float4 pj = C[closest];
-      const int cid = ring_clamped(pj.w);
-      int same = -1, other = -1;
-      ring_search(corner ? gca : gsa, sel, closest, cid, !corner, same, other);
       if (corner) {
         if (other >= 0) {
           i1 = closest; i2 = other;
@@ -176,22 +244,21 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
         fac.b[0] = n.x / nn; fac.b[1] = n.y / nn; fac.b[2] = n.z / nn;
       }
     }
-    if (ln == 0) {
-      a.factors[(size_t)lane * a.factor_cap + f] = fac;
-      if (corner) {
-        int* c = a.corner_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer) * a.cap_sharp + f) * 2;
-        c[0] = i1; c[1] = i2;
-        if (fac.type >= 0) ncorr_c++;
-      } else {
-        int* c = a.plane_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer) * a.cap_flat + (f - ns)) * 3;
-        c[0] = i1; c[1] = i2; c[2] = i3;
-        if (fac.type >= 0) ncorr_p++;
-      }
+    a.factors[(size_t)lane * a.factor_cap + f] = fac;
+    if (corner) {
+      int* c = a.corner_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer) * a.cap_sharp + f) * 2;
+      c[0] = i1; c[1] = i2;
+      made_c = fac.type >= 0;
+    } else {
+      int* c = a.plane_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer) * a.cap_flat + (f - ns)) * 3;
+      c[0] = i1; c[1] = i2; c[2] = i3;
+      made_p = fac.type >= 0;
     }
   }
-  if (ln == 0) {
-    if (ncorr_c) atomicAdd(&s.stats.odo_corner_corr[a.outer], ncorr_c);
-    if (ncorr_p) atomicAdd(&s.stats.odo_plane_corr[a.outer], ncorr_p);
+  const int nc = __popc(__ballot_sync(0xffffffffu, made_c)), np = __popc(__ballot_sync(0xffffffffu, made_p));
+  if ((threadIdx.x & 31) == 0) {
+    if (nc) atomicAdd(&s.stats.odo_corner_corr[a.outer], nc);
+    if (np) atomicAdd(&s.stats.odo_plane_corr[a.outer], np);
   }
 }
 
@@ -239,7 +306,7 @@ static inline void lvo_launch_odometry(cudaStream_t st, OdoArgs a, const SolveAr
   k_odo_begin<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a);
   if (launches) *launches += 1;
   const int nfeat_cap = a.cap_sharp + a.cap_flat;
-  dim3 ga(max(1, lvo_div_up(nfeat_cap, 8)), lanes);
+  dim3 ga(max(1, lvo_div_up(nfeat_cap * LVO_TW, 256)), lanes);
   for (int o = 0; o < outer_iters; ++o) {
     a.outer = o;
     k_odo_assoc<<<ga, 256, 0, st>>>(a);
