@@ -176,6 +176,15 @@ int lvo_voxel_downsample(lvo_ctx* ctx, lvo_cloud_view in, float leaf, lvo_cloud_
  * (laserMapping.cpp:582-584; laserOdometry.cpp:386-389). */
 int lvo_knn(lvo_ctx* ctx, lvo_cloud_view cloud, lvo_cloud_view queries, int K, float max_sq, int* ind, float* sq);
 
+/* Camera-lidar depth association (BASELINE config 5; reference src/vloam/Frame.cpp:289-352 + src/vloam/Frontend.cpp:223-301).
+ * The sweep is moved into the camera frame by the 3x4 extrinsic, every point with z > 0 becomes a depth-cloud point
+ * (10 x/z, 10 y/z, 10, intensity = z); each keypoint (normalised coordinates u = (px - cx)/fx, v = (py - cy)/fy) gets the
+ * depth of the plane through its 3 nearest depth-cloud points when the nearest lies within d^2 < 0.5, with the reference's
+ * clamps.  depth_out / valid_out are [n_kp]; nn_out (optional) is [n_kp][3] indices into the depth cloud (-1 if rejected). */
+typedef struct lvo_camera { float fx, fy, cx, cy; int width, height; float extrinsic[12]; /* row-major 3x4 lidar -> camera */ } lvo_camera;
+int lvo_depth_associate(lvo_ctx* ctx, lvo_cloud_view sweep, const lvo_camera* cam, const float* keypoints_uv, size_t n_kp, float* depth_out,
+                        int* valid_out, int* nn_out, lvo_cloud_out* depth_cloud_or_null);
+
 /* Throughput-mode 5-NN benchmark entry: S independent (map, query) problems in ONE launch.
  * d_maps / d_queries are device pointers to packed points, problems laid out back to back with the given
  * per-problem counts.  Builds the cell grids (untimed part) on first call with build != 0, then runs the search

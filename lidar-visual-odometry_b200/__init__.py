@@ -49,6 +49,17 @@ class Stats(C.Structure):
                 ("map_corner_total", C.c_int), ("map_surf_total", C.c_int), ("center_cube", C.c_int * 3), ("cen", C.c_int * 3)]
 
 
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("width", C.c_int), ("height", C.c_int), ("extrinsic", C.c_float * 12)]
+
+
+# params/KITTI00.yaml:4-10,27-33 of the reference
+KITTI00_CAMERA = dict(fx=718.856, fy=718.856, cx=607.1928, cy=185.2157, width=1241, height=376,
+                      extrinsic=[0.0004276802385584, -0.9999672484946, -0.008084491683471, -0.01198459927713,
+                                 -0.007210626507497, 0.008081198471645, -0.9999413164504, -0.05403984729748,
+                                 0.9999738645903, 0.0004859485810390, -0.007206933692422, -0.2921968648686])
+
+
 class Timings(C.Structure):
     _fields_ = [("extract_ms", C.c_float), ("odometry_ms", C.c_float), ("mapping_ms", C.c_float), ("knn_ms", C.c_float), ("knn_launches", C.c_int),
                 ("kernel_launches", C.c_int), ("knn_bytes", C.c_double)]
@@ -57,7 +68,7 @@ class Timings(C.Structure):
 EXPORTS = ["lvo_default_config", "lvo_create", "lvo_destroy", "lvo_last_error", "lvo_get_stats", "lvo_extract_features", "lvo_scan_to_scan",
            "lvo_scan_to_map", "lvo_step_batch", "lvo_step_batch_dev", "lvo_lane_status", "lvo_map_import", "lvo_map_export",
            "lvo_get_map_correction", "lvo_set_map_correction", "lvo_set_odometry_state", "lvo_probe_fetch", "lvo_voxel_downsample", "lvo_knn",
-           "lvo_knn5_throughput", "lvo_get_timings", "lvo_set_stream", "lvo_state_bytes"]
+           "lvo_knn5_throughput", "lvo_get_timings", "lvo_set_stream", "lvo_state_bytes", "lvo_depth_associate"]
 
 
 def load_library():
@@ -90,6 +101,7 @@ def load_library():
     L.lvo_get_timings.argtypes = [vp, C.POINTER(Timings)]
     L.lvo_set_stream.argtypes = [vp, vp]
     L.lvo_state_bytes.restype = C.c_size_t
+    L.lvo_depth_associate.argtypes = [vp, CloudView, C.POINTER(Camera), vp, C.c_size_t, vp, vp, vp, C.POINTER(CloudOut)]
     return L
 
 
@@ -295,6 +307,23 @@ class Lvo:
         self._check(self.lib.lvo_knn5_throughput(self.h, C.c_void_p(d_maps_ptr), mc, C.c_void_p(d_queries_ptr), qc, S, reps, C.c_void_p(d_ind_ptr),
                                                  C.c_void_p(d_sq_ptr), C.byref(ms)))
         return ms.value
+
+    def depth_associate(self, sweep, keypoints_uv, camera=None):
+        """Config 5: returns (depth_cloud, depth[n], valid[n], nn[n,3])."""
+        cam = Camera()
+        cd = dict(KITTI00_CAMERA if camera is None else camera)
+        cam.fx, cam.fy, cam.cx, cam.cy, cam.width, cam.height = cd["fx"], cd["fy"], cd["cx"], cd["cy"], cd["width"], cd["height"]
+        for k in range(12):
+            cam.extrinsic[k] = cd["extrinsic"][k]
+        v, keep = view_of(sweep)
+        uv = np.ascontiguousarray(keypoints_uv, np.float32).reshape(-1, 2)
+        n = len(uv)
+        depth = np.zeros(max(n, 1), np.float32)
+        valid = np.zeros(max(n, 1), np.int32)
+        nn = np.full((max(n, 1), 3), -1, np.int32)
+        out, buf = self._out(max(v.n, 1))
+        self._check(self.lib.lvo_depth_associate(self.h, v, C.byref(cam), uv.ctypes.data, n, depth.ctypes.data, valid.ctypes.data, nn.ctypes.data, C.byref(out)))
+        return buf[:out.n].copy(), depth[:n], valid[:n], nn[:n]
 
     # ---- stand-alone operators
     def voxel_downsample(self, pts, leaf):

@@ -10,6 +10,7 @@
 #include "lvo_solver.cuh"
 #include "lvo_odometry.cuh"
 #include "lvo_mapping.cuh"
+#include "lvo_depth.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -132,9 +133,10 @@ __global__ void k_setup_grid_problems(GridProblem* prob, int nprob, const float4
   prob[p].want_cell = which == 0 ? (k >= 6 ? 8.0f : (k >= 4 ? 2.0f : (k == 1 ? 0.5f : 1.0f))) : cell;
   prob[p].want_cell_z = which == 0 ? (k >= 6 ? 8.0f : 2.0f) : 0.f;
   prob[p].mode = (which == 0 && (k == 2 || k == 3)) ? 1 : 0;
+  prob[p].clamp_xy = 0.f;
 }
-__global__ void k_setup_one_problem(GridProblem* prob, const float4* pts, const int* d_n, float cell) {
-  prob[0].pts = pts; prob[0].d_n = d_n; prob[0].want_cell = cell; prob[0].want_cell_z = 0.f; prob[0].mode = 0;
+__global__ void k_setup_one_problem(GridProblem* prob, const float4* pts, const int* d_n, float cell, float clamp = 0.f) {
+  prob[0].pts = pts; prob[0].d_n = d_n; prob[0].want_cell = cell; prob[0].want_cell_z = 0.f; prob[0].mode = 0; prob[0].clamp_xy = clamp;
 }
 __global__ void k_vx_single_setup(VoxelEngine e, int n, float leaf) {
   if (blockIdx.x == 0 && threadIdx.x == 0) { *e.d_n = n; *e.d_nsegs = 1; e.seg_leaf[0] = leaf; }
@@ -346,7 +348,7 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
 
   // stand-alone kNN operator: one problem, storage borrowed from the mapping grid
   c->gknn = mp.grid; c->gknn.nprob = 1;
-  LVO_TRY(dalloc(c, &c->d_knn_prob, 1)); LVO_TRY(dalloc(c, &c->d_knn_n, 1));
+  LVO_TRY(dalloc(c, &c->d_knn_prob, 1)); LVO_TRY(dalloc(c, &c->d_knn_n, 4));
   c->gknn.prob = c->d_knn_prob;
   LVO_TRY(dalloc(c, &c->d_knn_ind, (size_t)P * 5)); LVO_TRY(dalloc(c, &c->d_knn_sq, (size_t)P * 5));
 
@@ -709,7 +711,54 @@ int lvo_knn(lvo_ctx* c, lvo_cloud_view cloud, lvo_cloud_view queries, int K, flo
 __global__ void k_setup_batch_problems(GridProblem* prob, int S, const float4* maps, const unsigned* m_off, const int* m_cnt, float cell) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= S) return;
-  prob[p].pts = maps + m_off[p]; prob[p].d_n = m_cnt + p; prob[p].want_cell = cell; prob[p].want_cell_z = 0.f; prob[p].mode = 0;
+  prob[p].pts = maps + m_off[p]; prob[p].d_n = m_cnt + p; prob[p].want_cell = cell; prob[p].want_cell_z = 0.f; prob[p].mode = 0; prob[p].clamp_xy = 0.f;
+}
+
+int lvo_depth_associate(lvo_ctx* c, lvo_cloud_view sweep, const lvo_camera* cam, const float* keypoints_uv, size_t n_kp, float* depth_out, int* valid_out,
+                        int* nn_out, lvo_cloud_out* depth_cloud_or_null) {
+  if (!c || !cam || (n_kp && (!keypoints_uv || !depth_out || !valid_out))) return LVO_E_BADARG;
+  LVO_TRY(check_view(c, sweep, (size_t)c->P));
+  if (n_kp > (size_t)c->P) { lvo_set_error(c, "too many keypoints"); return LVO_E_CAPACITY; }
+  c->launches = 0;
+  // scratch borrowed from the stages that are idle during this call
+  float4* d_sweep = c->ex.lf_ring;                 // [P]
+  float4* d_dc = c->map.registered;                // [P]
+  unsigned* d_flag = (unsigned*)c->ex.sort_ind;    // [P]
+  float* d_uv = (float*)c->ex.curv;                // [P] floats >= 2 * n_kp?  (checked below)
+  if (2 * n_kp > (size_t)c->P) { lvo_set_error(c, "too many keypoints"); return LVO_E_CAPACITY; }
+  LVO_TRY(upload_cloud(c, sweep, d_sweep));
+  if (n_kp) LVO_CUDA_OK(c, cudaMemcpyAsync(d_uv, keypoints_uv, 2 * n_kp * sizeof(float), cudaMemcpyHostToDevice, c->st));
+  DepthArgs a;
+  memset(&a, 0, sizeof(a));
+  a.sweep = d_sweep; a.n = (int)sweep.n;
+  for (int k = 0; k < 12; ++k) a.extr[k] = cam->extrinsic[k];
+  a.flag = d_flag; a.d_n = c->d_knn_n; a.d_ndc = c->d_knn_n + 1; a.dc = d_dc;
+  a.uv = d_uv; a.nkp = (int)n_kp;
+  a.depth = c->d_knn_sq; a.valid = c->d_knn_ind; a.nn = c->d_knn_ind + c->P;
+  a.grid = c->gknn;
+  const int gb = std::max(1, std::min(lvo_div_up((long long)sweep.n, 256), 592));
+  unsigned* d_total = c->map.vx.d_n_out;
+  k_depth_flag<<<gb, 256, 0, c->st>>>(a);
+  lvo_scan_exclusive(c->st, d_flag, a.d_n, (int)std::max<size_t>(sweep.n, 1), d_total, c->map.vx.scan, &c->launches);
+  k_depth_write<<<gb, 256, 0, c->st>>>(a, d_total);
+  // 2-D grid over the image plane: 0.125-unit cells (the cloud is in 10 x normalised coordinates), clamped to +-16
+  k_setup_one_problem<<<1, 1, 0, c->st>>>(c->d_knn_prob, d_dc, a.d_ndc, 0.125f, 16.0f);
+  lvo_grid_build(c->st, c->gknn, &c->launches);
+  if (n_kp) k_depth_assoc<<<std::max(1, std::min(lvo_div_up((long long)n_kp, 8), 592)), 256, 0, c->st>>>(a);
+  c->launches += 4;
+  int ndc = 0;
+  LVO_CUDA_OK(c, cudaMemcpyAsync(&ndc, a.d_ndc, 4, cudaMemcpyDeviceToHost, c->st));
+  if (n_kp) {
+    LVO_CUDA_OK(c, cudaMemcpyAsync(depth_out, a.depth, n_kp * 4, cudaMemcpyDeviceToHost, c->st));
+    LVO_CUDA_OK(c, cudaMemcpyAsync(valid_out, a.valid, n_kp * 4, cudaMemcpyDeviceToHost, c->st));
+    if (nn_out) LVO_CUDA_OK(c, cudaMemcpyAsync(nn_out, a.nn, n_kp * 12, cudaMemcpyDeviceToHost, c->st));
+  }
+  LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  LVO_CUDA_OK(c, cudaGetLastError());
+  if (sweep.n == 0) ndc = 0;
+  int r = download_cloud(c, d_dc, (size_t)ndc, depth_cloud_or_null);
+  LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  return r;
 }
 
 int lvo_knn5_throughput(lvo_ctx* c, const lvo_point* d_maps, const int* map_counts, const lvo_point* d_queries, const int* query_counts, int S, int reps,

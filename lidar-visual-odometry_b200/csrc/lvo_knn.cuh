@@ -29,6 +29,8 @@ struct GridProblem {   // device-resident descriptor
   float want_cell;     // requested cell size in x and y (power of two)
   float want_cell_z;   // requested cell size in z (power of two; 0 = same as want_cell)
   int mode;            // 0: uniform xyz grid; 1: (ring, azimuth) grid — cell = ring * LVO_AZ_BUCKETS + azimuth bucket
+  float clamp_xy;      // > 0: the table only covers |x|, |y| <= clamp_xy; points outside go to the border cells (their true
+                       //      distance is larger than the cell suggests, so every ring bound stays valid)
   // filled by k_grid_setup
   float cell, inv_cell;      // x / y cell size (the smallest one: all search bounds use it)
   float inv_cell_z;
@@ -84,6 +86,7 @@ __global__ void k_grid_reset(GridSet g) {
 __global__ void k_grid_bbox(GridSet g) {
   const int p = blockIdx.y;
   GridProblem& q = g.prob[p];
+  if (q.mode == 1) return;  // the (ring, azimuth) grid has fixed dimensions
   const int n = *q.d_n;
   int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -119,7 +122,9 @@ __global__ void __launch_bounds__(256) k_grid_setup(GridSet g) {
           nc = 1;
           for (int c = 0; c < 3; ++c) {
             const float inv = 1.0f / (c == 2 ? cellz : cell);
-            const int lo = cell_coord(ord2f_k(q.bb_mn[c]), inv), hi = cell_coord(ord2f_k(q.bb_mx[c]), inv);
+            float fmn = ord2f_k(q.bb_mn[c]), fmx = ord2f_k(q.bb_mx[c]);
+            if (q.clamp_xy > 0.f && c < 2) { fmn = fminf(fmaxf(fmn, -q.clamp_xy), q.clamp_xy); fmx = fminf(fmaxf(fmx, -q.clamp_xy), q.clamp_xy); }
+            const int lo = cell_coord(fmn, inv), hi = cell_coord(fmx, inv);
             org[c] = lo; dim[c] = hi - lo + 1;
             nc *= (long long)dim[c];
           }
@@ -154,7 +159,8 @@ __device__ __forceinline__ int az_bucket(float x, float y) {
 __device__ __forceinline__ int ring_clamped(float intensity) { return min(max(int(intensity), 0), LVO_AZ_RINGS - 1); }
 __device__ __forceinline__ int grid_cell_of(const GridProblem& q, float4 v) {
   if (q.mode == 1) return ring_clamped(v.w) * LVO_AZ_BUCKETS + az_bucket(v.x, v.y);
-  const int cx = cell_coord(v.x, q.inv_cell) - q.org[0], cy = cell_coord(v.y, q.inv_cell) - q.org[1], cz = cell_coord(v.z, q.inv_cell_z) - q.org[2];
+  int cx = cell_coord(v.x, q.inv_cell) - q.org[0], cy = cell_coord(v.y, q.inv_cell) - q.org[1], cz = cell_coord(v.z, q.inv_cell_z) - q.org[2];
+  cx = min(max(cx, 0), q.dim[0] - 1); cy = min(max(cy, 0), q.dim[1] - 1); cz = min(max(cz, 0), q.dim[2] - 1);
   return (cz * q.dim[1] + cy) * q.dim[0] + cx;
 }
 __global__ void k_grid_count(GridSet g) {

@@ -2,6 +2,7 @@
 #include "scan_registration.hpp"
 #include "laser_odometry.hpp"
 #include "laser_mapping.hpp"
+#include "depth_assoc.hpp"
 #include <chrono>
 
 using namespace lvo_oracle;
@@ -102,6 +103,18 @@ int lvo_oracle_solve(const double* f, long nf, double* x, int max_iters, double 
 
 void lvo_oracle_sym_eigen3(const double* M, double* w, double* V) { sym_eigen3(M, w, V); }
 void lvo_oracle_plane_fit5(const double* A, double* n) { plane_fit5(A, n); }
+
+// depth association (config 5).  Returns the number of depth-cloud points; dc_out [cap] / src_out [cap] optional.
+long lvo_oracle_depth(const Pt* sweep, long n, const float* extr12, const float* uv, long nkp, Pt* dc_out, int* src_out, long cap, float* depth, int* valid,
+                      int* nn) {
+  Cloud dc;
+  std::vector<int> src;
+  depth_cloud(sweep, (size_t)n, extr12, dc, &src);
+  if (dc_out && cap >= (long)dc.size() && !dc.empty()) memcpy(dc_out, dc.data(), dc.size() * sizeof(Pt));
+  if (src_out && cap >= (long)src.size() && !src.empty()) memcpy(src_out, src.data(), src.size() * sizeof(int));
+  if (nkp > 0) depth_associate(dc, uv, (size_t)nkp, depth, valid, nn);
+  return (long)dc.size();
+}
 
 // ---- the three stages as one stateful pipeline -------------------------------------------------------------
 void* lvo_oracle_create(int n_scans, double min_range, double line_res, double plane_res, int outer_iters, int lm_iters,

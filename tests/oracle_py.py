@@ -72,6 +72,8 @@ class Oracle:
         L.lvo_oracle_atan2f.restype = C.c_float
         L.lvo_oracle_atan2f.argtypes = [C.c_float, C.c_float]
         L.lvo_oracle_sym_eigen3.argtypes = [C.c_void_p] * 3
+        L.lvo_oracle_depth.restype = C.c_long
+        L.lvo_oracle_depth.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]
         L.lvo_oracle_plane_fit5.argtypes = [C.c_void_p] * 2
         self.outer = outer
         self.h = L.lvo_oracle_create(n_scans, min_range, line_res, plane_res, outer, lm_iters, huber, 1 if kdtree else 0)
@@ -181,6 +183,20 @@ class Oracle:
         sq = np.empty((len(q), K), np.float32)
         self.lib.lvo_oracle_knn(_ptr(cloud), len(cloud), _ptr(q), len(q), K, max_sq, method, _ptr(ind), _ptr(sq))
         return ind, sq
+
+    def depth(self, sweep, extr12, uv):
+        """Depth cloud + association (config 5).  Returns (depth_cloud, src_index, depth, valid, nn)."""
+        sweep = as_pts(sweep)
+        extr = np.ascontiguousarray(extr12, np.float32).reshape(12)
+        uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        cap = max(len(sweep), 1)
+        dc = np.empty((cap, 4), np.float32)
+        src = np.empty(cap, np.int32)
+        depth = np.zeros(max(len(uv), 1), np.float32)
+        valid = np.zeros(max(len(uv), 1), np.int32)
+        nn = np.full((max(len(uv), 1), 3), -1, np.int32)
+        n = self.lib.lvo_oracle_depth(_ptr(sweep), len(sweep), _ptr(extr), _ptr(uv), len(uv), _ptr(dc), _ptr(src), cap, _ptr(depth), _ptr(valid), _ptr(nn))
+        return dc[:n].copy(), src[:n].copy(), depth[:len(uv)], valid[:len(uv)], nn[:len(uv)]
 
     def eval_factor(self, f14, x7):
         f14 = np.ascontiguousarray(f14, np.float64)

@@ -300,3 +300,31 @@ def test_oracle_reproduces_golden_fixture():
         st, pose, _ = o.mapping(f["less_sharp"], f["less_flat"], f["full"], w)
         assert st == int(g[f"map{k}_status"]) and np.allclose(pose, g[f"map{k}_pose"], atol=1e-12)
         assert np.array_equal(sha(o.mapping_info()["corner_stack"]), g[f"map{k}_corner_stack_sha"])
+
+
+def test_depth_association_oracle_against_numpy():
+    """Config 5 oracle vs an independent numpy statement (brute-force 3-NN in double-checked float arithmetic)."""
+    s, o = Synth(), Oracle()
+    pts = s.sweep(64, 0, 0)[0]
+    E = np.array([0.0004276802385584, -0.9999672484946, -0.008084491683471, -0.01198459927713, -0.007210626507497, 0.008081198471645, -0.9999413164504,
+                  -0.05403984729748, 0.9999738645903, 0.0004859485810390, -0.007206933692422, -0.2921968648686], np.float32)
+    rng = np.random.default_rng(0)
+    uv = np.stack([rng.uniform(-0.8, 0.8, 200), rng.uniform(-0.22, 0.22, 200)], 1).astype(np.float32)
+    dc, src, d, v, nn = o.depth(pts, E, uv)
+    M = E.reshape(3, 4)
+    cam = ((M[:, 0] * pts[:, :1] + M[:, 1] * pts[:, 1:2]) + M[:, 2] * pts[:, 2:3]) + M[:, 3]
+    keep = cam[:, 2] > 0
+    assert np.array_equal(src, np.nonzero(keep)[0])
+    ref = np.stack([cam[keep, 0] * np.float32(10) / cam[keep, 2], cam[keep, 1] * np.float32(10) / cam[keep, 2], np.full(keep.sum(), 10, np.float32), cam[keep, 2]], 1)
+    assert np.array_equal(dc.view(np.uint32), ref.astype(np.float32).view(np.uint32))
+    for k in range(0, 200, 7):
+        dx, dy = dc[:, 0] - np.float32(10) * uv[k, 0], dc[:, 1] - np.float32(10) * uv[k, 1]
+        d2 = (dx * dx + dy * dy) + np.float32(0)
+        order = np.lexsort((np.arange(len(d2)), d2))[:3]
+        if d2[order[0]] < 0.5:
+            assert list(nn[k]) == list(order)
+        else:
+            assert v[k] == 0 and (nn[k] == -1).all()
+    ok = v == 1
+    zs = dc[nn[ok]][:, :, 3]
+    assert np.all(d[ok] >= zs.min(1) - 0.2001) and np.all(d[ok] <= zs.max(1) + 0.2001)   # the +-0.2 clamp
