@@ -97,6 +97,29 @@ __device__ __forceinline__ void tile_block_nn1(const GridView& g, bool active, f
   if (active && g.dim[0] > 0 && tl == 0) row_bounds(g, cz + 1, cy + 1, cx - 1, cx + 1, b, e);            // row 8
   tile_scan_ranges(g.pts, b, e, consider);
 }
+// Box query: every cell that intersects [q - rad, q + rad] (at most 3 x 3 rows when rad < cell).  Used when an upper bound
+// on the nearest-neighbour distance is known (the previous outer iteration's closest point): any point that beats or ties
+// the bound lies inside the box.
+__device__ __forceinline__ void tile_box_nn1(const GridView& g, bool active, float4 sel, float rad, float& d, int& id) {
+  const int tl = (int)tile_lane();
+  auto consider = [&](float4 p, int) {
+    const int i = __float_as_int(p.w);
+    const float dd = sqdist3(p, sel.x, sel.y, sel.z);
+    if (dd < d || (dd == d && i < id)) { d = dd; id = i; }
+  };
+  const int x0 = cell_coord(sel.x - rad, g.inv_cell) - g.org[0], x1 = cell_coord(sel.x + rad, g.inv_cell) - g.org[0];
+  const int y0 = cell_coord(sel.y - rad, g.inv_cell) - g.org[1], y1 = cell_coord(sel.y + rad, g.inv_cell) - g.org[1];
+  const int z0 = cell_coord(sel.z - rad, g.inv_cell_z) - g.org[2], z1 = cell_coord(sel.z + rad, g.inv_cell_z) - g.org[2];
+  const int ny = y1 - y0 + 1, nrows = ny * (z1 - z0 + 1);   // <= 9 by construction (rad < cell)
+  unsigned b = 0, e = 0;
+  if (active && g.dim[0] > 0 && tl < nrows) row_bounds(g, z0 + tl / ny, y0 + tl % ny, x0, x1, b, e);
+  tile_scan_ranges(g.pts, b, e, consider);
+  if (__any_sync(0xffffffffu, active && nrows > 8)) {
+    b = e = 0;
+    if (active && g.dim[0] > 0 && tl == 0 && nrows > 8) row_bounds(g, z0 + 8 / ny, y0 + 8 % ny, x0, x1, b, e);
+    tile_scan_ranges(g.pts, b, e, consider);
+  }
+}
 // shell r >= 2 of the coarse grid, 8 ranges at a time
 __device__ __forceinline__ void tile_shell_nn1(const GridView& g, bool active, float4 sel, int r, float& d, int& id) {
   const int tl = (int)tile_lane();
@@ -148,9 +171,30 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
   // (0.5 m) settle it when the best squared distance is below cell^2; otherwise the middle grid (2 m), then the coarse
   // grid (8 m, whose 27 cells cover the whole 5 m gate), then coarse shells if the cells had to be enlarged.
   float d = FLT_MAX; int id = INT_MAX, key;
-  tile_block_nn1(gfine, have, sel, d, id);
-  key = id; tile_min3(d, key, id);
-  bool more = have && !(d < gfine.cell * gfine.cell);
+  // Upper bounds from the previous outer iteration of this frame (same clouds, slightly different pose): the points found
+  // then still exist, so their distances to the new query bound the new minima and the searches shrink to a small box /
+  // azimuth window.  Results are identical to the unbounded search.
+  int pc = -1, pA = -1, pB = -1;
+  if (have && a.outer > 0) {
+    if (corner) { const int* c = a.corner_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer - 1) * a.cap_sharp + f) * 2; pc = c[0]; pB = c[1]; }
+    else { const int* c = a.plane_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer - 1) * a.cap_flat + (f - ns)) * 3; pc = c[0]; pA = c[1]; pB = c[2]; }
+  }
+  bool boxed = false;
+  if (pc >= 0) {
+    const float dp = sqdist3(C[pc], sel.x, sel.y, sel.z);
+    const float rad = sqrtf(dp) * 1.0001f + 1e-5f;
+    if (rad < gfine.cell) { boxed = true; d = dp; id = pc; }
+  }
+  if (__any_sync(0xffffffffu, boxed)) {
+    tile_box_nn1(gfine, boxed, sel, sqrtf(d) * 1.0001f + 1e-5f, d, id);
+    key = id; tile_min3(d, key, id);
+  }
+  const bool unboxed = have && !boxed;
+  if (__any_sync(0xffffffffu, unboxed)) {
+    tile_block_nn1(gfine, unboxed, sel, d, id);
+    key = id; tile_min3(d, key, id);
+  }
+  bool more = unboxed && !(d < gfine.cell * gfine.cell);
   if (__any_sync(0xffffffffu, more)) {
     tile_block_nn1(gmid, more, sel, d, id);
     key = id; tile_min3(d, key, id);
@@ -193,26 +237,44 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
   };
   const int ring = cid - 2 + tl;   // lanes 0..4 of the tile own rings cid-2 .. cid+2
   const bool ring_ok = ok && tl < 5 && ring >= 0 && ring < LVO_AZ_RINGS && (ring != cid || needA);
-  for (int part = 0; part < 2; ++part) {   // phase 1: +-2 buckets (part 1 only exists when the window wraps)
+  // seeds from the previous outer iteration, if they still satisfy the ring filter relative to the new closest point
+  auto seed = [&](int pidx, bool same_ring, Best& best) {
+    if (!ok || pidx < 0 || pidx == closest) return;
+    const float4 p = C[pidx];
+    const int dr = ring_clamped(p.w) - cid;
+    if (same_ring ? (dr != 0) : (dr == 0 || dr > 2 || dr < -2)) return;
+    if ((pidx > closest && dr < 0) || (pidx < closest && dr > 0)) return;
+    const float dd = (p.x - sel.x) * (p.x - sel.x) + (p.y - sel.y) * (p.y - sel.y) + (p.z - sel.z) * (p.z - sel.z);
+    if (!(dd < 25.0f)) return;
+    best = Best{dd, pidx > closest ? (pidx - closest) : ((closest - pidx) + (1 << 30)), pidx};
+  };
+  if (needA) seed(pA, true, bA);
+  seed(pB, false, bB);
+  // phase 1: +-2 buckets, or the window implied by the seed (part 1 only exists when the window wraps)
+  const int h1 = ring == cid ? (bA.j >= 0 ? az_halfwidth(bA.d, rho) : 2) : (bB.j >= 0 ? az_halfwidth(bB.d, rho) : 2);
+  for (int part = 0; part < 2; ++part) {
     unsigned b = 0, e = 0;
-    if (ring_ok) az_bounds(gaz, ring, bq - 2, bq + 2, part, b, e);
+    if (ring_ok) az_bounds(gaz, ring, bq - h1, bq + h1, part, b, e);
     tile_scan_ranges(gaz.pts, b, e, consider);
   }
   tile_min3(bA.d, bA.pos, bA.j); tile_min3(bB.d, bB.pos, bB.j);
   {  // phase 2: the rest of the window implied by the best distances so far (or by the 5 m gate)
     const int h = ring == cid ? (needA ? az_halfwidth(bA.d, rho) : 0) : az_halfwidth(bB.d, rho);
     const bool whole = 2 * h + 1 >= LVO_AZ_BUCKETS;
-    for (int sp = 0; sp < 4; ++sp) {   // side (bit 1), part (bit 0)
-      unsigned b = 0, e = 0;
-      if (ring_ok && h > 2) {
-        if (whole) { if (sp == 0) az_bounds(gaz, ring, 0, LVO_AZ_BUCKETS - 1, 0, b, e); }
-        else if ((sp >> 1) == 0) az_bounds(gaz, ring, bq - h, bq - 3, sp & 1, b, e);
-        else az_bounds(gaz, ring, bq + 3, bq + h, sp & 1, b, e);
+    const bool need2 = ring_ok && h > h1 && 2 * h1 + 1 < LVO_AZ_BUCKETS;
+    if (__any_sync(0xffffffffu, need2)) {
+      for (int sp = 0; sp < 4; ++sp) {   // side (bit 1), part (bit 0)
+        unsigned b = 0, e = 0;
+        if (need2) {
+          if (whole) { if (sp == 0) az_bounds(gaz, ring, 0, LVO_AZ_BUCKETS - 1, 0, b, e); }
+          else if ((sp >> 1) == 0) az_bounds(gaz, ring, bq - h, bq - h1 - 1, sp & 1, b, e);
+          else az_bounds(gaz, ring, bq + h1 + 1, bq + h, sp & 1, b, e);
+        }
+        tile_scan_ranges(gaz.pts, b, e, consider);
       }
-      tile_scan_ranges(gaz.pts, b, e, consider);
+      tile_min3(bA.d, bA.pos, bA.j); tile_min3(bB.d, bB.pos, bB.j);
     }
   }
-  tile_min3(bA.d, bA.pos, bA.j); tile_min3(bB.d, bB.pos, bB.j);
   const int same = bA.j, other = bB.j;
   // ---- factor record (tile leader)
   bool made_c = false, made_p = false;

@@ -286,6 +286,11 @@ struct LmCtl {
 };
 
 __device__ inline double gradient_max_norm_dev(const double* x, const double* g) {
+  // || x - Plus(x, -g) ||_inf.  The translation block of Plus is a plain addition, so its entries of the difference are
+  // |g_t| exactly: if one of them already exceeds the tolerance the test "<= 1e-10" is decided without the quaternion
+  // exponential (sin / cos in double on the one thread everybody waits for).
+  const double gt = fmax(fabs(g[3]), fmax(fabs(g[4]), fabs(g[5])));
+  if (gt > 1e-10) return gt;
   double ng[6], xp[7];
   for (int c = 0; c < 6; ++c) ng[c] = -g[c];
   plus7_dev(x, ng, xp);
