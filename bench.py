@@ -5,8 +5,9 @@ A "step" advances every lane (independent sequence) of this rank's context by on
 path: lvo_extract_features -> lvo_scan_to_scan -> lvo_scan_to_map (device-resident chain, `lvo_step_batch_dev`).
   value : scans/s, whole job (all ranks, all lanes), inputs already resident in HBM, timed with CUDA events on the
           launching stream, one event pair per step with an L2 flush between steps, max over ranks.
-  e2e   : the same metric through `lvo_step_batch` with HOST (pinned) sweep buffers: H2D of every sweep and D2H of the
-          poses / lane state inside the timed region.
+  e2e   : the same metric through `lvo_step_batch_pipelined` with HOST (pinned) sweep buffers: every step uploads one frame
+          of sweeps (the next frame's, on a copy stream, overlapping this frame's compute) and reads the poses / lane state
+          back, all inside the timed region.
   roofline     : the 5-NN map-search kernel (k_map_knn) of the timed steps —
                  algorithmic bytes 16 M + 56 Q per launch / its CUDA-event duration, vs the measured HBM peak.
   cpu_baseline : the CPU oracle (restated reference, own kd-tree + own LM; NOT the PCL/Ceres binaries) on one host core,
@@ -190,7 +191,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--lanes", type=int, default=int(os.environ.get("LVO_BENCH_LANES", "32")), help="independent sequences per GPU")
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("LVO_BENCH_LANES", "128")), help="independent sequences per GPU")
     ap.add_argument("--ref-threads", type=int, default=0)
     ap.add_argument("--cpu-sample-frames", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -276,11 +277,22 @@ def main():
     ctx_e.set_stream(stream.cuda_stream)
     h2d = [0]
 
+    host_views = {}
+
+    def views_of(k):
+        if k not in host_views:
+            host_views[k] = [pinned[(s, k + o)].numpy() for s, o in plan]
+        return host_views[k]
+
     def step_host(k):
-        views = [pinned[(s, k + o)].numpy() for s, o in plan]
+        # every step uploads exactly one frame of sweeps from pinned host memory: frame k+1 goes up on the copy stream
+        # while frame k computes (lvo_step_batch_pipelined), and the poses / lane state of frame k come back before it returns
+        views = views_of(k)
+        nxt = views_of(k + 1) if k + 1 < total else None
         h2d[0] = sum(v.nbytes for v in views)
-        st, odo, mp = ctx_e.step_batch(views)
+        st, odo, mp = ctx_e.step_batch_pipelined(views, nxt)
         assert st >= 0
+        host_views.pop(k - 1, None)
 
     sampler = ClockSampler(local_rank)
     sampler.start()

@@ -123,6 +123,13 @@ int lvo_scan_to_map(lvo_ctx* ctx, lvo_cloud_view corner_last, lvo_cloud_view sur
  * per-lane statuses through lvo_lane_status. */
 int lvo_step_batch(lvo_ctx* ctx, const lvo_cloud_view* sweeps, lvo_pose* T_wodom_curr, lvo_pose* T_wmap_curr);
 
+/* Pipelined form of lvo_step_batch for a host loop: computes the frame `sweeps` and, while it runs, uploads `next_sweeps`
+ * (may be NULL) on a copy stream into a second staging buffer, the way the reference's ROS nodes overlap transport and
+ * compute.  If `sweeps` is the set that the previous call prefetched (same pointers and sizes) no copy is issued for it.
+ * The buffers of next_sweeps must stay valid and unchanged until the next call. */
+int lvo_step_batch_pipelined(lvo_ctx* ctx, const lvo_cloud_view* sweeps, const lvo_cloud_view* next_sweeps_or_null, lvo_pose* T_wodom_curr,
+                             lvo_pose* T_wmap_curr);
+
 /* Same, with sweeps already resident in device memory as packed lvo_point arrays (d_sweeps[l] is a device
  * pointer with n[l] points).  This is what bench.py's device-resident `value` times. */
 int lvo_step_batch_dev(lvo_ctx* ctx, const lvo_point* const* d_sweeps, const size_t* n, lvo_pose* T_wodom_curr,

@@ -68,7 +68,7 @@ class Timings(C.Structure):
 EXPORTS = ["lvo_default_config", "lvo_create", "lvo_destroy", "lvo_last_error", "lvo_get_stats", "lvo_extract_features", "lvo_scan_to_scan",
            "lvo_scan_to_map", "lvo_step_batch", "lvo_step_batch_dev", "lvo_lane_status", "lvo_map_import", "lvo_map_export",
            "lvo_get_map_correction", "lvo_set_map_correction", "lvo_set_odometry_state", "lvo_probe_fetch", "lvo_voxel_downsample", "lvo_knn",
-           "lvo_knn5_throughput", "lvo_get_timings", "lvo_set_stream", "lvo_state_bytes", "lvo_depth_associate"]
+           "lvo_knn5_throughput", "lvo_get_timings", "lvo_set_stream", "lvo_state_bytes", "lvo_depth_associate", "lvo_step_batch_pipelined"]
 
 
 def load_library():
@@ -87,6 +87,7 @@ def load_library():
     L.lvo_scan_to_scan.argtypes = [vp] + [CloudView] * 4 + [C.POINTER(Pose)] * 2
     L.lvo_scan_to_map.argtypes = [vp] + [CloudView] * 3 + [C.POINTER(Pose), C.POINTER(Pose), C.POINTER(CloudOut)]
     L.lvo_step_batch.argtypes = [vp, C.POINTER(CloudView), C.POINTER(Pose), C.POINTER(Pose)]
+    L.lvo_step_batch_pipelined.argtypes = [vp, C.POINTER(CloudView), C.POINTER(CloudView), C.POINTER(Pose), C.POINTER(Pose)]
     L.lvo_step_batch_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(Pose), C.POINTER(Pose)]
     L.lvo_lane_status.argtypes = [vp, ip]
     L.lvo_map_import.argtypes = [vp, ip, vp, vp, C.c_size_t, vp, vp, C.c_size_t]
@@ -214,6 +215,19 @@ class Lvo:
         arr = (CloudView * self.lanes)(*[v[0] for v in views])
         po, pm = (Pose * self.lanes)(), (Pose * self.lanes)()
         r = self._check(self.lib.lvo_step_batch(self.h, arr, po, pm))
+        return r, np.stack([pose_to_np(p) for p in po]), np.stack([pose_to_np(p) for p in pm])
+
+    def step_batch_pipelined(self, sweeps, next_sweeps=None):
+        """Like step_batch, but uploads next_sweeps on a copy stream while this frame computes.  The arrays of next_sweeps
+        must be kept alive and unchanged by the caller until the next call (they are handed over by pointer)."""
+        views = [view_of(s) for s in sweeps]
+        arr = (CloudView * self.lanes)(*[v[0] for v in views])
+        nxt = None
+        if next_sweeps is not None:
+            nviews = [view_of(s) for s in next_sweeps]
+            nxt = (CloudView * self.lanes)(*[v[0] for v in nviews])
+        po, pm = (Pose * self.lanes)(), (Pose * self.lanes)()
+        r = self._check(self.lib.lvo_step_batch_pipelined(self.h, arr, nxt, po, pm))
         return r, np.stack([pose_to_np(p) for p in po]), np.stack([pose_to_np(p) for p in pm])
 
     def step_batch_dev(self, dev_ptrs, counts):

@@ -33,6 +33,11 @@ struct lvo_ctx {
   GridProblem* d_knn_prob = nullptr;
   int* d_knn_n = nullptr;
   unsigned char* d_raw = nullptr;   // [lanes][P * 32] raw sweep records
+  unsigned char* d_raw2 = nullptr;  // second staging buffer for lvo_step_batch_pipelined (allocated on first use)
+  cudaStream_t copy_st = nullptr;
+  cudaEvent_t copy_ev = nullptr, compute_ev = nullptr;
+  std::vector<lvo_cloud_view> prefetched;  // the sweep set sitting in the "next" staging buffer
+  int raw_cur = 0;                  // which staging buffer the current frame reads
   size_t raw_lane_bytes = 0;
   const unsigned char** d_in_ptr = nullptr; const unsigned char** h_in_ptr = nullptr;
   int* d_in_n = nullptr; int* h_in_n = nullptr;
@@ -362,6 +367,7 @@ int lvo_destroy(lvo_ctx* c) {
   if (c->st) cudaStreamSynchronize(c->st);
   for (void* p : c->allocs) cudaFree(p);
   for (void* p : c->pinned) cudaFreeHost(p);
+  if (c->copy_st) { cudaStreamSynchronize(c->copy_st); cudaStreamDestroy(c->copy_st); cudaEventDestroy(c->copy_ev); cudaEventDestroy(c->compute_ev); }
   if (c->own_st) { for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]); for (auto& e : c->knn_ev) cudaEventDestroy(e); cudaStreamDestroy(c->own_st); }
   delete c;
   return LVO_OK;
@@ -526,6 +532,44 @@ int lvo_step_batch(lvo_ctx* c, const lvo_cloud_view* sweeps, lvo_pose* T_wodom, 
     unsigned char* dst = c->d_raw + c->raw_lane_bytes * l;
     if (sweeps[l].n) LVO_CUDA_OK(c, cudaMemcpyAsync(dst, sweeps[l].data, sweeps[l].n * sweeps[l].stride, cudaMemcpyHostToDevice, c->st));
     c->h_in_ptr[l] = dst; c->h_in_n[l] = (int)sweeps[l].n;
+  }
+  return step_common(c, (int)sweeps[0].stride, (int)sweeps[0].off_xyz, max_n, T_wodom, T_wmap);
+}
+
+int lvo_step_batch_pipelined(lvo_ctx* c, const lvo_cloud_view* sweeps, const lvo_cloud_view* next, lvo_pose* T_wodom, lvo_pose* T_wmap) {
+  if (!c || !sweeps) return LVO_E_BADARG;
+  if (!c->copy_st) {
+    LVO_CUDA_OK(c, cudaStreamCreateWithFlags(&c->copy_st, cudaStreamNonBlocking));
+    LVO_CUDA_OK(c, cudaEventCreateWithFlags(&c->copy_ev, cudaEventDisableTiming));
+    LVO_CUDA_OK(c, cudaEventCreateWithFlags(&c->compute_ev, cudaEventDisableTiming));
+    LVO_TRY(dalloc(c, &c->d_raw2, c->raw_lane_bytes * c->lanes, false));
+  }
+  int max_n = 0;
+  for (int l = 0; l < c->lanes; ++l) {
+    LVO_TRY(check_view(c, sweeps[l], (size_t)c->P));
+    if (next) LVO_TRY(check_view(c, next[l], (size_t)c->P));
+    if (sweeps[l].stride != sweeps[0].stride || sweeps[l].off_xyz != sweeps[0].off_xyz || sweeps[l].stride > 32) { lvo_set_error(c, "all lanes must share one point layout (stride <= 32)"); return LVO_E_BADARG; }
+    max_n = std::max(max_n, (int)sweeps[l].n);
+  }
+  bool hit = (int)c->prefetched.size() == c->lanes;
+  for (int l = 0; hit && l < c->lanes; ++l) hit = c->prefetched[l].data == sweeps[l].data && c->prefetched[l].n == sweeps[l].n && c->prefetched[l].stride == sweeps[l].stride;
+  unsigned char* bufs[2] = {c->d_raw, c->d_raw2};
+  if (hit) {
+    c->raw_cur ^= 1;                                         // the prefetched buffer becomes current
+    LVO_CUDA_OK(c, cudaStreamWaitEvent(c->st, c->copy_ev, 0));
+  } else {
+    for (int l = 0; l < c->lanes; ++l)
+      if (sweeps[l].n) LVO_CUDA_OK(c, cudaMemcpyAsync(bufs[c->raw_cur] + c->raw_lane_bytes * l, sweeps[l].data, sweeps[l].n * sweeps[l].stride, cudaMemcpyHostToDevice, c->st));
+  }
+  c->prefetched.clear();
+  for (int l = 0; l < c->lanes; ++l) { c->h_in_ptr[l] = bufs[c->raw_cur] + c->raw_lane_bytes * l; c->h_in_n[l] = (int)sweeps[l].n; }
+  if (next) {
+    // the other buffer was last read by the previous frame's kernels, which have completed (every call ends synchronised)
+    unsigned char* nb = bufs[c->raw_cur ^ 1];
+    for (int l = 0; l < c->lanes; ++l)
+      if (next[l].n) LVO_CUDA_OK(c, cudaMemcpyAsync(nb + c->raw_lane_bytes * l, next[l].data, next[l].n * next[l].stride, cudaMemcpyHostToDevice, c->copy_st));
+    LVO_CUDA_OK(c, cudaEventRecord(c->copy_ev, c->copy_st));
+    c->prefetched.assign(next, next + c->lanes);
   }
   return step_common(c, (int)sweeps[0].stride, (int)sweeps[0].off_xyz, max_n, T_wodom, T_wmap);
 }

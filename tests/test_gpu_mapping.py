@@ -135,3 +135,17 @@ def test_map_too_small_warning(lvo_mod, synth):
         po, co = O.map_export(which)
         assert np.array_equal(cg, co) and np.array_equal(_bits(pg), _bits(po))
     lvo.close()
+
+
+def test_pipelined_host_entry_matches_plain(lvo_mod, synth):
+    """lvo_step_batch_pipelined (next frame uploaded on a copy stream during compute) gives bit-identical poses."""
+    L = lvo_mod
+    a = L.Lvo(lanes=2, max_map_corner=1 << 18, max_map_surf=1 << 19)
+    b = L.Lvo(lanes=2, max_map_corner=1 << 18, max_map_surf=1 << 19)
+    frames = [[np.ascontiguousarray(synth.sweep(64, s, k)[0]) for s in (0, 1)] for k in range(5)]
+    for k in range(5):
+        _, oa, ma = a.step_batch(frames[k])
+        nxt = frames[k + 1] if (k + 1 < 5 and k != 2) else None   # k == 2: no prefetch -> next call takes the fallback copy path
+        _, ob, mb = b.step_batch_pipelined(frames[k], nxt)
+        assert np.array_equal(oa, ob) and np.array_equal(ma, mb), k
+    a.close(); b.close()
