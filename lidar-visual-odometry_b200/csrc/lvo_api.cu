@@ -304,6 +304,7 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
   LVO_TRY(dalloc(c, &od.corner_last, (size_t)L * c->cap_lsharp)); LVO_TRY(dalloc(c, &od.surf_last, (size_t)L * P));
   od.factor_cap = std::max(c->cap_sharp + c->cap_flat, c->cap_lsharp + P);
   LVO_TRY(dalloc(c, &od.factors, (size_t)L * od.factor_cap));
+  LVO_TRY(dalloc(c, &od.slow_list, (size_t)L * (c->cap_sharp + c->cap_flat))); LVO_TRY(dalloc(c, &od.slow_cnt, (size_t)L));
   LVO_TRY(dalloc(c, &od.corner_corr, (size_t)L * LVO_MAX_OUTER * c->cap_sharp * 2));
   LVO_TRY(dalloc(c, &od.plane_corr, (size_t)L * LVO_MAX_OUTER * c->cap_flat * 3));
   LVO_TRY(alloc_grid(c, &od.grid, 8 * L, 1 << 22, (size_t)4 * L * (c->cap_lsharp + P), P));

@@ -364,35 +364,35 @@ __device__ __forceinline__ void warp_scan_ranges(unsigned b, unsigned e, F&& f) 
   }
 }
 // ---------------------------------------------------------------------------------------------------------------
-// 8-lane tiles: four queries per warp.  Every primitive below is executed by all 32 lanes (full-mask shuffles with
-// width 8); a tile that has nothing to do passes empty ranges.  This shares all per-query overhead (bounds, prefix
+// Tiles: TW lanes per query.  Every primitive below is executed by all 32 lanes (full-mask shuffles with width TW); a
+// tile that has nothing to do passes empty ranges.  This shares all per-query overhead (bounds, prefix
 // sums, reductions, control flow) between four queries, which is what the latency-bound association kernels need.
 // ---------------------------------------------------------------------------------------------------------------
-#define LVO_TW 8
-__device__ __forceinline__ unsigned tile_lane() { return threadIdx.x & (LVO_TW - 1); }
+// TW = lanes per query (8: four queries per warp; 32: one query per warp, for the few expensive ones).
+template <int TW> __device__ __forceinline__ unsigned tile_lane() { return threadIdx.x & (TW - 1); }
+template <int TW>
 __device__ __forceinline__ unsigned tile_incl_scan(unsigned v) {
-  const unsigned tl = tile_lane();
+  const unsigned tl = tile_lane<TW>();
 #pragma unroll
-  for (int o = 1; o < LVO_TW; o <<= 1) {
-    const unsigned t = __shfl_up_sync(0xffffffffu, v, o, LVO_TW);
+  for (int o = 1; o < TW; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, v, o, TW);
     if (tl >= (unsigned)o) v += t;
   }
   return v;
 }
-// lane j of the tile holds range [b, e) (possibly empty); f(t, r) is called for candidate t of range r
-// f(p, r): candidate point p (w = original index) of range r.  Software-pipelined: the candidate of step k+1 is
-// fetched before step k is processed, so two loads per lane are in flight.
-template <class F>
+// Lane j < NR of the tile holds range [b, e) (possibly empty); f(p, r): candidate point p (w = original index) of range r.
+// Software-pipelined: the candidate of step k+1 is fetched before step k is processed, so two loads per lane are in flight.
+template <int TW, int NR, class F>
 __device__ __forceinline__ void tile_scan_ranges(const float4* __restrict__ pts, unsigned b, unsigned e, F&& f) {
-  const unsigned tl = tile_lane();
+  const unsigned tl = tile_lane<TW>();
   const unsigned len = e > b ? e - b : 0u;
-  const unsigned incl = tile_incl_scan(len);
-  const unsigned total = __shfl_sync(0xffffffffu, incl, LVO_TW - 1, LVO_TW);
+  const unsigned incl = tile_incl_scan<TW>(len);
+  const unsigned total = __shfl_sync(0xffffffffu, incl, TW - 1, TW);
   auto locate = [&](unsigned k, int& r) -> unsigned {
     r = 0;
 #pragma unroll
-    for (int j = 0; j < LVO_TW - 1; ++j) r += (k >= __shfl_sync(0xffffffffu, incl, j, LVO_TW)) ? 1 : 0;
-    const unsigned rb = __shfl_sync(0xffffffffu, b, r, LVO_TW), ri = __shfl_sync(0xffffffffu, incl, r, LVO_TW), rl = __shfl_sync(0xffffffffu, len, r, LVO_TW);
+    for (int j = 0; j < NR - 1; ++j) r += (k >= __shfl_sync(0xffffffffu, incl, j, TW)) ? 1 : 0;
+    const unsigned rb = __shfl_sync(0xffffffffu, b, r, TW), ri = __shfl_sync(0xffffffffu, incl, r, TW), rl = __shfl_sync(0xffffffffu, len, r, TW);
     return rb + (k - (ri - rl));
   };
   if (!__any_sync(0xffffffffu, total > 0)) return;
@@ -401,10 +401,10 @@ __device__ __forceinline__ void tile_scan_ranges(const float4* __restrict__ pts,
   bool v_cur = tl < total;
   float4 p_cur = make_float4(0.f, 0.f, 0.f, 0.f), p_nxt = p_cur;
   if (v_cur) p_cur = __ldg(pts + t);
-  for (unsigned k0 = 0; __any_sync(0xffffffffu, k0 < total); k0 += LVO_TW) {
-    const unsigned kn = k0 + LVO_TW + tl;
+  for (unsigned k0 = 0; __any_sync(0xffffffffu, k0 < total); k0 += TW) {
+    const unsigned kn = k0 + TW + tl;
     const bool v_nxt = kn < total;
-    if (__any_sync(0xffffffffu, k0 + LVO_TW < total)) {
+    if (__any_sync(0xffffffffu, k0 + TW < total)) {
       const unsigned tn = locate(kn, r_nxt);
       if (v_nxt) p_nxt = __ldg(pts + tn);
     }
@@ -413,11 +413,12 @@ __device__ __forceinline__ void tile_scan_ranges(const float4* __restrict__ pts,
   }
 }
 // (d, key) lexicographic minimum over the tile, payload j
+template <int TW>
 __device__ __forceinline__ void tile_min3(float& d, int& key, int& j) {
 #pragma unroll
-  for (int o = LVO_TW / 2; o > 0; o >>= 1) {
-    const float od = __shfl_xor_sync(0xffffffffu, d, o, LVO_TW);
-    const int ok = __shfl_xor_sync(0xffffffffu, key, o, LVO_TW), oj = __shfl_xor_sync(0xffffffffu, j, o, LVO_TW);
+  for (int o = TW / 2; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, d, o, TW);
+    const int ok = __shfl_xor_sync(0xffffffffu, key, o, TW), oj = __shfl_xor_sync(0xffffffffu, j, o, TW);
     if (od < d || (od == d && ok < key)) { d = od; key = ok; j = oj; }
   }
 }

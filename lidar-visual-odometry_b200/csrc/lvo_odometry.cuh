@@ -26,6 +26,8 @@ struct OdoArgs {
   float4* corner_last; float4* surf_last;  // [lanes][cap_lsharp], [lanes][P]
   GridSet grid;                            // problems 8*lane + {0/1 corner/surf fine xyz, 2/3 corner/surf (ring,azimuth), 4/5 corner/surf middle xyz, 6/7 corner/surf coarse xyz}
   LvoFactor* factors; int factor_cap;
+  int* slow_list;    // [lanes][cap_sharp + cap_flat] features the fast kernel hands to the tile kernel
+  int* slow_cnt;     // [lanes]
   int* corner_corr;  // [lanes][LVO_MAX_OUTER][cap_sharp][2]   probes
   int* plane_corr;   // [lanes][LVO_MAX_OUTER][cap_flat][3]
 };
@@ -82,26 +84,28 @@ __device__ __forceinline__ int az_halfwidth(float d2, float rho) {
 }
 // ---- one 8-lane tile per feature (four features per warp); every call below is made by all 32 lanes --------------------
 // rows 3k .. 3k+2 (k = part) of the 3x3 row block around (cx, cy, cz): lanes 0..2 of the tile fetch the bounds
+template <int TW>
 __device__ __forceinline__ void tile_block_nn1(const GridView& g, bool active, float4 sel, float& d, int& id) {
-  const int tl = (int)tile_lane();
+  const int tl = (int)tile_lane<TW>();
   const int cx = cell_coord(sel.x, g.inv_cell) - g.org[0], cy = cell_coord(sel.y, g.inv_cell) - g.org[1], cz = cell_coord(sel.z, g.inv_cell_z) - g.org[2];
   auto consider = [&](float4 p, int) {
     const int i = __float_as_int(p.w);
     const float dd = sqdist3(p, sel.x, sel.y, sel.z);
     if (dd < d || (dd == d && i < id)) { d = dd; id = i; }
   };
-  unsigned b = 0, e = 0;
-  if (active && g.dim[0] > 0) row_bounds(g, cz + tl / 3 - 1, cy + tl % 3 - 1, cx - 1, cx + 1, b, e);   // rows 0..7
-  tile_scan_ranges(g.pts, b, e, consider);
-  b = e = 0;
-  if (active && g.dim[0] > 0 && tl == 0) row_bounds(g, cz + 1, cy + 1, cx - 1, cx + 1, b, e);            // row 8
-  tile_scan_ranges(g.pts, b, e, consider);
+  for (int base = 0; base < 9; base += TW) {   // 9 rows: two steps for 8-lane tiles, one for full warps
+    const int row = base + tl;
+    unsigned b = 0, e = 0;
+    if (active && g.dim[0] > 0 && row < 9) row_bounds(g, cz + row / 3 - 1, cy + row % 3 - 1, cx - 1, cx + 1, b, e);
+    tile_scan_ranges<TW, (TW < 9 ? TW : 9)>(g.pts, b, e, consider);
+  }
 }
 // Box query: every cell that intersects [q - rad, q + rad] (at most 3 x 3 rows when rad < cell).  Used when an upper bound
 // on the nearest-neighbour distance is known (the previous outer iteration's closest point): any point that beats or ties
 // the bound lies inside the box.
+template <int TW>
 __device__ __forceinline__ void tile_box_nn1(const GridView& g, bool active, float4 sel, float rad, float& d, int& id) {
-  const int tl = (int)tile_lane();
+  const int tl = (int)tile_lane<TW>();
   auto consider = [&](float4 p, int) {
     const int i = __float_as_int(p.w);
     const float dd = sqdist3(p, sel.x, sel.y, sel.z);
@@ -111,38 +115,263 @@ __device__ __forceinline__ void tile_box_nn1(const GridView& g, bool active, flo
   const int y0 = cell_coord(sel.y - rad, g.inv_cell) - g.org[1], y1 = cell_coord(sel.y + rad, g.inv_cell) - g.org[1];
   const int z0 = cell_coord(sel.z - rad, g.inv_cell_z) - g.org[2], z1 = cell_coord(sel.z + rad, g.inv_cell_z) - g.org[2];
   const int ny = y1 - y0 + 1, nrows = ny * (z1 - z0 + 1);   // <= 9 by construction (rad < cell)
-  unsigned b = 0, e = 0;
-  if (active && g.dim[0] > 0 && tl < nrows) row_bounds(g, z0 + tl / ny, y0 + tl % ny, x0, x1, b, e);
-  tile_scan_ranges(g.pts, b, e, consider);
-  if (__any_sync(0xffffffffu, active && nrows > 8)) {
-    b = e = 0;
-    if (active && g.dim[0] > 0 && tl == 0 && nrows > 8) row_bounds(g, z0 + 8 / ny, y0 + 8 % ny, x0, x1, b, e);
-    tile_scan_ranges(g.pts, b, e, consider);
+  for (int base = 0; base < 9; base += TW) {
+    if (base > 0 && !__any_sync(0xffffffffu, active && nrows > base)) break;
+    const int row = base + tl;
+    unsigned b = 0, e = 0;
+    if (active && g.dim[0] > 0 && row < nrows) row_bounds(g, z0 + row / ny, y0 + row % ny, x0, x1, b, e);
+    tile_scan_ranges<TW, (TW < 9 ? TW : 9)>(g.pts, b, e, consider);
   }
 }
-// shell r >= 2 of the coarse grid, 8 ranges at a time
-__device__ __forceinline__ void tile_shell_nn1(const GridView& g, bool active, float4 sel, int r, float& d, int& id) {
-  const int tl = (int)tile_lane();
+// Shell r >= 2 of a grid, TW/2 rows per step.  Rows (and end cells) whose cell box is farther from the query than the
+// current bound min(best, gate) are skipped: a point `k` cells away along an axis is more than (k - 1) cells away.
+template <int TW>
+__device__ __forceinline__ void tile_shell_nn1(const GridView& g, bool active, float4 sel, int r, float gate, float& d, int& id) {
+  const int tl = (int)tile_lane<TW>();
+  constexpr int H = TW / 2;
   const int cx = cell_coord(sel.x, g.inv_cell) - g.org[0], cy = cell_coord(sel.y, g.inv_cell) - g.org[1], cz = cell_coord(sel.z, g.inv_cell_z) - g.org[2];
   auto consider = [&](float4 p, int) {
     const int i = __float_as_int(p.w);
     const float dd = sqdist3(p, sel.x, sel.y, sel.z);
     if (dd < d || (dd == d && i < id)) { d = dd; id = i; }
   };
+  const float cz_size = 1.0f / g.inv_cell_z;
   const int side = 2 * r + 1, nrows = side * side;
-  for (int base = 0; base < nrows; base += 4) {   // 4 rows per step: lanes 0..3 left / full part, lanes 4..7 right part
-    const int row = base + (tl & 3);
+  for (int base = 0; base < nrows; base += H) {   // lanes 0..H-1 left / full part, lanes H..TW-1 right part
+    const int row = base + (tl % H);
     unsigned b = 0, e = 0;
     if (active && row < nrows) {
       const int dz = row / side - r, dy = row % side - r;
-      const bool edge = dz == -r || dz == r || dy == -r || dy == r;
-      if (edge) { if (tl < 4) row_bounds(g, cz + dz, cy + dy, cx - r, cx + r, b, e); }
-      else row_bounds(g, cz + dz, cy + dy, tl < 4 ? cx - r : cx + r, tl < 4 ? cx - r : cx + r, b, e);
+      const float gz = (float)max(abs(dz) - 1, 0) * cz_size, gy = (float)max(abs(dy) - 1, 0) * g.cell;
+      const float bound = fminf(d, gate);
+      if (!(gz * gz + gy * gy > bound)) {
+        const bool edge = dz == -r || dz == r || dy == -r || dy == r;
+        if (edge) { if (tl < H) row_bounds(g, cz + dz, cy + dy, cx - r, cx + r, b, e); }
+        else {
+          const float gx = (float)(r - 1) * g.cell;
+          if (!(gz * gz + gy * gy + gx * gx > bound)) row_bounds(g, cz + dz, cy + dy, tl < H ? cx - r : cx + r, tl < H ? cx - r : cx + r, b, e);
+        }
+      }
     }
-    tile_scan_ranges(g.pts, b, e, consider);
+    tile_scan_ranges<TW, TW>(g.pts, b, e, consider);
   }
 }
 
+// factor record + correspondence probes of one feature (laserOdometry.cpp:442-462 / :534-557); returns the factor type
+__device__ __forceinline__ int odo_emit(const OdoArgs& a, int lane, int f, int ns, bool corner, bool ok, float4 pt, const float4* C, int closest, float4 pj,
+                                        int same, int other) {
+  LvoFactor fac;
+  fac.type = -1; fac.pad = 0; fac.d = 0;
+  int i1 = -1, i2 = -1, i3 = -1;
+  if (ok) {
+    if (corner) {
+      if (other >= 0) {
+        i1 = closest; i2 = other;
+        const float4 pb = C[other];
+        fac.type = 0;
+        fac.c[0] = pt.x; fac.c[1] = pt.y; fac.c[2] = pt.z;
+        fac.a[0] = pj.x; fac.a[1] = pj.y; fac.a[2] = pj.z;
+        fac.b[0] = pb.x; fac.b[1] = pb.y; fac.b[2] = pb.z;
+      }
+    } else if (same >= 0 && other >= 0) {
+      i1 = closest; i2 = same; i3 = other;
+      const float4 pl = C[same], pm = C[other];
+      // LidarPlaneFactor constructor, lidarFactor.hpp:64-65
+      const d3 jl{(double)pj.x - (double)pl.x, (double)pj.y - (double)pl.y, (double)pj.z - (double)pl.z};
+      const d3 jm{(double)pj.x - (double)pm.x, (double)pj.y - (double)pm.y, (double)pj.z - (double)pm.z};
+      d3 n = d3cross(jl, jm);
+      const double nn = sqrt(n.x * n.x + n.y * n.y + n.z * n.z);
+      fac.type = 1;
+      fac.c[0] = pt.x; fac.c[1] = pt.y; fac.c[2] = pt.z;
+      fac.a[0] = pj.x; fac.a[1] = pj.y; fac.a[2] = pj.z;
+      fac.b[0] = n.x / nn; fac.b[1] = n.y / nn; fac.b[2] = n.z / nn;
+    }
+  }
+  a.factors[(size_t)lane * a.factor_cap + f] = fac;
+  if (corner) {
+    int* c = a.corner_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer) * a.cap_sharp + f) * 2;
+    c[0] = i1; c[1] = i2;
+  } else {
+    int* c = a.plane_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer) * a.cap_flat + (f - ns)) * 3;
+    c[0] = i1; c[1] = i2; c[2] = i3;
+  }
+  return fac.type;
+}
+
+// Fast path for outer iterations >= 1: ONE THREAD per feature.  A feature qualifies when the previous outer iteration
+// produced a factor for it (so the previous closest / same-ring / adjacent-ring points exist and bound the new searches)
+// and the bounds are tight enough for a box query on the fine grid; every search then touches a handful of candidates and
+// the per-feature overhead is shared by 32 features per warp instead of 4.  Features that do not qualify are appended to
+// `slow_list` and processed by the tile kernel below.  Same results: both paths compute exact minima with the same keys.
+// four independent loads in flight per thread
+template <class F>
+__device__ __forceinline__ void scan_range4(const float4* __restrict__ pts, unsigned b, unsigned e, F&& f) {
+  for (unsigned t = b; t < e; t += 4) {
+    const unsigned last = e - 1;
+    const float4 p0 = __ldg(pts + t), p1 = __ldg(pts + min(t + 1, last)), p2 = __ldg(pts + min(t + 2, last)), p3 = __ldg(pts + min(t + 3, last));
+    f(p0);
+    if (t + 1 < e) f(p1);
+    if (t + 2 < e) f(p2);
+    if (t + 3 < e) f(p3);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
+  __shared__ GridView gv[4];
+  const int lane = blockIdx.y;
+  LaneState& s = a.ls[lane];
+  if (!s.odo_inited) return;
+  if (threadIdx.x < 4) gv[threadIdx.x] = grid_view(a.grid, 8 * lane + threadIdx.x);
+  __syncthreads();
+  const int ns = s.n_sharp, nf = s.n_flat;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  bool made_c = false, made_p = false;
+  if (f < ns + nf) {
+    const bool corner = f < ns;
+    const float4* C = corner ? a.corner_last + (size_t)lane * a.cap_lsharp : a.surf_last + (size_t)lane * a.P;
+    const GridView& g = gv[corner ? 0 : 1];
+    const GridView& gaz = gv[corner ? 2 : 3];
+    const float4 pt = corner ? a.sharp[(size_t)lane * a.cap_sharp + f] : a.flat[(size_t)lane * a.cap_flat + (f - ns)];
+    const float4 sel = transform_point(s.para_q, s.para_t, pt);
+    int pc = -1, pA = -1, pB = -1;
+    if (a.outer > 0) {
+      if (corner) { const int* c = a.corner_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer - 1) * a.cap_sharp + f) * 2; pc = c[0]; pB = c[1]; }
+      else { const int* c = a.plane_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer - 1) * a.cap_flat + (f - ns)) * 3; pc = c[0]; pA = c[1]; pB = c[2]; }
+    }
+    float d = FLT_MAX; int id = INT_MAX;
+    auto near = [&](float4 p) {
+      const int i = __float_as_int(p.w);
+      const float dd = sqdist3(p, sel.x, sel.y, sel.z);
+      if (dd < d || (dd == d && i < id)) { d = dd; id = i; }
+    };
+    const int cx = cell_coord(sel.x, g.inv_cell) - g.org[0], cy = cell_coord(sel.y, g.inv_cell) - g.org[1], cz = cell_coord(sel.z, g.inv_cell_z) - g.org[2];
+    // ---- bound on the closest point: the previous iteration's closest point, else the best point of the query's own cell
+    if (pc >= 0) { d = sqdist3(C[pc], sel.x, sel.y, sel.z); id = pc; }
+    else if (g.dim[0] > 0) { unsigned b, e; row_bounds(g, cz, cy, cx, cx, b, e); scan_range4(g.pts, b, e, near); }
+    float rad = sqrtf(d) * 1.0001f + 1e-5f;
+    bool fast = id != INT_MAX && rad < g.cell && (double)d < 25.0;
+    int closest = -1, same = -1, other = -1;
+    float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (fast) {
+      // ---- closest point: box query on the fine grid (every cell that intersects [q - rad, q + rad])
+      const int x0 = cell_coord(sel.x - rad, g.inv_cell) - g.org[0], x1 = cell_coord(sel.x + rad, g.inv_cell) - g.org[0];
+      const int y0 = cell_coord(sel.y - rad, g.inv_cell) - g.org[1], y1 = cell_coord(sel.y + rad, g.inv_cell) - g.org[1];
+      const int z0 = cell_coord(sel.z - rad, g.inv_cell_z) - g.org[2], z1 = cell_coord(sel.z + rad, g.inv_cell_z) - g.org[2];
+      unsigned rb[9], re[9];   // rad < cell: at most 3 x 3 rows; all bounds are fetched before the first candidate
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        rb[k] = re[k] = 0;
+        const int z = z0 + k / 3, y = y0 + k % 3;
+        if (z <= z1 && y <= y1) row_bounds(g, z, y, x0, x1, rb[k], re[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) scan_range4(g.pts, rb[k], re[k], near);
+      closest = id;
+      pj = C[closest];
+      const int cid = ring_clamped(pj.w);
+      // ---- adjacent-ring searches.  Seeds: the previous iteration's points if they still pass the ring filter, else
+      // the best points of the +-2 bucket windows.
+      Best bA{25.0f, INT_MAX, -1}, bB{25.0f, INT_MAX, -1};
+      auto seed = [&](int pidx, bool same_ring, Best& best) {
+        if (pidx < 0 || pidx == closest) return;
+        const float4 p = C[pidx];
+        const int dr = ring_clamped(p.w) - cid;
+        if (same_ring ? (dr != 0) : (dr == 0 || dr > 2 || dr < -2)) return;
+        if ((pidx > closest && dr < 0) || (pidx < closest && dr > 0)) return;
+        const float dd = (p.x - sel.x) * (p.x - sel.x) + (p.y - sel.y) * (p.y - sel.y) + (p.z - sel.z) * (p.z - sel.z);
+        if (!(dd < 25.0f)) return;
+        best = Best{dd, pidx > closest ? (pidx - closest) : ((closest - pidx) + (1 << 30)), pidx};
+      };
+      if (!corner) seed(pA, true, bA);
+      seed(pB, false, bB);
+      const float rho = sqrtf(sel.x * sel.x + sel.y * sel.y);
+      const int bq = az_bucket(sel.x, sel.y);
+      auto scan_windows = [&](int hA, int hB, int skipA, int skipB) {   // buckets with |offset| <= skip were scanned before
+        unsigned wb[10], we[10];   // (ring slot, side) -> part 0 of the bucket range; fetched together before any candidate
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+          wb[k] = we[k] = 0;
+          const int r = k >> 1, side = k & 1, ring = cid - 2 + r;
+          if (ring < 0 || ring >= LVO_AZ_RINGS || (r == 2 && corner)) continue;
+          const int h = r == 2 ? hA : hB, skip = r == 2 ? skipA : skipB;
+          if (h <= skip) continue;
+          int lo, hi;
+          if (skip < 0) { if (side) continue; lo = bq - h; hi = bq + h; }
+          else if (side == 0) { lo = bq - h; hi = bq - skip - 1; }
+          else { lo = bq + skip + 1; hi = bq + h; }
+          az_bounds(gaz, ring, lo, hi, 0, wb[k], we[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+          const int dr = (k >> 1) - 2;
+          auto cand = [&](float4 p) {
+            const int idx = __float_as_int(p.w);
+            if (idx == closest) return;
+            if ((idx > closest && dr < 0) || (idx < closest && dr > 0)) return;
+            const float dd = (p.x - sel.x) * (p.x - sel.x) + (p.y - sel.y) * (p.y - sel.y) + (p.z - sel.z) * (p.z - sel.z);
+            if (!(dd < 25.0f)) return;
+            const Best c{dd, idx > closest ? (idx - closest) : ((closest - idx) + (1 << 30)), idx};
+            if (dr == 0) bA = best_min(bA, c); else bB = best_min(bB, c);
+          };
+          scan_range4(gaz.pts, wb[k], we[k], cand);
+        }
+        // wrapped windows (the range crosses bucket 0): second part, rare
+        const int hmax = max(hA, hB);
+        if (bq - hmax < 0 || bq + hmax >= LVO_AZ_BUCKETS) {
+          for (int k = 0; k < 10; ++k) {
+            const int r = k >> 1, side = k & 1, ring = cid - 2 + r, dr = r - 2;
+            if (ring < 0 || ring >= LVO_AZ_RINGS || (r == 2 && corner)) continue;
+            const int h = r == 2 ? hA : hB, skip = r == 2 ? skipA : skipB;
+            if (h <= skip) continue;
+            int lo, hi;
+            if (skip < 0) { if (side) continue; lo = bq - h; hi = bq + h; }
+            else if (side == 0) { lo = bq - h; hi = bq - skip - 1; }
+            else { lo = bq + skip + 1; hi = bq + h; }
+            unsigned b, e;
+            az_bounds(gaz, ring, lo, hi, 1, b, e);
+            auto cand = [&](float4 p) {
+              const int idx = __float_as_int(p.w);
+              if (idx == closest) return;
+              if ((idx > closest && dr < 0) || (idx < closest && dr > 0)) return;
+              const float dd = (p.x - sel.x) * (p.x - sel.x) + (p.y - sel.y) * (p.y - sel.y) + (p.z - sel.z) * (p.z - sel.z);
+              if (!(dd < 25.0f)) return;
+              const Best c{dd, idx > closest ? (idx - closest) : ((closest - idx) + (1 << 30)), idx};
+              if (dr == 0) bA = best_min(bA, c); else bB = best_min(bB, c);
+            };
+            scan_range4(gaz.pts, b, e, cand);
+          }
+        }
+      };
+      int sA = -1, sB = -1;   // half-widths already scanned
+      if ((!corner && bA.j < 0) || bB.j < 0) {   // no seed for some target: first look at +-2 buckets
+        const int wA = (!corner && bA.j < 0) ? 2 : -1, wB = bB.j < 0 ? 2 : -1;
+        scan_windows(wA < 0 ? 0 : wA, wB < 0 ? 0 : wB, wA < 0 ? 0 : -1, wB < 0 ? 0 : -1);
+        if (wA >= 0) sA = wA;
+        if (wB >= 0) sB = wB;
+      }
+      const int hA = corner ? 0 : (bA.j >= 0 ? az_halfwidth(bA.d, rho) : LVO_AZ_BUCKETS);
+      const int hB = bB.j >= 0 ? az_halfwidth(bB.d, rho) : LVO_AZ_BUCKETS;
+      if (hA > 6 || hB > 6) fast = false;   // a target has no candidate nearby or its window is wide: leave it to the cooperative kernel
+      if (fast) {
+        scan_windows(hA, hB, corner ? hA : sA, sB);
+        same = bA.j; other = bB.j;
+      }
+    }
+    if (fast) {
+      const int type = odo_emit(a, lane, f, ns, corner, true, pt, C, closest, pj, same, other);
+      made_c = corner && type >= 0; made_p = !corner && type >= 0;
+    } else {
+      a.slow_list[(size_t)lane * (a.cap_sharp + a.cap_flat) + atomicAdd(&a.slow_cnt[lane], 1)] = f;
+    }
+  }
+  const int nc = __popc(__ballot_sync(0xffffffffu, made_c)), np = __popc(__ballot_sync(0xffffffffu, made_p));
+  if ((threadIdx.x & 31) == 0) {
+    if (nc) atomicAdd(&s.stats.odo_corner_corr[a.outer], nc);
+    if (np) atomicAdd(&s.stats.odo_plane_corr[a.outer], np);
+  }
+}
+
+template <int TW>
 __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
   __shared__ GridView gv[8];
   const int lane = blockIdx.y;
@@ -151,17 +380,20 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
   if (threadIdx.x < 8) gv[threadIdx.x] = grid_view(a.grid, 8 * lane + threadIdx.x);
   __syncthreads();
   const int ns = s.n_sharp, nf = s.n_flat;
-  const int tl = (int)tile_lane();
-  const int f = (blockIdx.x * blockDim.x + threadIdx.x) / LVO_TW;   // one tile per feature
-  if (__all_sync(0xffffffffu, f >= ns + nf)) return;                // whole warp idle
-  const bool have = f < ns + nf;
+  const int tl = (int)tile_lane<TW>();
+  // one tile per feature the fast kernel could not take
+  const int nwork = a.slow_cnt[lane];   // the features the fast kernel could not take
+  const int tiles_total = (gridDim.x * blockDim.x) / TW;
+  for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) / TW;; slot += tiles_total) {
+  if (__all_sync(0xffffffffu, slot >= nwork)) break;                // whole warp idle
+  const bool have = slot < nwork;
+  const int f = have ? a.slow_list[(size_t)lane * (a.cap_sharp + a.cap_flat) + slot] : ns + nf;
   const bool corner = f < ns;
   const double* q = s.para_q; const double* t = s.para_t;
   const float4* C = corner ? a.corner_last + (size_t)lane * a.cap_lsharp : a.surf_last + (size_t)lane * a.P;
   const GridView& gfine = gv[corner ? 0 : 1];
   const GridView& gaz = gv[corner ? 2 : 3];
   const GridView& gmid = gv[corner ? 4 : 5];
-  const GridView& gcoarse = gv[corner ? 6 : 7];
   float4 pt = make_float4(0.f, 0.f, 0.f, 0.f), sel = pt;
   if (have) {
     pt = corner ? a.sharp[(size_t)lane * a.cap_sharp + f] : a.flat[(size_t)lane * a.cap_flat + (f - ns)];
@@ -186,31 +418,28 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
     if (rad < gfine.cell) { boxed = true; d = dp; id = pc; }
   }
   if (__any_sync(0xffffffffu, boxed)) {
-    tile_box_nn1(gfine, boxed, sel, sqrtf(d) * 1.0001f + 1e-5f, d, id);
-    key = id; tile_min3(d, key, id);
+    tile_box_nn1<TW>(gfine, boxed, sel, sqrtf(d) * 1.0001f + 1e-5f, d, id);
+    key = id; tile_min3<TW>(d, key, id);
   }
   const bool unboxed = have && !boxed;
   if (__any_sync(0xffffffffu, unboxed)) {
-    tile_block_nn1(gfine, unboxed, sel, d, id);
-    key = id; tile_min3(d, key, id);
+    tile_block_nn1<TW>(gfine, unboxed, sel, d, id);
+    key = id; tile_min3<TW>(d, key, id);
   }
   bool more = unboxed && !(d < gfine.cell * gfine.cell);
   if (__any_sync(0xffffffffu, more)) {
-    tile_block_nn1(gmid, more, sel, d, id);
-    key = id; tile_min3(d, key, id);
+    tile_block_nn1<TW>(gmid, more, sel, d, id);
+    key = id; tile_min3<TW>(d, key, id);
     more = more && !(d < gmid.cell * gmid.cell);
-  }
-  if (__any_sync(0xffffffffu, more)) {
-    tile_block_nn1(gcoarse, more, sel, d, id);
-    key = id; tile_min3(d, key, id);
-    more = more && !(d < gcoarse.cell * gcoarse.cell);
-    const int R = (int)ceilf(5.0f * gcoarse.inv_cell);
+    // beyond the 27 middle cells: shells of the middle grid, pruned by min(best, gate) (the coarse grid is kept only as the
+    // fallback for clouds whose bounding box forced larger middle cells)
+    const int R = (int)ceilf(5.0f * gmid.inv_cell);
     for (int r = 2; r <= R; ++r) {
-      const float bound = (float)(r - 1) * gcoarse.cell;
+      const float bound = (float)(r - 1) * gmid.cell;
       more = more && !(d < bound * bound);
       if (!__any_sync(0xffffffffu, more)) break;
-      tile_shell_nn1(gcoarse, more, sel, r, d, id);
-      key = id; tile_min3(d, key, id);
+      tile_shell_nn1<TW>(gmid, more, sel, r, 25.0f, d, id);
+      key = id; tile_min3<TW>(d, key, id);
     }
   }
   const bool ok = have && id != INT_MAX && (double)d < 25.0;
@@ -255,9 +484,9 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
   for (int part = 0; part < 2; ++part) {
     unsigned b = 0, e = 0;
     if (ring_ok) az_bounds(gaz, ring, bq - h1, bq + h1, part, b, e);
-    tile_scan_ranges(gaz.pts, b, e, consider);
+    tile_scan_ranges<TW, 5>(gaz.pts, b, e, consider);
   }
-  tile_min3(bA.d, bA.pos, bA.j); tile_min3(bB.d, bB.pos, bB.j);
+  tile_min3<TW>(bA.d, bA.pos, bA.j); tile_min3<TW>(bB.d, bB.pos, bB.j);
   {  // phase 2: the rest of the window implied by the best distances so far (or by the 5 m gate)
     const int h = ring == cid ? (needA ? az_halfwidth(bA.d, rho) : 0) : az_halfwidth(bB.d, rho);
     const bool whole = 2 * h + 1 >= LVO_AZ_BUCKETS;
@@ -270,58 +499,24 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
           else if ((sp >> 1) == 0) az_bounds(gaz, ring, bq - h, bq - h1 - 1, sp & 1, b, e);
           else az_bounds(gaz, ring, bq + h1 + 1, bq + h, sp & 1, b, e);
         }
-        tile_scan_ranges(gaz.pts, b, e, consider);
+        tile_scan_ranges<TW, 5>(gaz.pts, b, e, consider);
       }
-      tile_min3(bA.d, bA.pos, bA.j); tile_min3(bB.d, bB.pos, bB.j);
+      tile_min3<TW>(bA.d, bA.pos, bA.j); tile_min3<TW>(bB.d, bB.pos, bB.j);
     }
   }
   const int same = bA.j, other = bB.j;
   // ---- factor record (tile leader)
   bool made_c = false, made_p = false;
   if (have && tl == 0) {
-    LvoFactor fac;
-    fac.type = -1; fac.pad = 0; fac.d = 0;
-    int i1 = -1, i2 = -1, i3 = -1;
-    if (ok) {
-      if (corner) {
-        if (other >= 0) {
-          i1 = closest; i2 = other;
-          const float4 pb = C[other];
-          fac.type = 0;
-          fac.c[0] = pt.x; fac.c[1] = pt.y; fac.c[2] = pt.z;
-          fac.a[0] = pj.x; fac.a[1] = pj.y; fac.a[2] = pj.z;
-          fac.b[0] = pb.x; fac.b[1] = pb.y; fac.b[2] = pb.z;
-        }
-      } else if (same >= 0 && other >= 0) {
-        i1 = closest; i2 = same; i3 = other;
-        const float4 pl = C[same], pm = C[other];
-        // LidarPlaneFactor constructor, lidarFactor.hpp:64-65
-        const d3 jl{(double)pj.x - (double)pl.x, (double)pj.y - (double)pl.y, (double)pj.z - (double)pl.z};
-        const d3 jm{(double)pj.x - (double)pm.x, (double)pj.y - (double)pm.y, (double)pj.z - (double)pm.z};
-        d3 n = d3cross(jl, jm);
-        const double nn = sqrt(n.x * n.x + n.y * n.y + n.z * n.z);
-        fac.type = 1;
-        fac.c[0] = pt.x; fac.c[1] = pt.y; fac.c[2] = pt.z;
-        fac.a[0] = pj.x; fac.a[1] = pj.y; fac.a[2] = pj.z;
-        fac.b[0] = n.x / nn; fac.b[1] = n.y / nn; fac.b[2] = n.z / nn;
-      }
-    }
-    a.factors[(size_t)lane * a.factor_cap + f] = fac;
-    if (corner) {
-      int* c = a.corner_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer) * a.cap_sharp + f) * 2;
-      c[0] = i1; c[1] = i2;
-      made_c = fac.type >= 0;
-    } else {
-      int* c = a.plane_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer) * a.cap_flat + (f - ns)) * 3;
-      c[0] = i1; c[1] = i2; c[2] = i3;
-      made_p = fac.type >= 0;
-    }
+    const int type = odo_emit(a, lane, f, ns, corner, ok, pt, C, closest, pj, same, other);
+    made_c = corner && type >= 0; made_p = !corner && type >= 0;
   }
   const int nc = __popc(__ballot_sync(0xffffffffu, made_c)), np = __popc(__ballot_sync(0xffffffffu, made_p));
   if ((threadIdx.x & 31) == 0) {
     if (nc) atomicAdd(&s.stats.odo_corner_corr[a.outer], nc);
     if (np) atomicAdd(&s.stats.odo_plane_corr[a.outer], np);
   }
+  }  // slot loop
 }
 
 // after the outer loop: few-correspondence warning (:566-568), pose integration (:581-582)
@@ -368,10 +563,16 @@ static inline void lvo_launch_odometry(cudaStream_t st, OdoArgs a, const SolveAr
   k_odo_begin<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a);
   if (launches) *launches += 1;
   const int nfeat_cap = a.cap_sharp + a.cap_flat;
-  dim3 ga(max(1, lvo_div_up(nfeat_cap * LVO_TW, 256)), lanes);
+  dim3 ga(max(1, lvo_div_up(nfeat_cap * 8, 256)), lanes);          // 8-lane tiles, every feature (outer iteration 0)
+  dim3 gs(max(1, lvo_div_up(nfeat_cap * 32 / 8, 256)), lanes);     // full-warp tiles for the slow list (an eighth of the features per pass, grid-strided)
+  dim3 gf(max(1, lvo_div_up(nfeat_cap, 128)), lanes);
   for (int o = 0; o < outer_iters; ++o) {
     a.outer = o;
-    k_odo_assoc<<<ga, 256, 0, st>>>(a);
+    cudaMemsetAsync(a.slow_cnt, 0, sizeof(int) * lanes, st);
+    k_odo_assoc_fast<<<gf, 128, 0, st>>>(a);
+    if (launches) *launches += 1;
+    if (o == 0) k_odo_assoc<8><<<ga, 256, 0, st>>>(a);   // first iteration: more features lack a nearby candidate
+    else k_odo_assoc<32><<<gs, 256, 0, st>>>(a);
     SolveArgs sa = solve_proto;
     sa.which = 0; sa.outer = o; sa.factors = a.factors; sa.factor_cap = a.factor_cap;
     lvo_launch_lm(st, sa, lanes);
