@@ -145,7 +145,11 @@ def knn_throughput(L, frames, reps, device):
     ctx.close()
     alg = 16.0 * sum(mc) + 56.0 * sum(qc)
     found = float((ind[:, 0] >= 0).float().mean())
-    return {"problems": len(mc), "map_points_total": int(sum(mc)), "queries_total": int(sum(qc)), "map_bytes": 16 * int(sum(mc)), "kernel_ms": ms,
+    return {"kernel": "k_knn5_batch (same search as k_map_knn, 256 problems per launch, L2 flushed before every timed launch)",
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r1_knn5_batch_throughput_ncu.csv (128 frames): the
+            # grid search only touches the cells around the queries, so DRAM traffic is ~0.27 x the algorithmic 16 M + 56 Q bytes
+            "traffic": 283.8e6 if frames == 128 else None,
+            "problems": len(mc), "map_points_total": int(sum(mc)), "queries_total": int(sum(qc)), "map_bytes": 16 * int(sum(mc)), "kernel_ms": ms,
             "algorithmic_bytes_per_launch": alg, "achieved_gbs": alg / 1e9 / (ms * 1e-3), "queries_with_5_neighbours": found, "reps": reps}
 
 
@@ -216,6 +220,8 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sampler = ClockSampler(local_rank)
+    sampler.start()   # early: nvidia-smi's start-up (NVML init takes a driver lock) must not fall into a timed region
     L = load_pkg()
     if args.only_knn:
         print(json.dumps({"knn_throughput": knn_throughput(L, args.knn_frames, 5, local_rank)}), flush=True)
@@ -294,8 +300,6 @@ def main():
         assert st >= 0
         host_views.pop(k - 1, None)
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     if args.skip_e2e:
         ms_e, wall_e = float("nan"), float("nan")
     else:
@@ -359,7 +363,10 @@ def main():
                 "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": h2d[0], "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / args.steps},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": "k_map_knn (5-NN grid search, thread per query)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src, "launches": knn_launches,
+                             "frac": achieved / peak if peak else None,
+                             # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full`, 128 lanes, 5th step
+                             # (profiles/r1_final_hot_kernels_l128_ncu.csv); null for other lane counts
+                             "traffic": 41.0e6 if lanes == 128 else None, "peak_source": peak_src, "launches": knn_launches,
                              "avg_launch_us": 1e3 * knn_ms / max(knn_launches, 1), "algorithmic_bytes_per_launch": knn_bytes / max(knn_launches, 1)},
                 "knn_throughput": knn_tp, "cpu_baseline": cpu, "clocks": clocks,
                 "host": {"wall_ms_per_step_dev": 1e3 * wall_d / args.steps, "wall_ms_per_step_e2e": 1e3 * wall_e / args.steps, "gen_s": t_gen, "cores": host_threads}}

@@ -139,9 +139,10 @@ __global__ void k_setup_grid_problems(GridProblem* prob, int nprob, const float4
   prob[p].want_cell_z = which == 0 ? (k >= 6 ? 8.0f : 2.0f) : 0.f;
   prob[p].mode = (which == 0 && (k == 2 || k == 3)) ? 1 : 0;
   prob[p].clamp_xy = 0.f;
+  prob[p].bbox_from = (which == 0 && k >= 4) ? p - k + (k & 1) : -1;   // middle / coarse grids reuse the fine grid's box
 }
 __global__ void k_setup_one_problem(GridProblem* prob, const float4* pts, const int* d_n, float cell, float clamp = 0.f) {
-  prob[0].pts = pts; prob[0].d_n = d_n; prob[0].want_cell = cell; prob[0].want_cell_z = 0.f; prob[0].mode = 0; prob[0].clamp_xy = clamp;
+  prob[0].pts = pts; prob[0].d_n = d_n; prob[0].want_cell = cell; prob[0].want_cell_z = 0.f; prob[0].mode = 0; prob[0].clamp_xy = clamp; prob[0].bbox_from = -1;
 }
 __global__ void k_vx_single_setup(VoxelEngine e, int n, float leaf) {
   if (blockIdx.x == 0 && threadIdx.x == 0) { *e.d_n = n; *e.d_nsegs = 1; e.seg_leaf[0] = leaf; }
@@ -756,7 +757,7 @@ int lvo_knn(lvo_ctx* c, lvo_cloud_view cloud, lvo_cloud_view queries, int K, flo
 __global__ void k_setup_batch_problems(GridProblem* prob, int S, const float4* maps, const unsigned* m_off, const int* m_cnt, float cell) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= S) return;
-  prob[p].pts = maps + m_off[p]; prob[p].d_n = m_cnt + p; prob[p].want_cell = cell; prob[p].want_cell_z = 0.f; prob[p].mode = 0; prob[p].clamp_xy = 0.f;
+  prob[p].pts = maps + m_off[p]; prob[p].d_n = m_cnt + p; prob[p].want_cell = cell; prob[p].want_cell_z = 0.f; prob[p].mode = 0; prob[p].clamp_xy = 0.f; prob[p].bbox_from = -1;
 }
 
 int lvo_depth_associate(lvo_ctx* c, lvo_cloud_view sweep, const lvo_camera* cam, const float* keypoints_uv, size_t n_kp, float* depth_out, int* valid_out,

@@ -21,7 +21,7 @@
 
 #define LVO_EX_THREADS 256
 #define LVO_PICK_THREADS 128
-#define LVO_PICK_SMEM_KEYS 2048  // sectors / ring voxel inputs up to this size sort in shared memory
+#define LVO_PICK_SMEM_KEYS 3072  // 6 x 512 padded sector keys, or one ring's voxel keys (24 KB)
 
 struct ExtractArgs {
   // input
@@ -272,6 +272,22 @@ __device__ __forceinline__ void block_bitonic_sort(unsigned long long* keys, int
     }
 }
 __device__ __forceinline__ int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+// nseg independent ascending sorts of npad keys each (segment s at keys + s * npad), one block barrier per network step
+__device__ __forceinline__ void block_bitonic_sort_multi(unsigned long long* keys, int nseg, int npad) {
+  const int half = npad >> 1, total = nseg * half;
+  for (int k = 2; k <= npad; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        const int sg = t / half, u = t - sg * half;
+        const int i = ((u & ~(j - 1)) << 1) | (u & (j - 1));   // u-th index with bit j clear
+        unsigned long long* kk = keys + sg * npad;
+        const unsigned long long x = kk[i], y = kk[i | j];
+        const bool up = (i & k) == 0;
+        if ((x > y) == up) { kk[i] = y; kk[i | j] = x; }
+      }
+      __syncthreads();
+    }
+}
 
 // Marks the neighbours of a picked point (:319-342 / :365-388).  Called by a full warp.
 __device__ __forceinline__ void mark_neighbours(volatile int* picked, const unsigned char* gapbig, int ind, unsigned ln) {
@@ -309,22 +325,45 @@ __global__ void __launch_bounds__(LVO_PICK_THREADS) k_sector_pick(ExtractArgs a)
   if (threadIdx.x < LVO_SECTORS * 3) a.slot_cnt[sbase * 3 + threadIdx.x] = 0;
   if (E - S < 6) return;  // :279-280
 
+  // ---- :288 sort cloudSortInd[sp..ep] by (curvature, index) ascending.  When six padded sectors fit in shared memory
+  // they are sorted together (one block barrier per network step instead of six).
+  const int mmax = (E - S + 5) / 6 + 1;
+  const int npad_all = next_pow2(mmax);
+  const bool joint = LVO_SECTORS * npad_all <= LVO_PICK_SMEM_KEYS;
+  if (joint) {
+    for (int t = threadIdx.x; t < LVO_SECTORS * npad_all; t += blockDim.x) {
+      const int j = t / npad_all, u = t - j * npad_all;
+      const int sp = S + (E - S) * j / 6, ep = S + (E - S) * (j + 1) / 6 - 1;
+      unsigned long long k = ~0ull;
+      if (u <= ep - sp) k = ((unsigned long long)__float_as_uint(curv[sp + u]) << 32) | (unsigned)(sp + u);  // curvature >= 0: bit order == value order
+      skeys[t] = k;
+    }
+    __syncthreads();
+    block_bitonic_sort_multi(skeys, LVO_SECTORS, npad_all);
+    for (int t = threadIdx.x; t < LVO_SECTORS * npad_all; t += blockDim.x) {
+      const int j = t / npad_all, u = t - j * npad_all;
+      const int sp = S + (E - S) * j / 6, ep = S + (E - S) * (j + 1) / 6 - 1;
+      if (u <= ep - sp) sort_ind[sp + u] = (int)(unsigned)(skeys[t] & 0xffffffffull);
+    }
+    __syncthreads();
+  }
   for (int j = 0; j < LVO_SECTORS; ++j) {
     const int sp = S + (E - S) * j / 6;            // :284
     const int ep = S + (E - S) * (j + 1) / 6 - 1;  // :285
     const int m = ep - sp + 1;
-    // ---- :288 sort cloudSortInd[sp..ep] by (curvature, index) ascending
-    const int npad = next_pow2(m);
-    unsigned long long* keys = (npad <= LVO_PICK_SMEM_KEYS) ? skeys : (a.sort_scratch + (size_t)lane * 2 * a.P + 2 * (size_t)sp);
-    for (int t = threadIdx.x; t < npad; t += blockDim.x) {
-      unsigned long long k = ~0ull;
-      if (t < m) k = ((unsigned long long)__float_as_uint(curv[sp + t]) << 32) | (unsigned)(sp + t);  // curvature >= 0: bit order == value order
-      keys[t] = k;
+    if (!joint) {
+      const int npad = next_pow2(m);
+      unsigned long long* keys = (npad <= LVO_PICK_SMEM_KEYS) ? skeys : (a.sort_scratch + (size_t)lane * 2 * a.P + 2 * (size_t)sp);
+      for (int t = threadIdx.x; t < npad; t += blockDim.x) {
+        unsigned long long k = ~0ull;
+        if (t < m) k = ((unsigned long long)__float_as_uint(curv[sp + t]) << 32) | (unsigned)(sp + t);
+        keys[t] = k;
+      }
+      __syncthreads();
+      block_bitonic_sort(keys, npad);
+      for (int t = threadIdx.x; t < m; t += blockDim.x) sort_ind[sp + t] = (int)(unsigned)(keys[t] & 0xffffffffull);
+      __syncthreads();
     }
-    __syncthreads();
-    block_bitonic_sort(keys, npad);
-    for (int t = threadIdx.x; t < m; t += blockDim.x) sort_ind[sp + t] = (int)(unsigned)(keys[t] & 0xffffffffull);
-    __syncthreads();
     // ---- greedy picks, warp 0 (sequential semantics, 32 candidates examined per step)
     if (w == 0) {
       int nsharp = 0, nls = 0, largest = 0;

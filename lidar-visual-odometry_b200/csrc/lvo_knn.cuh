@@ -29,6 +29,8 @@ struct GridProblem {   // device-resident descriptor
   float want_cell;     // requested cell size in x and y (power of two)
   float want_cell_z;   // requested cell size in z (power of two; 0 = same as want_cell)
   int mode;            // 0: uniform xyz grid; 1: (ring, azimuth) grid — cell = ring * LVO_AZ_BUCKETS + azimuth bucket
+  int bbox_from;       // >= 0: this problem searches the same cloud as problem `bbox_from` (offset back from its own index is
+                       //       not used; absolute index) and copies its bounding box instead of recomputing it
   float clamp_xy;      // > 0: the table only covers |x|, |y| <= clamp_xy; points outside go to the border cells (their true
                        //      distance is larger than the cell suggests, so every ring bound stays valid)
   // filled by k_grid_setup
@@ -86,7 +88,7 @@ __global__ void k_grid_reset(GridSet g) {
 __global__ void k_grid_bbox(GridSet g) {
   const int p = blockIdx.y;
   GridProblem& q = g.prob[p];
-  if (q.mode == 1) return;  // the (ring, azimuth) grid has fixed dimensions
+  if (q.mode == 1 || q.bbox_from >= 0) return;  // fixed dimensions / box copied from the problem that shares the cloud
   const int n = *q.d_n;
   int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(256) k_grid_setup(GridSet g) {
     unsigned my_cells = 0, my_pts = 0;
     if (p < g.nprob) {
       GridProblem& q = g.prob[p];
+      if (q.bbox_from >= 0) for (int c = 0; c < 3; ++c) { q.bb_mn[c] = g.prob[q.bbox_from].bb_mn[c]; q.bb_mx[c] = g.prob[q.bbox_from].bb_mx[c]; }
       float cell = q.want_cell, cellz = q.want_cell_z > 0.f ? q.want_cell_z : q.want_cell;
       int org[3] = {0, 0, 0}, dim[3] = {0, 0, 0};
       long long nc = 0;
@@ -184,7 +187,8 @@ __global__ void k_grid_fill(GridSet g) {
 }
 
 static inline void lvo_grid_build(cudaStream_t st, const GridSet& g, long long* launches) {
-  const int gx = max(1, min(lvo_div_up(g.pts_cap_per_problem, 256), 296));
+  // grid-stride kernels: a few thousand threads per problem are enough; capacity-sized grids would launch ~300 k idle blocks
+  const int gx = max(1, min(lvo_div_up(g.pts_cap_per_problem, 256), max(24, 2368 / g.nprob)));
   dim3 gp(gx, g.nprob);
   k_grid_reset<<<lvo_div_up(g.nprob, 64), 64, 0, st>>>(g);
   k_grid_bbox<<<gp, 256, 0, st>>>(g);
