@@ -153,6 +153,45 @@ def knn_throughput(L, frames, reps, device):
             "algorithmic_bytes_per_launch": alg, "achieved_gbs": alg / 1e9 / (ms * 1e-3), "queries_with_5_neighbours": found, "reps": reps}
 
 
+def extra_configs(L, device):
+    """BASELINE configs 2 and 5 (reported next to the headline, not part of it).
+    config 2: VLP-16 extract + scan-to-scan latency per frame through the host API (one trajectory, wall clock).
+    config 5: camera-lidar depth association of 1120 keypoints against HDL-64 sweeps (wall clock, host API)."""
+    from oracle_py import Synth
+    synth = Synth()
+    out = {}
+    ctx = L.Lvo(n_scans=16, minimum_range=0.3, line_res=0.2, plane_res=0.4, device=device, max_points=65536, max_map_corner=1 << 16, max_map_surf=1 << 17)
+    sweeps = [synth.sweep(16, 0, k)[0] for k in range(60)]
+    lat = []
+    for k, sw in enumerate(sweeps):
+        t0 = time.perf_counter()
+        _, f = ctx.extract_features(sw)
+        ctx.scan_to_scan(f["sharp"], f["less_sharp"], f["flat"], f["less_flat"])
+        if k >= 10:
+            lat.append(1e3 * (time.perf_counter() - t0))
+    ctx.close()
+    out["config2_vlp16_scan_to_scan_latency_ms"] = {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)), "frames": len(lat),
+                                                     "what": "lvo_extract_features + lvo_scan_to_scan per frame, host API incl. python binding"}
+    ctx = L.Lvo(device=device, max_points=131072, max_map_corner=1 << 16, max_map_surf=1 << 17)
+    cam = L.KITTI00_CAMERA
+    rng = np.random.default_rng(5)
+    px = np.stack([rng.uniform(20, cam["width"] - 20, 1120), rng.uniform(15, cam["height"] - 15, 1120)], 1)
+    uv = np.stack([(px[:, 0] - cam["cx"]) / cam["fx"], (px[:, 1] - cam["cy"]) / cam["fy"]], 1).astype(np.float32)
+    sweeps = [synth.sweep(64, 0, k)[0] for k in range(12)]
+    for sw in sweeps[:2]:
+        ctx.depth_associate(sw, uv)
+    t0 = time.perf_counter()
+    valid = 0
+    for sw in sweeps[2:]:
+        _, d, v, _ = ctx.depth_associate(sw, uv)
+        valid += int(v.sum())
+    dt = time.perf_counter() - t0
+    ctx.close()
+    out["config5_depth_association"] = {"sweeps_per_s": 10 / dt, "keypoints_per_s": 11200 / dt, "valid_fraction": valid / 11200.0,
+                                        "what": "lvo_depth_associate, 120k-point sweep + 1120 keypoints per call, host API"}
+    return out
+
+
 def run_reference(args, rank, world):
     """CPU oracle with all host threads: one independent sequence per thread."""
     if rank != 0:
@@ -201,6 +240,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: only the device-resident arm")
     ap.add_argument("--knn-frames", type=int, default=128, help="throughput-mode 5-NN: number of config-3 frames in one launch (0 = skip)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config-2 / config-5 side measurements")
     ap.add_argument("--only-knn", action="store_true", help="profiling aid: only the throughput-mode 5-NN measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -338,6 +378,9 @@ def main():
         torch.cuda.empty_cache()
         knn_tp = knn_throughput(L, args.knn_frames, 5, local_rank)
         knn_tp["frac"] = knn_tp["achieved_gbs"] / peak
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = extra_configs(L, local_rank)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle_py import Oracle
@@ -368,7 +411,7 @@ def main():
                              # (profiles/r1_final_hot_kernels_l128_ncu.csv); null for other lane counts
                              "traffic": 41.0e6 if lanes == 128 else None, "peak_source": peak_src, "launches": knn_launches,
                              "avg_launch_us": 1e3 * knn_ms / max(knn_launches, 1), "algorithmic_bytes_per_launch": knn_bytes / max(knn_launches, 1)},
-                "knn_throughput": knn_tp, "cpu_baseline": cpu, "clocks": clocks,
+                "knn_throughput": knn_tp, "other_configs": extras, "cpu_baseline": cpu, "clocks": clocks,
                 "host": {"wall_ms_per_step_dev": 1e3 * wall_d / args.steps, "wall_ms_per_step_e2e": 1e3 * wall_e / args.steps, "gen_s": t_gen, "cores": host_threads}}
         print(json.dumps(line), flush=True)
     if world > 1:
