@@ -213,6 +213,11 @@ int lvo_get_timings(const lvo_ctx* ctx, lvo_timings* out);
 /* Enqueue all work of this context on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL restores the
  * context's own stream).  Lets a harness bracket calls with its own CUDA events on the launching stream. */
 int lvo_set_stream(lvo_ctx* ctx, void* cuda_stream);
+/* Options.  LVO_OPT_GRAPHS: 1 = replay the per-frame launch sequence of lvo_step_batch* from a CUDA graph (captured once per
+ * mapping-on/off state and map generation; all data-dependent sizes live on the device, so the sequence is static),
+ * 0 = plain launches (needed for the per-kernel timings of lvo_get_timings), -1 = automatic: graphs when lanes <= 8. */
+#define LVO_OPT_GRAPHS 1
+int lvo_set_option(lvo_ctx* ctx, int option, int value);
 /* Bytes copied device->host per lane at the end of every synchronous call (poses, counters, status). */
 size_t lvo_state_bytes(void);
 

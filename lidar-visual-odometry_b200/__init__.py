@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(HERE, "liblvo.so")
 
 LVO_OK, LVO_E_BADARG, LVO_E_CAPACITY, LVO_E_CUDA, LVO_E_STATE = 0, -1, -2, -3, -4
 LVO_W_FIRST_FRAME, LVO_W_FEW_CORR, LVO_W_MAP_TOO_SMALL = 1, 2, 3
+LVO_OPT_GRAPHS = 1
 
 # enum lvo_probe
 (P_FULL, P_CURVATURE, P_SORT_IND, P_LABEL, P_PICKED, P_SCAN_START, P_SCAN_END, P_SHARP, P_LESS_SHARP, P_FLAT, P_LESS_FLAT,
@@ -68,7 +69,7 @@ class Timings(C.Structure):
 EXPORTS = ["lvo_default_config", "lvo_create", "lvo_destroy", "lvo_last_error", "lvo_get_stats", "lvo_extract_features", "lvo_scan_to_scan",
            "lvo_scan_to_map", "lvo_step_batch", "lvo_step_batch_dev", "lvo_lane_status", "lvo_map_import", "lvo_map_export",
            "lvo_get_map_correction", "lvo_set_map_correction", "lvo_set_odometry_state", "lvo_probe_fetch", "lvo_voxel_downsample", "lvo_knn",
-           "lvo_knn5_throughput", "lvo_get_timings", "lvo_set_stream", "lvo_state_bytes", "lvo_depth_associate", "lvo_step_batch_pipelined"]
+           "lvo_knn5_throughput", "lvo_get_timings", "lvo_set_stream", "lvo_state_bytes", "lvo_depth_associate", "lvo_step_batch_pipelined", "lvo_set_option"]
 
 
 def load_library():
@@ -101,6 +102,7 @@ def load_library():
     L.lvo_knn5_throughput.argtypes = [vp, vp, vp, vp, vp, ip, ip, vp, vp, C.POINTER(C.c_float)]
     L.lvo_get_timings.argtypes = [vp, C.POINTER(Timings)]
     L.lvo_set_stream.argtypes = [vp, vp]
+    L.lvo_set_option.argtypes = [vp, ip, ip]
     L.lvo_state_bytes.restype = C.c_size_t
     L.lvo_depth_associate.argtypes = [vp, CloudView, C.POINTER(Camera), vp, C.c_size_t, vp, vp, vp, C.POINTER(CloudOut)]
     return L
@@ -272,6 +274,9 @@ class Lvo:
 
     def set_stream(self, cuda_stream_handle):
         self._check(self.lib.lvo_set_stream(self.h, C.c_void_p(cuda_stream_handle) if cuda_stream_handle else None))
+
+    def set_option(self, option, value):
+        self._check(self.lib.lvo_set_option(self.h, option, value))
 
     def stats(self, lane=0):
         s = Stats()

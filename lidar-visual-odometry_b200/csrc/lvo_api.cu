@@ -51,6 +51,11 @@ struct lvo_ctx {
   std::vector<cudaEvent_t> knn_ev;
   lvo_timings tim;
   bool have_knn_events = false;
+  // CUDA graphs of the fused per-frame sequence: [mapping on/off][map generation]
+  cudaGraphExec_t graph_exec[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  long long graph_launches[2][2] = {{0, 0}, {0, 0}};
+  int graph_stride = -1, graph_off = -1;
+  int opt_graphs = -1;
 };
 
 void lvo_set_error(lvo_ctx* ctx, const std::string& msg) { if (ctx) ctx->err = msg; }
@@ -220,6 +225,10 @@ void collect_knn_timing(lvo_ctx* c) {
 
 }  // namespace
 
+static void destroy_graphs(lvo_ctx* c) {
+  for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) if (c->graph_exec[a][b]) { cudaGraphExecDestroy(c->graph_exec[a][b]); c->graph_exec[a][b] = nullptr; }
+}
+
 extern "C" {
 
 void lvo_default_config(lvo_config* cfg) {
@@ -369,6 +378,7 @@ int lvo_destroy(lvo_ctx* c) {
   if (c->st) cudaStreamSynchronize(c->st);
   for (void* p : c->allocs) cudaFree(p);
   for (void* p : c->pinned) cudaFreeHost(p);
+  destroy_graphs(c);
   if (c->copy_st) { cudaStreamSynchronize(c->copy_st); cudaStreamDestroy(c->copy_st); cudaEventDestroy(c->copy_ev); cudaEventDestroy(c->compute_ev); }
   if (c->own_st) { for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]); for (auto& e : c->knn_ev) cudaEventDestroy(e); cudaStreamDestroy(c->own_st); }
   delete c;
@@ -384,9 +394,15 @@ int lvo_get_stats(const lvo_ctx* c, int lane, lvo_stats* out, size_t bytes) {
 }
 int lvo_lane_status(const lvo_ctx* c, int lane) { return (c && lane >= 0 && lane < c->lanes) ? c->lane_status[lane] : LVO_E_BADARG; }
 size_t lvo_state_bytes(void) { return sizeof(LaneState); }
+int lvo_set_option(lvo_ctx* c, int option, int value) {
+  if (!c) return LVO_E_BADARG;
+  if (option == LVO_OPT_GRAPHS) { c->opt_graphs = value; return LVO_OK; }
+  return LVO_E_BADARG;
+}
 int lvo_set_stream(lvo_ctx* c, void* cuda_stream) {
   if (!c) return LVO_E_BADARG;
   cudaStreamSynchronize(c->st);
+  destroy_graphs(c);
   c->st = cuda_stream ? (cudaStream_t)cuda_stream : c->own_st;
   return LVO_OK;
 }
@@ -480,21 +496,55 @@ int lvo_scan_to_map(lvo_ctx* c, lvo_cloud_view corner_last, lvo_cloud_view surf_
 static int step_common(lvo_ctx* c, int stride, int off_xyz, int max_n, lvo_pose* T_wodom, lvo_pose* T_wmap) {
   c->launches = 0;
   LVO_TRY(set_inputs(c));
-  cudaEventRecord(c->ev[0], c->st);
-  enqueue_extract(c, stride, off_xyz, max_n);
-  cudaEventRecord(c->ev[1], c->st);
-  c->solve.trace = c->d_trace[0];
-  enqueue_odometry(c);
-  cudaEventRecord(c->ev[2], c->st);
   const bool do_map = (c->frame % c->cfg.skip_frame) == 0;  // laserOdometry.cpp:643
-  if (do_map) { c->solve.trace = c->d_trace[1]; enqueue_mapping(c, 1, true, true); }
-  cudaEventRecord(c->ev[3], c->st);
-  c->frame++;
-  LVO_TRY(sync_state(c));
-  cudaEventElapsedTime(&c->tim.extract_ms, c->ev[0], c->ev[1]);
-  cudaEventElapsedTime(&c->tim.odometry_ms, c->ev[1], c->ev[2]);
-  cudaEventElapsedTime(&c->tim.mapping_ms, c->ev[2], c->ev[3]);
-  if (do_map) collect_knn_timing(c);
+  const bool want_graph = c->opt_graphs == 1 || (c->opt_graphs < 0 && c->lanes <= 8);
+  const bool use_graph = want_graph && c->st != nullptr;    // the legacy default stream cannot be captured
+  if (use_graph) {
+    if (c->graph_stride != stride || c->graph_off != off_xyz) { destroy_graphs(c); c->graph_stride = stride; c->graph_off = off_xyz; }
+    const int gen = c->map.gen;
+    cudaEventRecord(c->ev[0], c->st);
+    if (!c->graph_exec[do_map][gen]) {
+      // capture one frame: the launch sequence is static (grids from capacities, sizes read from device memory)
+      cudaGraph_t graph = nullptr;
+      LVO_CUDA_OK(c, cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
+      enqueue_extract(c, stride, off_xyz, c->P);
+      c->solve.trace = c->d_trace[0];
+      enqueue_odometry(c);
+      if (do_map) { c->solve.trace = c->d_trace[1]; enqueue_mapping(c, 1, true, false); }
+      cudaError_t e = cudaStreamEndCapture(c->st, &graph);
+      if (do_map) c->map.gen = gen;   // enqueue_mapping flipped it; the flip belongs to the execution below
+      if (e != cudaSuccess || !graph) { lvo_set_error(c, std::string("graph capture: ") + cudaGetErrorString(e)); return LVO_E_CUDA; }
+      e = cudaGraphInstantiate(&c->graph_exec[do_map][gen], graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) { lvo_set_error(c, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); return LVO_E_CUDA; }
+      c->graph_launches[do_map][gen] = c->launches;
+    }
+    LVO_CUDA_OK(c, cudaGraphLaunch(c->graph_exec[do_map][gen], c->st));
+    c->launches = c->graph_launches[do_map][gen];
+    if (do_map) c->map.gen = gen ^ 1;
+    c->have_knn_events = false;
+    cudaEventRecord(c->ev[3], c->st);
+    c->frame++;
+    LVO_TRY(sync_state(c));
+    c->tim.extract_ms = c->tim.odometry_ms = 0.f;     // per-stage times are only available with plain launches
+    cudaEventElapsedTime(&c->tim.mapping_ms, c->ev[0], c->ev[3]);
+    collect_knn_timing(c);
+  } else {
+    cudaEventRecord(c->ev[0], c->st);
+    enqueue_extract(c, stride, off_xyz, max_n);
+    cudaEventRecord(c->ev[1], c->st);
+    c->solve.trace = c->d_trace[0];
+    enqueue_odometry(c);
+    cudaEventRecord(c->ev[2], c->st);
+    if (do_map) { c->solve.trace = c->d_trace[1]; enqueue_mapping(c, 1, true, true); }
+    cudaEventRecord(c->ev[3], c->st);
+    c->frame++;
+    LVO_TRY(sync_state(c));
+    cudaEventElapsedTime(&c->tim.extract_ms, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&c->tim.odometry_ms, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&c->tim.mapping_ms, c->ev[2], c->ev[3]);
+    if (do_map) collect_knn_timing(c);
+  }
   int worst = LVO_OK;
   for (int l = 0; l < c->lanes; ++l) {
     const LaneState& s = c->h_ls[l];

@@ -187,3 +187,22 @@ def test_cube_window_shifts_match_oracle(lvo_mod, synth):
         assert (s.map_corner_total, s.map_surf_total) == (info[6], info[7])
     assert shifted >= 8   # the window really moved, in both directions on all three axes
     lvo.close()
+
+
+def test_graph_replay_matches_plain_launches(lvo_mod, synth):
+    """The CUDA-graph replay of the fused frame (default for few lanes) and plain launches give bit-identical poses, also with
+    mapping_skip_frame = 2 (two graph variants) and when the point layout changes (graphs are re-captured)."""
+    L = lvo_mod
+    for skip in (1, 2):
+        a = L.Lvo(lanes=1, skip_frame=skip, max_map_corner=1 << 18, max_map_surf=1 << 19)
+        b = L.Lvo(lanes=1, skip_frame=skip, max_map_corner=1 << 18, max_map_surf=1 << 19)
+        a.set_option(L.LVO_OPT_GRAPHS, 1)
+        b.set_option(L.LVO_OPT_GRAPHS, 0)
+        for k in range(7):
+            sw = synth.sweep(64, 1, k)[0]
+            arg = L.to_pcl_layout(sw) if k >= 5 else sw    # stride 32 from frame 5 on
+            _, oa, ma = a.step_batch([arg])
+            _, ob, mb = b.step_batch([arg])
+            assert np.array_equal(oa, ob) and np.array_equal(ma, mb), (skip, k)
+        assert a.timings().kernel_launches == b.timings().kernel_launches
+        a.close(); b.close()
