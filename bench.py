@@ -187,6 +187,50 @@ def extra_configs(L, device):
         valid += int(v.sum())
     dt = time.perf_counter() - t0
     ctx.close()
+    # ---- config 3: dense map stress
+    import torch
+    ctx = L.Lvo(device=device, max_points=131072, max_map_corner=1 << 18, max_map_surf=1 << 21)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    ax = torch.arange(-125.0, 125.0, 0.4, device="cuda")
+    gx, gy = torch.meshgrid(ax, ax, indexing="ij")
+    n_s = gx.numel()
+    surf = torch.stack([gx.reshape(-1), gy.reshape(-1), torch.full((n_s,), -1.73, device="cuda"), torch.zeros(n_s, device="cuda")], 1)
+    surf[:, :2] += (torch.rand(n_s, 2, device="cuda", generator=g) - 0.5) * 0.3
+    surf[:, 2] += torch.randn(n_s, device="cuda", generator=g) * 0.02
+    nl = 4000
+    lx = (torch.rand(nl, 2, device="cuda", generator=g) - 0.5) * 250.0
+    lz = torch.arange(-1.7, 8.3, 0.4, device="cuda")
+    corner = torch.cat([lx[:, None, :].expand(nl, len(lz), 2), lz[None, :, None].expand(nl, len(lz), 1), torch.zeros(nl, len(lz), 1, device="cuda")], 2).reshape(-1, 4).contiguous()
+    # (a) voxel-downsample kernels in isolation on a 1.6 M-point cloud (4 jittered copies of the surf map), leaf 0.8
+    big = torch.cat([surf + torch.tensor([0.05 * i, 0.03 * i, 0.0, 0.0], device="cuda") for i in range(4)]).contiguous()
+    dout = torch.empty_like(big)
+    times = []
+    for _ in range(4):
+        n_out, ms = ctx.voxel_downsample_dev(big.data_ptr(), len(big), 0.8, dout.data_ptr())
+        times.append(ms)
+    ms = float(np.median(times[1:]))
+    alg = 16.0 * (len(big) + n_out)
+    out["config3_voxel_downsample"] = {"points_in": int(len(big)), "points_out": int(n_out), "kernel_ms": ms, "algorithmic_bytes": alg,
+                                        "achieved_gbs": alg / 1e9 / (ms * 1e-3), "what": "lvo_voxel_downsample_dev (bbox + keys + 64-bit LSD radix sort + centroids), leaf 0.8 m"}
+
+    # (b) whole lvo_scan_to_map against an imported ~490 k-point map (laserMapping.cpp:741-750 cube indices, cen = 10,10,5)
+    def cubes(p):
+        c = torch.floor((p[:, :3].double() + 25.0) / 50.0).long() + torch.tensor([10, 10, 5], device="cuda")
+        return (c[:, 0] + 21 * c[:, 1] + 441 * c[:, 2]).int()
+    ctx.map_import(0, corner.cpu().numpy(), cubes(corner).cpu().numpy(), surf.cpu().numpy(), cubes(surf).cpu().numpy())
+    from oracle_py import Oracle
+    feats = Oracle().extract(synth.sweep(64, 0, 0)[0])
+    ident = np.array([0, 0, 0, 1, 0, 0, 0], float)
+    tms, knn_us = [], []
+    for _ in range(4):
+        st, pose, _ = ctx.scan_to_map(feats["less_sharp"], feats["less_flat"], feats["full"], ident)
+        tm = ctx.timings()
+        tms.append(tm.mapping_ms); knn_us.append(1e3 * tm.knn_ms / max(tm.knn_launches, 1))
+    stt = ctx.stats(0)
+    out["config3_scan_to_map_dense_map"] = {"map_points_in_neighbourhood": [stt.map_corner_from_map, stt.map_surf_from_map], "queries": [stt.map_corner_stack, stt.map_surf_stack],
+                                            "scan_to_map_ms": float(np.median(tms[1:])), "knn_launch_us": float(np.median(knn_us[1:])),
+                                            "what": "one lvo_scan_to_map call (1 lane, host API, incl. uploads and the per-cube re-filter of the whole neighbourhood)"}
+    ctx.close()
     out["config5_depth_association"] = {"sweeps_per_s": 10 / dt, "keypoints_per_s": 11200 / dt, "valid_fraction": valid / 11200.0,
                                         "what": "lvo_depth_associate, 120k-point sweep + 1120 keypoints per call, host API"}
     return out

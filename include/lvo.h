@@ -178,6 +178,9 @@ int lvo_probe_fetch(lvo_ctx* ctx, int lane, int what, void* out, size_t cap_byte
 /* Stand-alone operators (used by parity tests and by bench.py's per-kernel roofline; lane 0 scratch). */
 /* pcl::VoxelGrid::filter restated (scanRegistration.cpp:401-405, laserMapping.cpp:543-549,793-799). */
 int lvo_voxel_downsample(lvo_ctx* ctx, lvo_cloud_view in, float leaf, lvo_cloud_out* out);
+/* Device-resident form for kernel measurements: d_in / d_out are device pointers (packed points, d_out capacity >= n);
+ * *ms gets the CUDA-event time of the downsample kernels alone (no copies). */
+int lvo_voxel_downsample_dev(lvo_ctx* ctx, const lvo_point* d_in, size_t n, float leaf, lvo_point* d_out, size_t* n_out, float* ms);
 /* Exact K-NN (K<=5) of queries in cloud, squared-distance gate `max_sq`; ind/sq are [nq][K]; -1 when fewer
  * than K points lie inside the gate.  Replaces pcl::KdTreeFLANN::nearestKSearch + the d^2 gate
  * (laserMapping.cpp:582-584; laserOdometry.cpp:386-389). */

@@ -69,7 +69,7 @@ class Timings(C.Structure):
 EXPORTS = ["lvo_default_config", "lvo_create", "lvo_destroy", "lvo_last_error", "lvo_get_stats", "lvo_extract_features", "lvo_scan_to_scan",
            "lvo_scan_to_map", "lvo_step_batch", "lvo_step_batch_dev", "lvo_lane_status", "lvo_map_import", "lvo_map_export",
            "lvo_get_map_correction", "lvo_set_map_correction", "lvo_set_odometry_state", "lvo_probe_fetch", "lvo_voxel_downsample", "lvo_knn",
-           "lvo_knn5_throughput", "lvo_get_timings", "lvo_set_stream", "lvo_state_bytes", "lvo_depth_associate", "lvo_step_batch_pipelined", "lvo_set_option"]
+           "lvo_knn5_throughput", "lvo_get_timings", "lvo_set_stream", "lvo_state_bytes", "lvo_depth_associate", "lvo_step_batch_pipelined", "lvo_set_option", "lvo_voxel_downsample_dev"]
 
 
 def load_library():
@@ -98,6 +98,7 @@ def load_library():
     L.lvo_set_odometry_state.argtypes = [vp, ip, C.POINTER(Pose), C.POINTER(Pose)]
     L.lvo_probe_fetch.argtypes = [vp, ip, ip, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.lvo_voxel_downsample.argtypes = [vp, CloudView, C.c_float, C.POINTER(CloudOut)]
+    L.lvo_voxel_downsample_dev.argtypes = [vp, vp, C.c_size_t, C.c_float, vp, C.POINTER(C.c_size_t), C.POINTER(C.c_float)]
     L.lvo_knn.argtypes = [vp, CloudView, CloudView, ip, C.c_float, vp, vp]
     L.lvo_knn5_throughput.argtypes = [vp, vp, vp, vp, vp, ip, ip, vp, vp, C.POINTER(C.c_float)]
     L.lvo_get_timings.argtypes = [vp, C.POINTER(Timings)]
@@ -350,6 +351,12 @@ class Lvo:
         out, buf = self._out(max(v.n, 1))
         self._check(self.lib.lvo_voxel_downsample(self.h, v, leaf, C.byref(out)))
         return buf[:out.n].copy()
+
+    def voxel_downsample_dev(self, d_in_ptr, n, leaf, d_out_ptr):
+        """Device pointers in / out; returns (n_out, kernel milliseconds)."""
+        n_out, ms = C.c_size_t(0), C.c_float(0)
+        self._check(self.lib.lvo_voxel_downsample_dev(self.h, C.c_void_p(d_in_ptr), n, leaf, C.c_void_p(d_out_ptr), C.byref(n_out), C.byref(ms)))
+        return n_out.value, ms.value
 
     def knn(self, cloud, queries, K, max_sq):
         vc, k1 = view_of(cloud)

@@ -775,6 +775,28 @@ int lvo_voxel_downsample(lvo_ctx* c, lvo_cloud_view in, float leaf, lvo_cloud_ou
   return r;
 }
 
+int lvo_voxel_downsample_dev(lvo_ctx* c, const lvo_point* d_in, size_t n, float leaf, lvo_point* d_out, size_t* n_out, float* ms) {
+  if (!c || !d_in || !d_out || !n_out || !(leaf > 0.f)) return LVO_E_BADARG;
+  if (n > (size_t)c->map.vx.cap_items) { lvo_set_error(c, "input cloud exceeds the voxel engine capacity"); return LVO_E_CAPACITY; }
+  c->launches = 0;
+  VoxelEngine& vx = c->map.vx;
+  LVO_CUDA_OK(c, cudaMemcpyAsync(vx.in_pts, d_in, n * sizeof(lvo_point), cudaMemcpyDeviceToDevice, c->st));
+  k_vx_single_setup<<<std::max(1, std::min(lvo_div_up((long long)n, 256), 592)), 256, 0, c->st>>>(vx, (int)n, leaf);
+  cudaEventRecord(c->ev[6], c->st);
+  lvo_voxel_run(c->st, vx, (int)std::max<size_t>(n, 1), 1, 1, &c->launches);
+  cudaEventRecord(c->ev[7], c->st);
+  unsigned cnt = 0;
+  LVO_CUDA_OK(c, cudaMemcpyAsync(&cnt, vx.d_n_out, 4, cudaMemcpyDeviceToHost, c->st));
+  LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  LVO_CUDA_OK(c, cudaGetLastError());
+  if (n == 0) cnt = 0;
+  *n_out = cnt;
+  if (cnt) LVO_CUDA_OK(c, cudaMemcpyAsync(d_out, vx.out_pts, (size_t)cnt * sizeof(lvo_point), cudaMemcpyDeviceToDevice, c->st));
+  LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  if (ms) cudaEventElapsedTime(ms, c->ev[6], c->ev[7]);
+  return LVO_OK;
+}
+
 int lvo_knn(lvo_ctx* c, lvo_cloud_view cloud, lvo_cloud_view queries, int K, float max_sq, int* ind, float* sq) {
   if (!c || !ind || !sq || (K != 1 && K != 5)) return LVO_E_BADARG;
   LVO_TRY(check_view(c, cloud, (size_t)c->map.map_cap[1])); LVO_TRY(check_view(c, queries, (size_t)c->P));
