@@ -447,7 +447,7 @@ static inline void lvo_launch_mapping(cudaStream_t st, MapArgs a, const SolveArg
     if (launches) *launches += 1;
     SolveArgs sa = solve_proto;
     sa.which = 1; sa.outer = o; sa.factors = a.factors; sa.factor_cap = a.factor_cap;
-    lvo_launch_lm(st, sa, lanes);
+    lvo_launch_lm(st, sa, lanes, 16384);
     if (launches) *launches += 2;
   }
   k_map_finish<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a);

@@ -575,7 +575,7 @@ static inline void lvo_launch_odometry(cudaStream_t st, OdoArgs a, const SolveAr
     else k_odo_assoc<32><<<gs, 256, 0, st>>>(a);
     SolveArgs sa = solve_proto;
     sa.which = 0; sa.outer = o; sa.factors = a.factors; sa.factor_cap = a.factor_cap;
-    lvo_launch_lm(st, sa, lanes);
+    lvo_launch_lm(st, sa, lanes, nfeat_cap);
     if (launches) *launches += 2;
   }
   k_odo_integrate<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a, outer_iters);

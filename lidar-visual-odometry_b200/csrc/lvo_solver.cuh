@@ -436,9 +436,11 @@ __global__ void __launch_bounds__(LVO_LM_THREADS, 2) k_lm_solve(SolveArgs a) {
 
 // one cluster per lane; the cluster size is the largest of 8, 4, 2, 1 that keeps all lanes resident in one wave
 // (2 CTAs per SM x 148 SMs), so that few lanes get short latency and many lanes get full throughput
-static inline void lvo_launch_lm(cudaStream_t st, const SolveArgs& sa, int lanes) {
+static inline void lvo_launch_lm(cudaStream_t st, const SolveArgs& sa, int lanes, int max_slots) {
   int csize = LVO_LM_CLUSTER_MAX;
   while (csize > 1 && lanes * csize > 296) csize >>= 1;
+  // small problems (scan-to-scan: < 2.4 k slots) do not amortise the cluster barriers: at most 4 slots per thread is enough
+  while (csize > 1 && max_slots <= csize * LVO_LM_THREADS * 2) csize >>= 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(lanes * csize, 1, 1);
   cfg.blockDim = dim3(LVO_LM_THREADS, 1, 1);
