@@ -22,6 +22,7 @@
 #define LVO_EX_THREADS 256
 #define LVO_PICK_THREADS 128
 #define LVO_PICK_SMEM_KEYS 3072  // 6 x 512 padded sector keys, or one ring's voxel keys (24 KB)
+#define LVO_PICK_RING_SMEM 4096  // rings up to this many points keep their picked flags in shared memory
 
 struct ExtractArgs {
   // input
@@ -290,7 +291,13 @@ __device__ __forceinline__ void block_bitonic_sort_multi(unsigned long long* key
 }
 
 // Marks the neighbours of a picked point (:319-342 / :365-388).  Called by a full warp.
-__device__ __forceinline__ void mark_neighbours(volatile int* picked, const unsigned char* gapbig, int ind, unsigned ln) {
+// cloudNeighborPicked of one ring: shared memory while the picks run (written back afterwards), global for oversize rings
+struct PickedRef {
+  volatile unsigned char* sm; volatile int* gl; int r0; bool use_sm;
+  __device__ __forceinline__ int get(int i) const { return use_sm ? (int)sm[i - r0] : gl[i]; }
+  __device__ __forceinline__ void set(int i) const { if (use_sm) sm[i - r0] = 1; else gl[i] = 1; }
+};
+__device__ __forceinline__ void mark_neighbours(const PickedRef& picked, const unsigned char* gapbig, int ind, unsigned ln) {
   // lanes 0..4: l = 1..5 forward, gap between ind+l-1 and ind+l ; lanes 8..12: l = -1..-5, gap between ind+l and ind+l+1
   bool brk = false;
   int tgt = -1;
@@ -299,8 +306,8 @@ __device__ __forceinline__ void mark_neighbours(volatile int* picked, const unsi
   const unsigned b = __ballot_sync(0xffffffffu, brk);
   const unsigned bf = b & 0x1fu, bb = (b >> 8) & 0x1fu;
   const int stopf = bf ? (__ffs(bf) - 1) : 5, stopb = bb ? (__ffs(bb) - 1) : 5;
-  if (ln < 5 && (int)ln < stopf) picked[tgt] = 1;
-  if (ln >= 8 && ln < 13 && (int)(ln - 8) < stopb) picked[tgt] = 1;
+  if (ln < 5 && (int)ln < stopf) picked.set(tgt);
+  if (ln >= 8 && ln < 13 && (int)(ln - 8) < stopb) picked.set(tgt);
   __syncwarp();
 }
 
@@ -309,6 +316,7 @@ __global__ void __launch_bounds__(LVO_PICK_THREADS) k_sector_pick(ExtractArgs a)
   __shared__ float s_red[6][LVO_PICK_THREADS / 32];
   __shared__ int s_i[8];
   __shared__ unsigned s_scan[33];
+  __shared__ unsigned char s_picked[LVO_PICK_RING_SMEM];   // cloudNeighborPicked of this ring while the greedy picks run
   const int lane = blockIdx.y, ring = blockIdx.x;
   LaneState& s = a.ls[lane];
   const size_t lo = (size_t)lane * a.P;
@@ -324,6 +332,10 @@ __global__ void __launch_bounds__(LVO_PICK_THREADS) k_sector_pick(ExtractArgs a)
   if (threadIdx.x == 0) a.lf_cnt[lane * LVO_MAX_RINGS + ring] = 0;
   if (threadIdx.x < LVO_SECTORS * 3) a.slot_cnt[sbase * 3 + threadIdx.x] = 0;
   if (E - S < 6) return;  // :279-280
+  const int R0 = S - 5, RL = (E + 6) - R0 + 1;   // the ring occupies [S - 5, E + 6]
+  const bool sp_ok = RL <= LVO_PICK_RING_SMEM;
+  if (sp_ok) for (int t = threadIdx.x; t < RL; t += blockDim.x) s_picked[t] = 0;
+  const PickedRef pk{s_picked, picked, R0, sp_ok};
 
   // ---- :288 sort cloudSortInd[sp..ep] by (curvature, index) ascending.  When six padded sectors fit in shared memory
   // they are sorted together (one block barrier per network step instead of six).
@@ -360,7 +372,7 @@ __global__ void __launch_bounds__(LVO_PICK_THREADS) k_sector_pick(ExtractArgs a)
         keys[t] = k;
       }
       __syncthreads();
-      block_bitonic_sort(keys, npad);
+      if (npad <= LVO_PICK_SMEM_KEYS) block_bitonic_sort(skeys, npad); else block_bitonic_sort(keys, npad);
       for (int t = threadIdx.x; t < m; t += blockDim.x) sort_ind[sp + t] = (int)(unsigned)(keys[t] & 0xffffffffull);
       __syncthreads();
     }
@@ -374,7 +386,7 @@ __global__ void __launch_bounds__(LVO_PICK_THREADS) k_sector_pick(ExtractArgs a)
         const int ind = valid ? sort_ind[k] : 0;
         const float c = valid ? curv[ind] : 0.f;
         const bool big = valid && ((double)c > 0.1);
-        const bool ok = big && picked[ind] == 0;
+        const bool ok = big && pk.get(ind) == 0;
         const unsigned bo = __ballot_sync(0xffffffffu, ok);
         if (bo == 0) {
           if (__ballot_sync(0xffffffffu, valid && !big)) break;  // sorted: nothing further can exceed 0.1
@@ -393,9 +405,9 @@ __global__ void __launch_bounds__(LVO_PICK_THREADS) k_sector_pick(ExtractArgs a)
         } else {
           break;
         }
-        if (ln == 0) picked[sel] = 1;
+        if (ln == 0) pk.set(sel);
         __syncwarp();
-        mark_neighbours(picked, gapbig, sel, ln);
+        mark_neighbours(pk, gapbig, sel, ln);
         pos = pos - first - 1;
       }
       int nflat = 0;
@@ -406,7 +418,7 @@ __global__ void __launch_bounds__(LVO_PICK_THREADS) k_sector_pick(ExtractArgs a)
         const int ind = valid ? sort_ind[k] : 0;
         const float c = valid ? curv[ind] : 0.f;
         const bool small = valid && ((double)c < 0.1);
-        const bool ok = small && picked[ind] == 0;
+        const bool ok = small && pk.get(ind) == 0;
         const unsigned bo = __ballot_sync(0xffffffffu, ok);
         if (bo == 0) {
           if (__ballot_sync(0xffffffffu, valid && !small)) break;
@@ -418,9 +430,9 @@ __global__ void __launch_bounds__(LVO_PICK_THREADS) k_sector_pick(ExtractArgs a)
         if (ln == 0) { label[sel] = -1; a.slot_flat[sbase * 4 + j * 4 + nflat] = sel; }
         nflat++;
         if (nflat >= 4) break;  // :359-362 before the marking
-        if (ln == 0) picked[sel] = 1;
+        if (ln == 0) pk.set(sel);
         __syncwarp();
-        mark_neighbours(picked, gapbig, sel, ln);
+        mark_neighbours(pk, gapbig, sel, ln);
         pos = pos + first + 1;
       }
       if (ln == 0) { a.slot_cnt[(sbase + j) * 3 + 0] = nsharp; a.slot_cnt[(sbase + j) * 3 + 1] = nls; a.slot_cnt[(sbase + j) * 3 + 2] = nflat; }
@@ -429,6 +441,7 @@ __global__ void __launch_bounds__(LVO_PICK_THREADS) k_sector_pick(ExtractArgs a)
   }
   __threadfence_block();
   __syncthreads();
+  if (sp_ok) for (int t = threadIdx.x; t < RL; t += blockDim.x) if (s_picked[t]) picked[R0 + t] = 1;   // probe array (cloudNeighborPicked)
 
   // ---- :392-398 less-flat candidates k in [S, E-1] with label <= 0, in index order; then :401-407 VoxelGrid(0.2)
   // pass 1: bounding box of the candidates
@@ -494,7 +507,7 @@ __global__ void __launch_bounds__(LVO_PICK_THREADS) k_sector_pick(ExtractArgs a)
   }
   for (int t = ncand + threadIdx.x; t < npad; t += blockDim.x) keys[t] = ~0ull;
   __syncthreads();
-  block_bitonic_sort(keys, npad);
+  if (npad <= LVO_PICK_SMEM_KEYS) block_bitonic_sort(skeys, npad); else block_bitonic_sort(keys, npad);
   // pass 3: one centroid per run of equal voxel idx, accumulated in sorted order (float, as PCL's CentroidPoint)
   float4* out = a.lf_ring + lo + s.ring_start[ring];
   carry = 0;

@@ -6,9 +6,11 @@
 //   k_grid_bbox -> k_grid_setup (cell size, origin, dims, table offsets) -> k_grid_zero -> k_grid_count
 //   (rank = atomicAdd per cell) -> scan (cell start table) -> k_grid_fill (points + their original index, sorted by
 //   cell; x-fastest cell order so that the cells x-1..x+1 of a row are ONE contiguous range of points).
-// Search (device function, one warp per query): rings of cells of growing Chebyshev radius; a ring r can only
-// contain points with |d| > (r-1) * cell along some axis, so the search stops as soon as the K-th best squared
-// distance is < (r * cell)^2, and never goes beyond the ring that covers the gate radius.  Squared distances use
+// Search: rings of cells of growing Chebyshev radius; a ring r can only contain points with |d| > (r-1) * cell along
+// some axis, so the search stops as soon as the K-th best squared distance is < ((r-1) * cell)^2, and never goes beyond
+// the ring that covers the gate radius.  Three forms share this rule: one warp per query (warp_knn, stand-alone
+// operator and depth association), one thread per query (thread_knn, the map search: most queries, fewest instructions)
+// and TW-lane tiles (tile_* primitives, the scan-to-scan association).  Squared distances use
 // FLANN's L2_Simple accumulation ((dx*dx + dy*dy) + dz*dz) in float without FMA; candidates are ranked by
 // (distance, original index), which is the oracle's fixed tie-break, so the result does not depend on the order
 // of the points inside a cell (the atomics above are free to race).
@@ -347,27 +349,6 @@ __device__ __forceinline__ bool thread_knn(const GridView& g, float qx, float qy
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// flattened multi-range scan: lane j < NR holds one contiguous candidate range [b, e) (e.g. one x-row of cells); the
-// warp walks the concatenation of all ranges with every lane busy.  f(t, r) is called for candidate t of range r.
-// All range bounds are fetched before the first candidate is touched, so a query costs two dependent memory round
-// trips (bounds, candidates) instead of two per row.
-// ---------------------------------------------------------------------------------------------------------------
-template <int NR, class F>
-__device__ __forceinline__ void warp_scan_ranges(unsigned b, unsigned e, F&& f) {
-  const unsigned ln = threadIdx.x & 31;
-  const unsigned len = e > b ? e - b : 0u;
-  const unsigned incl = warp_incl_scan(len);
-  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-  for (unsigned k0 = 0; k0 < total; k0 += 32) {
-    const unsigned k = k0 + ln;
-    int r = 0;
-#pragma unroll
-    for (int j = 0; j < NR - 1; ++j) r += (k >= __shfl_sync(0xffffffffu, incl, j)) ? 1 : 0;
-    const unsigned rb = __shfl_sync(0xffffffffu, b, r), ri = __shfl_sync(0xffffffffu, incl, r), rl = __shfl_sync(0xffffffffu, len, r);
-    if (k < total) f(rb + (k - (ri - rl)), r);
-  }
-}
-// ---------------------------------------------------------------------------------------------------------------
 // Tiles: TW lanes per query.  Every primitive below is executed by all 32 lanes (full-mask shuffles with width TW); a
 // tile that has nothing to do passes empty ranges.  This shares all per-query overhead (bounds, prefix
 // sums, reductions, control flow) between four queries, which is what the latency-bound association kernels need.
@@ -436,58 +417,6 @@ __device__ __forceinline__ void row_bounds(const GridView& g, int cz, int cy, in
   const int rowbase = (cz * g.dim[1] + cy) * g.dim[0];
   b = __ldg(g.cell_start + rowbase + x0); e = __ldg(g.cell_start + rowbase + x1 + 1);
 }
-// Exact nearest neighbour with d^2 < max_sq on a two-level grid (fine cells, then coarse cells): the 27 fine cells
-// around the query settle it when the best squared distance is below cell_fine^2; otherwise the 27 coarse cells, then
-// the usual ring expansion on the coarse grid.  Worst case is bounded by the coarse grid's few rings.
-__device__ __forceinline__ bool warp_nn1_two_level(const GridView& gf, const GridView& gc, float qx, float qy, float qz, float max_sq, float& bd, int& bi) {
-  const unsigned ln = threadIdx.x & 31;
-  float d = FLT_MAX; int id = INT_MAX;
-  auto consider = [&](const GridView& g, unsigned t) {
-    const float4 p = __ldg(g.pts + t);
-    const int i = __float_as_int(p.w);
-    const float dd = sqdist3(p, qx, qy, qz);
-    if (dd < d || (dd == d && i < id)) { d = dd; id = i; }
-  };
-  auto reduce = [&]() {  // (d, id) lexicographic minimum over the warp with two REDUX instructions (d >= 0: bit order = value order)
-    const unsigned md = __reduce_min_sync(0xffffffffu, __float_as_uint(d));
-    const unsigned mi = __reduce_min_sync(0xffffffffu, __float_as_uint(d) == md ? (unsigned)id : 0xffffffffu);
-    d = __uint_as_float(md); id = (int)mi;
-  };
-  for (int level = 0; level < 2; ++level) {
-    const GridView& g = level ? gc : gf;
-    if (g.dim[0] <= 0) continue;
-    const int cx = cell_coord(qx, g.inv_cell) - g.org[0], cy = cell_coord(qy, g.inv_cell) - g.org[1], cz = cell_coord(qz, g.inv_cell_z) - g.org[2];
-    unsigned b = 0, e = 0;
-    if (ln < 9) row_bounds(g, cz + (int)ln / 3 - 1, cy + (int)ln % 3 - 1, cx - 1, cx + 1, b, e);
-    warp_scan_ranges<9>(b, e, [&](unsigned t, int) { consider(g, t); });
-    reduce();
-    if (d < g.cell * g.cell) break;  // nothing outside the 27 cells can beat or tie it
-    if (level == 1) {
-      int R = (int)ceilf(sqrtf(max_sq) * g.inv_cell);
-      for (int r = 2; r <= R; ++r) {
-        const float bound = (float)(r - 1) * g.cell;
-        if (d < bound * bound) break;
-        // shell r: (2r+1)^2 rows; boundary rows span x-r..x+r, inner rows contribute the two end cells
-        const int side = 2 * r + 1, nrows = side * side;
-        for (int base = 0; base < nrows; base += 16) {
-          const int row = base + (int)(ln & 15);
-          unsigned bb = 0, ee = 0;
-          if (row < nrows) {
-            const int dz = row / side - r, dy = row % side - r;
-            const bool edge = dz == -r || dz == r || dy == -r || dy == r;
-            if (edge) { if (ln < 16) row_bounds(g, cz + dz, cy + dy, cx - r, cx + r, bb, ee); }
-            else row_bounds(g, cz + dz, cy + dy, ln < 16 ? cx - r : cx + r, ln < 16 ? cx - r : cx + r, bb, ee);
-          }
-          warp_scan_ranges<32>(bb, ee, [&](unsigned t, int) { consider(g, t); });
-        }
-        reduce();
-      }
-    }
-  }
-  bd = d; bi = id;
-  return id != INT_MAX && (double)d < (double)max_sq;
-}
-
 // Stand-alone operator (lvo_knn): one warp per query, problem 0 of the grid set.
 template <int K>
 __global__ void k_knn_queries(GridSet gs, const float4* __restrict__ q, int nq, float max_sq, int* __restrict__ ind, float* __restrict__ sq) {
