@@ -278,7 +278,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--lanes", type=int, default=int(os.environ.get("LVO_BENCH_LANES", "128")), help="independent sequences per GPU")
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("LVO_BENCH_LANES", "0")),
+                    help="independent sequences per GPU (0 = 256 when the GPU has >= 150 GB, else 128)")
     ap.add_argument("--ref-threads", type=int, default=0)
     ap.add_argument("--cpu-sample-frames", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -306,6 +307,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sampler = ClockSampler(local_rank)
     sampler.start()   # early: nvidia-smi's start-up (NVML init takes a driver lock) must not fall into a timed region
+    if args.lanes <= 0:
+        args.lanes = 256 if torch.cuda.get_device_properties(local_rank).total_memory >= 150e9 else 128
     L = load_pkg()
     if args.only_knn:
         print(json.dumps({"knn_throughput": knn_throughput(L, args.knn_frames, 5, local_rank)}), flush=True)
@@ -453,7 +456,7 @@ def main():
                              "frac": achieved / peak if peak else None,
                              # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full`, 128 lanes, 5th step
                              # (profiles/r1_final_hot_kernels_l128_ncu.csv); null for other lane counts
-                             "traffic": 41.0e6 if lanes == 128 else None, "peak_source": peak_src, "launches": knn_launches,
+                             "traffic": 41.0e6 if lanes == 128 else None,  # the capture was taken at 128 lanes "peak_source": peak_src, "launches": knn_launches,
                              "avg_launch_us": 1e3 * knn_ms / max(knn_launches, 1), "algorithmic_bytes_per_launch": knn_bytes / max(knn_launches, 1)},
                 "knn_throughput": knn_tp, "other_configs": extras, "cpu_baseline": cpu, "clocks": clocks,
                 "host": {"wall_ms_per_step_dev": 1e3 * wall_d / args.steps, "wall_ms_per_step_e2e": 1e3 * wall_e / args.steps, "gen_s": t_gen, "cores": host_threads}}
