@@ -72,6 +72,13 @@ typedef struct lvo_config {
   int max_points;        /* capacity per sweep (reference: 400000, scanRegistration.cpp:66); 0 = 262144    */
   int max_map_corner;    /* capacity of the whole corner map per lane, points; 0 = 1<<20                   */
   int max_map_surf;      /* capacity of the whole surf map per lane, points;   0 = 1<<21                   */
+  int distortion;        /* the compile-time switch `#define DISTORTION` of laserOdometry.cpp:67 made a run-time option:
+                          * 0 = DISTORTION 0 (the shipped value): s = 1 everywhere;
+                          * 1 = DISTORTION 1 as the file is written: s = (intensity - int(intensity)) / SCAN_PERIOD per point in
+                          *     TransformToStart (:157-163) and in LidarEdgeFactor / LidarPlaneFactor (:455-459, :549-553;
+                          *     lidarFactor.hpp:27-30, 79-82); the TransformToEnd block (:610-625) stays off (`if (0)`);
+                          * 2 = 1 plus that block: less-sharp, less-flat and full clouds are moved to the sweep end (:176-191)
+                          *     before they become the "last" clouds and the mapping input.                                   */
 } lvo_config;
 
 /* Per-call counters, also the parity probes (SURVEY §5 "Metrics / logging").  One record per lane. */
@@ -144,6 +151,10 @@ int lvo_map_import(lvo_ctx* ctx, int lane, const lvo_point* corner, const int* c
                    const lvo_point* surf, const int* surf_cube, size_t n_surf);
 /* which: 0 = corner, 1 = surf.  Points are returned cube-major in array-index order; cube_out may be NULL. */
 int lvo_map_export(lvo_ctx* ctx, int lane, int which, lvo_cloud_out* pts, int* cube_out);
+/* Map outputs of laserMapping.cpp:806-836.  which: 0 = "surround" cloud (:806-815: the cubes of the last frame's valid list in
+ * i,j,k loop order, corner points then surf points of each cube), 1 = whole map (:823-836: all 4851 cubes in array order, corner
+ * then surf).  The reference publishes them every 5th / 20th mapping frame; the schedule is the caller's (host/lvo_handlers.hpp). */
+int lvo_map_cloud(lvo_ctx* ctx, int lane, int which, lvo_cloud_out* pts);
 /* (q_wmap_wodom, t_wmap_wodom), laserMapping.cpp:116-117 */
 int lvo_get_map_correction(lvo_ctx* ctx, int lane, lvo_pose* T_wmap_wodom);
 int lvo_set_map_correction(lvo_ctx* ctx, int lane, const lvo_pose* T_wmap_wodom);
@@ -176,6 +187,11 @@ enum lvo_probe {
 int lvo_probe_fetch(lvo_ctx* ctx, int lane, int what, void* out, size_t cap_bytes, size_t* n_bytes);
 
 /* Stand-alone operators (used by parity tests and by bench.py's per-kernel roofline; lane 0 scratch). */
+/* TransformToStart (to_end = 0, laserOdometry.cpp:154-172) / TransformToEnd (to_end = 1, :176-191) of a cloud under T_last_curr
+ * (NULL = lane 0's current para_q / para_t) with the context's distortion mode (to_end always interpolates, as :176-191 does
+ * whenever its block is enabled).  In distortion mode 2 a host that drives the three entry points separately uses it to obtain
+ * the full-resolution cloud that :610-625 would publish. */
+int lvo_transform_cloud(lvo_ctx* ctx, lvo_cloud_view in, const lvo_pose* T_last_curr_or_null, int to_end, lvo_cloud_out* out);
 /* pcl::VoxelGrid::filter restated (scanRegistration.cpp:401-405, laserMapping.cpp:543-549,793-799). */
 int lvo_voxel_downsample(lvo_ctx* ctx, lvo_cloud_view in, float leaf, lvo_cloud_out* out);
 /* Device-resident form for kernel measurements: d_in / d_out are device pointers (packed points, d_out capacity >= n);

@@ -39,7 +39,7 @@ class Pose(C.Structure):
 class Config(C.Structure):
     _fields_ = [("n_scans", C.c_int), ("minimum_range", C.c_double), ("line_res", C.c_double), ("plane_res", C.c_double),
                 ("skip_frame", C.c_int), ("outer_iters", C.c_int), ("lm_max_iters", C.c_int), ("huber", C.c_double), ("device", C.c_int),
-                ("lanes", C.c_int), ("max_points", C.c_int), ("max_map_corner", C.c_int), ("max_map_surf", C.c_int)]
+                ("lanes", C.c_int), ("max_points", C.c_int), ("max_map_corner", C.c_int), ("max_map_surf", C.c_int), ("distortion", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -69,7 +69,8 @@ class Timings(C.Structure):
 EXPORTS = ["lvo_default_config", "lvo_create", "lvo_destroy", "lvo_last_error", "lvo_get_stats", "lvo_extract_features", "lvo_scan_to_scan",
            "lvo_scan_to_map", "lvo_step_batch", "lvo_step_batch_dev", "lvo_lane_status", "lvo_map_import", "lvo_map_export",
            "lvo_get_map_correction", "lvo_set_map_correction", "lvo_set_odometry_state", "lvo_probe_fetch", "lvo_voxel_downsample", "lvo_knn",
-           "lvo_knn5_throughput", "lvo_get_timings", "lvo_set_stream", "lvo_state_bytes", "lvo_depth_associate", "lvo_step_batch_pipelined", "lvo_set_option", "lvo_voxel_downsample_dev"]
+           "lvo_knn5_throughput", "lvo_get_timings", "lvo_set_stream", "lvo_state_bytes", "lvo_depth_associate", "lvo_step_batch_pipelined", "lvo_set_option", "lvo_voxel_downsample_dev",
+           "lvo_map_cloud", "lvo_transform_cloud"]
 
 
 def load_library():
@@ -93,6 +94,8 @@ def load_library():
     L.lvo_lane_status.argtypes = [vp, ip]
     L.lvo_map_import.argtypes = [vp, ip, vp, vp, C.c_size_t, vp, vp, C.c_size_t]
     L.lvo_map_export.argtypes = [vp, ip, ip, C.POINTER(CloudOut), vp]
+    L.lvo_map_cloud.argtypes = [vp, ip, ip, C.POINTER(CloudOut)]
+    L.lvo_transform_cloud.argtypes = [vp, CloudView, C.POINTER(Pose), ip, C.POINTER(CloudOut)]
     L.lvo_get_map_correction.argtypes = [vp, ip, C.POINTER(Pose)]
     L.lvo_set_map_correction.argtypes = [vp, ip, C.POINTER(Pose)]
     L.lvo_set_odometry_state.argtypes = [vp, ip, C.POINTER(Pose), C.POINTER(Pose)]
@@ -151,13 +154,14 @@ class Lvo:
     """One lvo_ctx."""
 
     def __init__(self, n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, skip_frame=1, outer_iters=10, lm_max_iters=4, huber=0.1,
-                 device=0, lanes=1, max_points=0, max_map_corner=0, max_map_surf=0):
+                 device=0, lanes=1, max_points=0, max_map_corner=0, max_map_surf=0, distortion=0):
         self.lib = load_library()
         cfg = Config()
         self.lib.lvo_default_config(C.byref(cfg))
         cfg.n_scans, cfg.minimum_range, cfg.line_res, cfg.plane_res = n_scans, minimum_range, line_res, plane_res
         cfg.skip_frame, cfg.outer_iters, cfg.lm_max_iters, cfg.huber, cfg.device, cfg.lanes = skip_frame, outer_iters, lm_max_iters, huber, device, lanes
         cfg.max_points, cfg.max_map_corner, cfg.max_map_surf = max_points, max_map_corner, max_map_surf
+        cfg.distortion = distortion
         self.cfg = cfg
         self.h = C.c_void_p()
         r = self.lib.lvo_create(C.byref(cfg), C.byref(self.h))
@@ -258,6 +262,21 @@ class Lvo:
         cube = np.empty(cap, np.int32)
         self._check(self.lib.lvo_map_export(self.h, lane, which, C.byref(out), cube.ctypes.data))
         return buf[:out.n].copy(), cube[:out.n].copy()
+
+    def map_cloud(self, lane, which):
+        """which 0: surround cloud (laserMapping.cpp:806-815), 1: whole map (:823-836)."""
+        cap = (self.cfg.max_map_corner or (1 << 20)) + (self.cfg.max_map_surf or (1 << 21))
+        out, buf = self._out(cap)
+        self._check(self.lib.lvo_map_cloud(self.h, lane, which, C.byref(out)))
+        return buf[:out.n].copy()
+
+    def transform_cloud(self, pts, T_last_curr=None, to_end=False):
+        """TransformToStart / TransformToEnd (laserOdometry.cpp:154-191) with the context's distortion mode."""
+        v, keep = view_of(pts)
+        out, buf = self._out(max(v.n, 1))
+        p = np_to_pose(T_last_curr) if T_last_curr is not None else None
+        self._check(self.lib.lvo_transform_cloud(self.h, v, C.byref(p) if p else None, int(to_end), C.byref(out)))
+        return buf[:out.n].copy()
 
     def set_map_correction(self, lane, qt7):
         p = np_to_pose(qt7)

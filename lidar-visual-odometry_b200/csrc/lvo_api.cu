@@ -154,6 +154,48 @@ __global__ void k_vx_single_setup(VoxelEngine e, int n, float leaf) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { e.in_seg[i] = 0; e.in_aux[i] = 0; }
 }
 
+// lvo_transform_cloud: TransformToStart / TransformToEnd of a packed cloud under (q, t) = pose or the lane's para_q / para_t
+struct PoseArg { double q[4], t[3]; int use; };
+__global__ void k_transform_cloud(const LaneState* ls, PoseArg pa, const float4* in, int n, int distortion, int to_end, float4* out) {
+  const double* q = pa.use ? pa.q : ls[0].para_q;
+  const double* t = pa.use ? pa.t : ls[0].para_t;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = to_end ? transform_to_end(q, t, in[i]) : transform_to_start(q, t, in[i], distortion);
+}
+// lvo_map_cloud: slot k = rank in the valid list (surround) or cube index (whole map); off[k] = exclusive prefix of the
+// corner + surf counts of the slots before it
+__global__ void __launch_bounds__(256) k_mapcloud_offsets(MapArgs a, int lane, int surround, unsigned* off) {
+  __shared__ unsigned sm[33];
+  const LaneState& s = a.ls[lane];
+  const int n = surround ? s.n_valid : LVO_NCUBES;
+  const unsigned* cs0 = a.cube_start[a.gen][0] + (size_t)lane * (LVO_NCUBES + 1);
+  const unsigned* cs1 = a.cube_start[a.gen][1] + (size_t)lane * (LVO_NCUBES + 1);
+  unsigned carry = 0;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int k = base + threadIdx.x;
+    unsigned cnt = 0;
+    if (k < n) { const int c = surround ? s.valid_cube[k] : k; cnt = (cs0[c + 1] - cs0[c]) + (cs1[c + 1] - cs1[c]); }
+    unsigned tot;
+    const unsigned ex = block_excl_scan(cnt, sm, &tot);
+    if (k < n) off[k] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) off[LVO_NCUBES] = carry;
+}
+__global__ void k_mapcloud_copy(MapArgs a, int lane, int surround, const unsigned* off, float4* out) {
+  const LaneState& s = a.ls[lane];
+  const int n = surround ? s.n_valid : LVO_NCUBES;
+  const unsigned* cs0 = a.cube_start[a.gen][0] + (size_t)lane * (LVO_NCUBES + 1);
+  const unsigned* cs1 = a.cube_start[a.gen][1] + (size_t)lane * (LVO_NCUBES + 1);
+  const float4* M0 = a.map_pts[a.gen][0] + (size_t)lane * a.map_cap[0];
+  const float4* M1 = a.map_pts[a.gen][1] + (size_t)lane * a.map_cap[1];
+  for (int k = blockIdx.x; k < n; k += gridDim.x) {
+    const int c = surround ? s.valid_cube[k] : k;
+    const unsigned b0 = cs0[c], n0 = cs0[c + 1] - b0, b1 = cs1[c], n1 = cs1[c + 1] - b1, o = off[k];
+    for (unsigned i = threadIdx.x; i < n0 + n1; i += blockDim.x) out[o + i] = i < n0 ? M0[b0 + i] : M1[b1 + (i - n0)];
+  }
+}
+
 int check_view(lvo_ctx* c, const lvo_cloud_view& v, size_t cap) {
   if (v.n == 0) return LVO_OK;
   if (!v.data || v.stride < 16 || v.stride > 64 || (v.stride & 3) || (v.off_xyz & 3) || (v.off_intensity & 3) || v.off_xyz + 12 > v.stride ||
@@ -237,12 +279,14 @@ void lvo_default_config(lvo_config* cfg) {
   cfg->n_scans = 64; cfg->minimum_range = 5.0; cfg->line_res = 0.4; cfg->plane_res = 0.8;  // launch/aloam_velodyne_HDL_64.launch:3-13
   cfg->skip_frame = 1; cfg->outer_iters = 10; cfg->lm_max_iters = 4; cfg->huber = 0.1; cfg->device = 0; cfg->lanes = 1;
   cfg->max_points = 0; cfg->max_map_corner = 0; cfg->max_map_surf = 0;
+  cfg->distortion = 0;  // laserOdometry.cpp:67
 }
 
 int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
   if (!cfg || !out) return LVO_E_BADARG;
   *out = nullptr;
   if (cfg->n_scans != 16 && cfg->n_scans != 32 && cfg->n_scans != 64) return LVO_E_BADARG;  // "wrong scan number", scanRegistration.cpp:203
+  if (cfg->distortion < 0 || cfg->distortion > 2) return LVO_E_BADARG;
   if (cfg->lanes < 1 || cfg->outer_iters < 1 || cfg->outer_iters > LVO_MAX_OUTER || cfg->lm_max_iters < 0 || cfg->lm_max_iters > LVO_MAX_LM) return LVO_E_BADARG;
   lvo_ctx* c = new (std::nothrow) lvo_ctx();
   if (!c) return LVO_E_CUDA;
@@ -308,7 +352,7 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
   // ---- odometry
   OdoArgs& od = c->odo;
   memset(&od, 0, sizeof(od));
-  od.ls = c->d_ls; od.lanes = L;
+  od.ls = c->d_ls; od.lanes = L; od.distortion = cfg->distortion; od.full = ex.full;
   od.sharp = ex.sharp; od.less_sharp = ex.less_sharp; od.flat = ex.flat; od.less_flat = ex.less_flat;
   od.cap_sharp = c->cap_sharp; od.cap_lsharp = c->cap_lsharp; od.cap_flat = c->cap_flat; od.P = P;
   LVO_TRY(dalloc(c, &od.corner_last, (size_t)L * c->cap_lsharp)); LVO_TRY(dalloc(c, &od.surf_last, (size_t)L * P));
@@ -673,6 +717,42 @@ int lvo_map_export(lvo_ctx* c, int lane, int which, lvo_cloud_out* pts, int* cub
   if (n) LVO_CUDA_OK(c, cudaMemcpy(pts->data, c->map.map_pts[c->map.gen][which] + (size_t)lane * c->map.map_cap[which], n * sizeof(lvo_point), cudaMemcpyDeviceToHost));
   if (cube_out) for (int k = 0; k < LVO_NCUBES; ++k) for (unsigned i = start[k]; i < start[k + 1]; ++i) cube_out[i] = k;
   return LVO_OK;
+}
+
+int lvo_map_cloud(lvo_ctx* c, int lane, int which, lvo_cloud_out* pts) {
+  if (!c || lane < 0 || lane >= c->lanes || which < 0 || which > 1 || !pts) return LVO_E_BADARG;
+  unsigned* off = c->map.new_cnt;              // [LVO_NCUBES + 1] scratch (rewritten by every mapping frame)
+  float4* out = (float4*)c->d_upload;          // >= 4 * max(map_cap) points
+  k_mapcloud_offsets<<<1, 256, 0, c->st>>>(c->map, lane, which == 0, off);
+  k_mapcloud_copy<<<which == 0 ? LVO_MAX_VALID : 296, 256, 0, c->st>>>(c->map, lane, which == 0, off, out);
+  unsigned n = 0;
+  LVO_CUDA_OK(c, cudaMemcpyAsync(&n, off + LVO_NCUBES, 4, cudaMemcpyDeviceToHost, c->st));
+  LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  LVO_CUDA_OK(c, cudaGetLastError());
+  const int r = download_cloud(c, out, n, pts);
+  LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  return r;
+}
+
+int lvo_transform_cloud(lvo_ctx* c, lvo_cloud_view in, const lvo_pose* T, int to_end, lvo_cloud_out* out) {
+  if (!c || !out) return LVO_E_BADARG;
+  const size_t cap = (size_t)std::max(c->P, std::max(c->map.map_cap[0], c->map.map_cap[1]));
+  LVO_TRY(check_view(c, in, cap));
+  if (in.n * in.stride > cap * 32) { lvo_set_error(c, "input cloud exceeds the staging buffer"); return LVO_E_CAPACITY; }
+  float4* d_in = (float4*)c->d_upload + 2 * cap;   // d_upload holds 4 * cap points; the first half stages strided uploads
+  float4* d_out = d_in + cap;
+  if (in.n) {
+    LVO_CUDA_OK(c, cudaMemcpyAsync(c->d_upload, in.data, in.n * in.stride, cudaMemcpyHostToDevice, c->st));
+    k_unpack<<<std::max(1, std::min(lvo_div_up((long long)in.n, 256), 592)), 256, 0, c->st>>>((const unsigned char*)c->d_upload, (int)in.n, (int)in.stride,
+                                                                                                 (int)in.off_xyz, (int)in.off_intensity, d_in);
+    PoseArg pa; memset(&pa, 0, sizeof(pa));
+    if (T) { pa.use = 1; for (int k = 0; k < 4; ++k) pa.q[k] = T->q[k]; for (int k = 0; k < 3; ++k) pa.t[k] = T->t[k]; }
+    k_transform_cloud<<<std::max(1, std::min(lvo_div_up((long long)in.n, 256), 592)), 256, 0, c->st>>>(c->d_ls, pa, d_in, (int)in.n, c->cfg.distortion, to_end, d_out);
+  }
+  const int r = download_cloud(c, d_out, in.n, out);
+  LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  LVO_CUDA_OK(c, cudaGetLastError());
+  return r;
 }
 
 static int set_pose(lvo_ctx* c, int lane, int what, const lvo_pose* p) {

@@ -28,8 +28,8 @@
 #define LVO_VSEGS (LVO_MAX_VALID + 1)                        // + one pseudo segment for inserts into non-valid cubes
 
 // One residual block, the parameters of the reference functors (lidarFactor.hpp):
-//   type 0 LidarEdgeFactor      : c = curr_point, a = last_point_a, b = last_point_b
-//   type 1 LidarPlaneFactor     : c = curr_point, a = last_point_j, b = ljm_norm (unit normal, built at construction)
+//   type 0 LidarEdgeFactor      : c = curr_point, a = last_point_a, b = last_point_b, d = s (interpolation ratio; 1 unless DISTORTION)
+//   type 1 LidarPlaneFactor     : c = curr_point, a = last_point_j, b = ljm_norm (unit normal, built at construction), d = s
 //   type 2 LidarPlaneNormFactor : c = curr_point, a = plane_unit_norm, d = negative_OA_dot_norm
 //   type -1 : no factor for this feature
 struct __align__(16) LvoFactor {
@@ -118,6 +118,52 @@ __device__ __forceinline__ void quat_mul(const double* a, const double* b, doubl
 __device__ __forceinline__ float4 transform_point(const double* q, const double* t, float4 p) {
   d3 r = quat_rotate(q, d3{(double)p.x, (double)p.y, (double)p.z});
   return make_float4((float)(r.x + t[0]), (float)(r.y + t[1]), (float)(r.z + t[2]), p.w);
+}
+// Eigen 3.3.7 QuaternionBase::slerp (Quaternion.h:716-746) of Identity towards q at parameter s: the blend weights of
+// q_s = scale0 * Identity + scale1 * q, and their derivatives with respect to q.w (d = Identity.dot(q) = q.w), as forward-mode
+// autodiff of the reference functors propagates them (lidarFactor.hpp:27-30,79-82).
+struct SlerpW { double scale0, scale1, ds0_dw, ds1_dw; };
+__device__ __forceinline__ SlerpW slerp_identity_weights(double w, double s, bool want_derivs) {
+  SlerpW o{0.0, 0.0, 0.0, 0.0};
+  const double one = 1.0 - 2.220446049250313e-16;
+  const double absD = fabs(w);
+  if (absD >= one) { o.scale0 = 1.0 - s; o.scale1 = s; }
+  else {
+    const double theta = acos(absD), sinTheta = sin(theta);
+    const double a0 = (1.0 - s) * theta, a1 = s * theta;
+    const double s0 = sin(a0), s1 = sin(a1);
+    o.scale0 = s0 / sinTheta;
+    o.scale1 = s1 / sinTheta;
+    if (want_derivs) {
+      const double cosTheta = cos(theta);
+      const double dtheta_dw = (w < 0 ? 1.0 : -1.0) / sqrt(1.0 - absD * absD);
+      o.ds0_dw = ((1.0 - s) * cos(a0) * sinTheta - s0 * cosTheta) / (sinTheta * sinTheta) * dtheta_dw;
+      o.ds1_dw = (s * cos(a1) * sinTheta - s1 * cosTheta) / (sinTheta * sinTheta) * dtheta_dw;
+    }
+  }
+  if (w < 0) { o.scale1 = -o.scale1; o.ds1_dw = -o.ds1_dw; }
+  return o;
+}
+// interpolation ratio of a point, laserOdometry.cpp:157-161 / :455-459: float subtraction, double division by SCAN_PERIOD
+__device__ __forceinline__ double distortion_ratio(float intensity, int distortion) {
+  return distortion ? (double)(intensity - (float)int(intensity)) / 0.1 : 1.0;
+}
+// TransformToStart, laserOdometry.cpp:154-172.  distortion == 0: s = 1 and Identity.slerp(1, q) is exactly q.
+__device__ __forceinline__ float4 transform_to_start(const double* q, const double* t, float4 p, int distortion) {
+  if (!distortion) return transform_point(q, t, p);
+  const double s = distortion_ratio(p.w, distortion);
+  const SlerpW k = slerp_identity_weights(q[3], s, false);
+  const double qs[4] = {k.scale0 * 0.0 + k.scale1 * q[0], k.scale0 * 0.0 + k.scale1 * q[1], k.scale0 * 0.0 + k.scale1 * q[2], k.scale0 * 1.0 + k.scale1 * q[3]};
+  const d3 r = quat_rotate(qs, d3{(double)p.x, (double)p.y, (double)p.z});
+  return make_float4((float)(r.x + s * t[0]), (float)(r.y + s * t[1]), (float)(r.z + s * t[2]), p.w);
+}
+// TransformToEnd, laserOdometry.cpp:176-191 (its call site :610-625 is disabled by `if (0)` in the reference; distortion mode 2 enables it)
+__device__ __forceinline__ float4 transform_to_end(const double* q, const double* t, float4 p) {
+  const float4 u = transform_to_start(q, t, p, 1);
+  const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];   // Eigen inverse(): conjugate / squaredNorm
+  const double qi[4] = {-q[0] / n2, -q[1] / n2, -q[2] / n2, q[3] / n2};
+  const d3 e = quat_rotate(qi, d3{(double)u.x - t[0], (double)u.y - t[1], (double)u.z - t[2]});
+  return make_float4((float)e.x, (float)e.y, (float)e.z, (float)int(p.w));
 }
 // FLANN L2_Simple accumulation order, no FMA (TU compiled with -fmad=false)
 __device__ __forceinline__ float sqdist3(float4 a, float qx, float qy, float qz) {

@@ -184,7 +184,7 @@ __device__ __forceinline__ void fit_factor(int t, const float4 ori, const float4
     sym_eigen3_dev(cov, w, V);
     if (w[2] > 3 * w[1]) {  // :611
       const double ux = V[0 * 3 + 2], uy = V[1 * 3 + 2], uz = V[2 * 3 + 2];
-      fac.type = 0;
+      fac.type = 0; fac.d = 1.0;
       fac.c[0] = ori.x; fac.c[1] = ori.y; fac.c[2] = ori.z;
       fac.a[0] = 0.1 * ux + center.x; fac.a[1] = 0.1 * uy + center.y; fac.a[2] = 0.1 * uz + center.z;
       fac.b[0] = -0.1 * ux + center.x; fac.b[1] = -0.1 * uy + center.y; fac.b[2] = -0.1 * uz + center.z;
@@ -446,7 +446,7 @@ static inline void lvo_launch_mapping(cudaStream_t st, MapArgs a, const SolveArg
     k_map_fit<<<ga, 128, 0, st>>>(a);
     if (launches) *launches += 1;
     SolveArgs sa = solve_proto;
-    sa.which = 1; sa.outer = o; sa.factors = a.factors; sa.factor_cap = a.factor_cap;
+    sa.which = 1; sa.outer = o; sa.factors = a.factors; sa.factor_cap = a.factor_cap; sa.distort = 0;  // LidarEdgeFactor(..., 1.0), :610
     lvo_launch_lm(st, sa, lanes, 16384);
     if (launches) *launches += 2;
   }

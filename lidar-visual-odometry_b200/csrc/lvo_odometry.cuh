@@ -1,5 +1,7 @@
-// lvo_odometry.cuh — lvo_scan_to_scan: the odometry frame body, reference src/laserOdometry.cpp:353-641
-// (DISTORTION 0, :67).
+// lvo_odometry.cuh — lvo_scan_to_scan: the odometry frame body, reference src/laserOdometry.cpp:353-641.
+// OdoArgs::distortion selects the compile-time switch of :67: 0 = DISTORTION 0 (the shipped value), 1 = DISTORTION 1 as the
+// file is written (per-point interpolation ratio in TransformToStart :157-163 and in the factors :455-459 / :549-553; the
+// TransformToEnd block :610-625 stays disabled by its `if (0)`), 2 = DISTORTION 1 with that block enabled (k_odo_to_end).
 //
 //   k_odo_begin      first-frame handling (:355-358), per-outer-iteration counter reset
 //   k_odo_assoc      one 8-lane tile per feature (4 features per warp): TransformToStart (:154-172, s = 1), 1-NN in the previous sweep's
@@ -19,8 +21,10 @@
 struct OdoArgs {
   LaneState* ls;
   int lanes, outer;
+  int distortion;    // 0 | 1 | 2, see the header comment
   // current features (stride caps)
-  const float4* sharp; const float4* less_sharp; const float4* flat; const float4* less_flat;
+  const float4* sharp; float4* less_sharp; const float4* flat; float4* less_flat;
+  float4* full;      // [lanes][P] ring-ordered full-resolution cloud (only touched by k_odo_to_end)
   int cap_sharp, cap_lsharp, cap_flat, P;
   // previous sweep
   float4* corner_last; float4* surf_last;  // [lanes][cap_lsharp], [lanes][P]
@@ -161,7 +165,8 @@ __device__ __forceinline__ void tile_shell_nn1(const GridView& g, bool active, f
 __device__ __forceinline__ int odo_emit(const OdoArgs& a, int lane, int f, int ns, bool corner, bool ok, float4 pt, const float4* C, int closest, float4 pj,
                                         int same, int other) {
   LvoFactor fac;
-  fac.type = -1; fac.pad = 0; fac.d = 0;
+  fac.type = -1; fac.pad = 0;
+  fac.d = distortion_ratio(pt.w, a.distortion);   // s of LidarEdgeFactor / LidarPlaneFactor, :455-459 / :549-553
   int i1 = -1, i2 = -1, i3 = -1;
   if (ok) {
     if (corner) {
@@ -232,7 +237,7 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
     const GridView& g = gv[corner ? 0 : 1];
     const GridView& gaz = gv[corner ? 2 : 3];
     const float4 pt = corner ? a.sharp[(size_t)lane * a.cap_sharp + f] : a.flat[(size_t)lane * a.cap_flat + (f - ns)];
-    const float4 sel = transform_point(s.para_q, s.para_t, pt);
+    const float4 sel = transform_to_start(s.para_q, s.para_t, pt, a.distortion);
     int pc = -1, pA = -1, pB = -1;
     if (a.outer > 0) {
       if (corner) { const int* c = a.corner_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer - 1) * a.cap_sharp + f) * 2; pc = c[0]; pB = c[1]; }
@@ -397,7 +402,7 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
   float4 pt = make_float4(0.f, 0.f, 0.f, 0.f), sel = pt;
   if (have) {
     pt = corner ? a.sharp[(size_t)lane * a.cap_sharp + f] : a.flat[(size_t)lane * a.cap_flat + (f - ns)];
-    sel = transform_point(q, t, pt);  // TransformToStart
+    sel = transform_to_start(q, t, pt, a.distortion);  // TransformToStart
   }
   // ---- closest point (laserOdometry.cpp:386 / :470, gate :389 / :473): the 27 cells around the query on the fine grid
   // (0.5 m) settle it when the best squared distance is below cell^2; otherwise the middle grid (2 m), then the coarse
@@ -538,6 +543,18 @@ __global__ void k_odo_integrate(OdoArgs a, int outer_iters) {
   s.n_surf_last = s.n_less_flat;
   for (int r = 0; r < LVO_MAX_RINGS + 2; ++r) { s.corner_ring_first[r] = s.n_less_sharp; s.surf_ring_first[r] = s.n_less_flat; }
 }
+// distortion mode 2: the block :610-625 with its `if (0)` lifted — TransformToEnd (:176-191) of the less-sharp, less-flat and
+// full-resolution clouds in place, on every frame (the first included: para = identity only strips the fractional intensity)
+__global__ void k_odo_to_end(OdoArgs a) {
+  const int lane = blockIdx.y;
+  const LaneState& s = a.ls[lane];
+  const int n0 = s.n_less_sharp, n1 = s.n_less_flat, n2 = s.n_kept;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1 + n2; i += gridDim.x * blockDim.x) {
+    float4* p = i < n0 ? a.less_sharp + (size_t)lane * a.cap_lsharp + i
+                       : (i < n0 + n1 ? a.less_flat + (size_t)lane * a.P + (i - n0) : a.full + (size_t)lane * a.P + (i - n0 - n1));
+    *p = transform_to_end(s.para_q, s.para_t, *p);
+  }
+}
 // copy less-sharp / less-flat into the "last" buffers (the pointer swap of :627-636) and build the ring-offset tables:
 // ring_first[r] = first index whose ring id int(intensity) is >= r
 __global__ void k_odo_swap(OdoArgs a) {
@@ -574,11 +591,12 @@ static inline void lvo_launch_odometry(cudaStream_t st, OdoArgs a, const SolveAr
     if (o == 0) k_odo_assoc<8><<<ga, 256, 0, st>>>(a);   // first iteration: more features lack a nearby candidate
     else k_odo_assoc<32><<<gs, 256, 0, st>>>(a);
     SolveArgs sa = solve_proto;
-    sa.which = 0; sa.outer = o; sa.factors = a.factors; sa.factor_cap = a.factor_cap;
+    sa.which = 0; sa.outer = o; sa.factors = a.factors; sa.factor_cap = a.factor_cap; sa.distort = a.distortion != 0;
     lvo_launch_lm(st, sa, lanes, nfeat_cap);
     if (launches) *launches += 2;
   }
   k_odo_integrate<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a, outer_iters);
+  if (a.distortion == 2) { k_odo_to_end<<<dim3(64, lanes), 256, 0, st>>>(a); if (launches) *launches += 1; }
   k_odo_swap<<<dim3(32, lanes), 256, 0, st>>>(a);
   if (launches) *launches += 2;
   lvo_grid_build(st, a.grid, launches);

@@ -155,11 +155,68 @@ __device__ inline void plus7_dev(const double* x, const double* delta, double* x
 }
 
 // ---- one residual block: accumulate rho' * J^T J (upper triangle), rho' * J^T r, rho / 2 --------------------------
+// DISTORT: the factor carries an interpolation ratio s (f.d) that may differ from 1 (DISTORTION 1, laserOdometry.cpp:455-459):
+// lp = slerp(Identity, q; s) * c + s t, lidarFactor.hpp:27-33 / :79-85.  The 3x4 Jacobian d lp / d(qx,qy,qz,qw) is taken through the
+// functor as written (the slerp weights depend on q.w; Eigen's v + w uv + u x uv, uv = 2 u x v, differentiated without assuming a
+// unit quaternion) and multiplied by the 4x3 plus-Jacobian of EigenQuaternionParameterization.
+__device__ __forceinline__ d3 interp_point_jacobian(const double* x, double s, const d3& c, double Jl[3][6]) {
+  const SlerpW k = slerp_identity_weights(x[3], s, true);
+  const double u[3] = {k.scale1 * x[0], k.scale1 * x[1], k.scale1 * x[2]};
+  const double ws = k.scale0 + k.scale1 * x[3];
+  const double qs[4] = {u[0], u[1], u[2], ws};
+  const d3 rc = quat_rotate(qs, c);
+  const double cv[3] = {c.x, c.y, c.z};
+  const double uc = u[0] * cv[0] + u[1] * cv[1] + u[2] * cv[2];
+  const double cx[3][3] = {{0, -c.z, c.y}, {c.z, 0, -c.x}, {-c.y, c.x, 0}};
+  const d3 b2 = d3cross(d3{u[0], u[1], u[2]}, c);
+  const double bw[3] = {2.0 * b2.x, 2.0 * b2.y, 2.0 * b2.z};
+  const double dws_dw = k.ds0_dw + k.ds1_dw * x[3] + k.scale1;
+  const double P[4][3] = {{x[3], x[2], -x[1]}, {-x[2], x[3], x[0]}, {x[1], -x[0], x[3]}, {-x[0], -x[1], -x[2]}};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double A[3], G[4];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) A[j] = -2.0 * ws * cx[i][j] + 2.0 * ((i == j ? uc : 0.0) + u[i] * cv[j] - 2.0 * cv[i] * u[j]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) G[j] = A[j] * k.scale1;
+    G[3] = (A[0] * x[0] + A[1] * x[1] + A[2] * x[2]) * k.ds1_dw + bw[i] * dws_dw;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      Jl[i][j] = G[0] * P[0][j] + G[1] * P[1][j] + G[2] * P[2][j] + G[3] * P[3][j];
+      Jl[i][3 + j] = i == j ? s : 0.0;
+    }
+  }
+  return d3{rc.x + s * x[4], rc.y + s * x[5], rc.z + s * x[6]};
+}
+
+template <bool DISTORT>
 __device__ __forceinline__ void accumulate_factor(const LvoFactor& f, const double* x, double huber, double* acc) {
-  const d3 rc = quat_rotate(x, d3{f.c[0], f.c[1], f.c[2]});
-  const d3 lp{rc.x + x[4], rc.y + x[5], rc.z + x[6]};
   double J[3][6], r[3];
   int k;
+  if (DISTORT && f.type <= 1 && f.d != 1.0) {
+    double Jl[3][6];
+    const d3 lp = interp_point_jacobian(x, f.d, d3{f.c[0], f.c[1], f.c[2]}, Jl);
+    if (f.type == 0) {
+      const d3 u{lp.x - f.a[0], lp.y - f.a[1], lp.z - f.a[2]}, v{lp.x - f.b[0], lp.y - f.b[1], lp.z - f.b[2]};
+      const d3 nu = d3cross(u, v);
+      const d3 de{f.a[0] - f.b[0], f.a[1] - f.b[1], f.a[2] - f.b[2]};
+      const double den = sqrt(de.x * de.x + de.y * de.y + de.z * de.z);
+      r[0] = nu.x / den; r[1] = nu.y / den; r[2] = nu.z / den;
+      const double D[3][3] = {{0, de.z / den, -de.y / den}, {-de.z / den, 0, de.x / den}, {de.y / den, -de.x / den, 0}};
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) J[i][c] = D[i][0] * Jl[0][c] + D[i][1] * Jl[1][c] + D[i][2] * Jl[2][c];
+      k = 3;
+    } else {
+      r[0] = (lp.x - f.a[0]) * f.b[0] + (lp.y - f.a[1]) * f.b[1] + (lp.z - f.a[2]) * f.b[2];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) J[0][c] = f.b[0] * Jl[0][c] + f.b[1] * Jl[1][c] + f.b[2] * Jl[2][c];
+      k = 1;
+    }
+  } else {
+  const d3 rc = quat_rotate(x, d3{f.c[0], f.c[1], f.c[2]});
+  const d3 lp{rc.x + x[4], rc.y + x[5], rc.z + x[6]};
   if (f.type == 0) {
     const d3 u{lp.x - f.a[0], lp.y - f.a[1], lp.z - f.a[2]}, v{lp.x - f.b[0], lp.y - f.b[1], lp.z - f.b[2]};
     const d3 nu = d3cross(u, v);
@@ -192,6 +249,7 @@ __device__ __forceinline__ void accumulate_factor(const LvoFactor& f, const doub
     J[0][3] = n[0]; J[0][4] = n[1]; J[0][5] = n[2];
     k = 1;
   }
+  }
   double s = 0;
   for (int i = 0; i < k; ++i) s += r[i] * r[i];
   double rho0, rho1;
@@ -220,6 +278,7 @@ struct SolveArgs {
   int max_iters;
   double huber;
   double* trace;              // [lanes][LVO_MAX_OUTER][LVO_MAX_LM + 1][LVO_TRACE_W] or null
+  int distort;                // != 0: factors may carry an interpolation ratio s != 1 (scan-to-scan with DISTORTION 1)
 };
 
 struct LmShared {
@@ -231,6 +290,7 @@ struct LmShared {
 };
 
 // All CTAs of the cluster call this; afterwards CTA 0's sh.sum holds the cluster-wide sums (fixed summation tree).
+template <bool DISTORT>
 __device__ __forceinline__ void lm_evaluate(const SolveArgs& a, const LvoFactor* F, int nslots, const double* x, LmShared& sh, cg::cluster_group& cluster) {
   const unsigned crank = cluster.block_rank(), csize = cluster.num_blocks();
   double acc[LVO_NACC];
@@ -238,7 +298,7 @@ __device__ __forceinline__ void lm_evaluate(const SolveArgs& a, const LvoFactor*
   for (int i = 0; i < LVO_NACC; ++i) acc[i] = 0.0;
   for (int s = crank * LVO_LM_THREADS + threadIdx.x; s < nslots; s += LVO_LM_THREADS * csize) {
     const LvoFactor f = F[s];
-    if (f.type >= 0) accumulate_factor(f, x, a.huber, acc);
+    if (f.type >= 0) accumulate_factor<DISTORT>(f, x, a.huber, acc);
   }
   const unsigned ln = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
@@ -348,6 +408,7 @@ __device__ inline bool lm_next_step(const SolveArgs& a, int lane, LmCtl& c) {
   }
 }
 
+template <bool DISTORT>
 __global__ void __launch_bounds__(LVO_LM_THREADS, 2) k_lm_solve(SolveArgs a) {
   __shared__ LmShared sh;
   __shared__ LmCtl ctl;  // only thread 0 of CTA 0 touches it; shared to keep it out of its registers
@@ -361,7 +422,7 @@ __global__ void __launch_bounds__(LVO_LM_THREADS, 2) k_lm_solve(SolveArgs a) {
   double* xg = a.which == 0 ? s.para_q : s.map_x;  // para_q[4], para_t[3] are contiguous
   if (threadIdx.x < 7) sh.xeval[threadIdx.x] = xg[threadIdx.x];
   __syncthreads();
-  lm_evaluate(a, F, nslots, sh.xeval, sh, cluster);
+  lm_evaluate<DISTORT>(a, F, nslots, sh.xeval, sh, cluster);
   if (lead) {
     LmCtl& c = ctl;
     for (int i = 0; i < 7; ++i) c.x[i] = sh.xeval[i];
@@ -387,7 +448,7 @@ __global__ void __launch_bounds__(LVO_LM_THREADS, 2) k_lm_solve(SolveArgs a) {
   }
   cluster.sync();
   while (sh.ctrl == 0) {
-    lm_evaluate(a, F, nslots, sh.xeval, sh, cluster);
+    lm_evaluate<DISTORT>(a, F, nslots, sh.xeval, sh, cluster);
     if (lead) {
       LmCtl& c = ctl;
       const double new_cost = sh.sum[27];
@@ -450,5 +511,6 @@ static inline void lvo_launch_lm(cudaStream_t st, const SolveArgs& sa, int lanes
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, k_lm_solve, sa);
+  if (sa.distort) cudaLaunchKernelEx(&cfg, k_lm_solve<true>, sa);
+  else cudaLaunchKernelEx(&cfg, k_lm_solve<false>, sa);
 }

@@ -110,9 +110,28 @@ class LaserOdometry {
     for (int k = 0; k < 3; ++k) { T_last_curr.t[k] = a.t[k]; T_w_curr.t[k] = b.t[k]; }
     return r;
   }
+  // Distortion mode 2 only (lvo_config::distortion): the clouds that laserOdometry.cpp:646-662 would publish after the
+  // TransformToEnd block :610-625 — call after process() and hand the results to LaserMapping::process.
+  // cornerLast / surfLast were transformed on the device by process(); the full-resolution cloud is transformed here.
+  template <class Cloud>
+  void publishedClouds(Cloud& laserCloudCornerLast, Cloud& laserCloudSurfLast, Cloud& laserCloudFullRes) {
+    if (buf_.size() < c_.capacity()) buf_.resize(c_.capacity());
+    const int what[2] = {LVO_P_LESS_SHARP, LVO_P_LESS_FLAT};
+    Cloud* dst[2] = {&laserCloudCornerLast, &laserCloudSurfLast};
+    for (int k = 0; k < 2; ++k) {
+      size_t bytes = 0;
+      c_.check(lvo_probe_fetch(c_.get(), 0, what[k], buf_.data(), buf_.size() * sizeof(lvo_point), &bytes));
+      detail::store(buf_, bytes / sizeof(lvo_point), *dst[k]);
+    }
+    lvo_cloud_out o;
+    o.data = buf_.data(); o.cap = buf_.size(); o.n = 0;
+    c_.check(lvo_transform_cloud(c_.get(), view_of(laserCloudFullRes), nullptr, 1, &o));
+    detail::store(buf_, o.n, laserCloudFullRes);
+  }
 
  private:
   Context& c_;
+  std::vector<lvo_point> buf_;
 };
 
 class LaserMapping {
@@ -130,12 +149,32 @@ class LaserMapping {
     for (int k = 0; k < 4; ++k) T_w_curr.q[k] = out.q[k];
     for (int k = 0; k < 3; ++k) T_w_curr.t[k] = out.t[k];
     detail::store(reg_, reg.n, laserCloudFullRes);
+    frameCount_++;
     return r;
   }
+  // The publication schedule of laserMapping.cpp:806-836 (frameCount is incremented at the end of process(), :854):
+  // true when the frame just processed is one on which the reference publishes /laser_cloud_surround (every 5th)
+  // or /laser_cloud_map (every 20th).
+  bool surroundDue() const { return frameCount_ > 0 && (frameCount_ - 1) % 5 == 0; }
+  bool mapDue() const { return frameCount_ > 0 && (frameCount_ - 1) % 20 == 0; }
+  template <class Cloud>
+  void laserCloudSurround(Cloud& out) { fetch(0, out); }   // :806-815
+  template <class Cloud>
+  void laserCloudMap(Cloud& out) { fetch(1, out); }        // :823-836
 
  private:
+  template <class Cloud>
+  void fetch(int which, Cloud& out) {
+    lvo_cloud_out o;
+    o.data = map_.data(); o.cap = map_.size(); o.n = 0;
+    int r = lvo_map_cloud(c_.get(), 0, which, &o);
+    if (r == LVO_E_CAPACITY) { map_.resize(o.n); o.data = map_.data(); o.cap = map_.size(); r = lvo_map_cloud(c_.get(), 0, which, &o); }
+    c_.check(r);
+    detail::store(map_, o.n, out);
+  }
   Context& c_;
-  std::vector<lvo_point> reg_;
+  std::vector<lvo_point> reg_, map_;
+  long frameCount_ = 0;
 };
 
 }  // namespace lvo

@@ -10,7 +10,9 @@
 // sensor pose into an endless procedural street: ground plane, two facades with hashed recesses (vertical edges),
 // poles, boxes.  Range noise N(0, 0.01 m); rays without a return inside 120 m are dropped.
 // The trajectory is KITTI-00-shaped: `speed` m/frame forward with an S-curve yaw and a small roll/pitch/z wobble,
-// applied rigidly per sweep (no intra-sweep distortion, consistent with DISTORTION 0, laserOdometry.cpp:67).
+// applied rigidly per sweep (no intra-sweep distortion, consistent with DISTORTION 0, laserOdometry.cpp:67) by
+// lvo_synth_sweep; lvo_synth_sweep_moving casts every azimuth column from the pose interpolated between frame and frame + 1
+// (a spinning sensor on a moving platform: the input DISTORTION 1 is written for).
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -129,7 +131,8 @@ struct Scene {
 
 struct Pose { double R[9]; double t[3]; double q[4]; };
 
-void pose_of(int seq, int frame, double speed, Pose& P) {
+// x, y, z, yaw, pitch, roll of the sensor at an integer frame
+void pose_params(int seq, int frame, double speed, double p[6]) {
   // integrate the planar path
   double x = 0, y = 0;
   const double A = 10.0 * M_PI / 180.0, T = 80.0;
@@ -138,10 +141,14 @@ void pose_of(int seq, int frame, double speed, Pose& P) {
     double yaw = A * std::sin(2 * M_PI * k / T + phase);
     x += speed * std::cos(yaw); y += speed * std::sin(yaw);
   }
-  double yaw = A * std::sin(2 * M_PI * frame / T + phase);
-  double roll = 0.5 * M_PI / 180.0 * std::sin(frame / 7.0 + seq);
-  double pitch = 0.3 * M_PI / 180.0 * std::sin(frame / 11.0 + 2.0 * seq);
-  double z = 0.05 * std::sin(frame / 13.0 + 0.5 * seq);
+  p[0] = x; p[1] = y;
+  p[2] = 0.05 * std::sin(frame / 13.0 + 0.5 * seq);
+  p[3] = A * std::sin(2 * M_PI * frame / T + phase);
+  p[4] = 0.3 * M_PI / 180.0 * std::sin(frame / 11.0 + 2.0 * seq);
+  p[5] = 0.5 * M_PI / 180.0 * std::sin(frame / 7.0 + seq);
+}
+void pose_from_params(const double p[6], Pose& P) {
+  const double x = p[0], y = p[1], z = p[2], yaw = p[3], pitch = p[4], roll = p[5];
   double cy = std::cos(yaw), sy = std::sin(yaw), cp = std::cos(pitch), sp = std::sin(pitch), cr = std::cos(roll), sr = std::sin(roll);
   // R = Rz(yaw) Ry(pitch) Rx(roll)
   double R[9] = {cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr,
@@ -157,6 +164,11 @@ void pose_of(int seq, int frame, double speed, Pose& P) {
   P.q[1] = crh * sph * cyh + srh * cph * syh;
   P.q[2] = crh * cph * syh - srh * sph * cyh;
 }
+void pose_of(int seq, int frame, double speed, Pose& P) {
+  double p[6];
+  pose_params(seq, frame, speed, p);
+  pose_from_params(p, P);
+}
 
 }  // namespace
 
@@ -165,18 +177,25 @@ extern "C" {
 // Number of rays of a sensor model (upper bound of the points a sweep can contain).
 long lvo_synth_rays(int model) { return model == 16 ? 16L * 1800 : 64L * 1875; }
 
+}  // extern "C"
+
 // Generates sweep `frame` of sequence `seq` into out[cap] (packed x,y,z,intensity=0).  gt_pose7 (optional) gets the
 // ground-truth sensor pose (q xyzw, t) in the frame of sweep 0 of the same sequence.  Returns the number of points,
 // or -1 if cap is too small / the model is unknown.
-long lvo_synth_sweep(int model, int seq, int frame, double speed, float* out_xyzi, long cap, double* gt_pose7) {
+static long synth_sweep(int model, int seq, int frame, double speed, float* out_xyzi, long cap, double* gt_pose7, bool moving) {
   if (model != 16 && model != 64) return -1;
   const int beams = model, naz = model == 16 ? 1800 : 1875;
   if (cap < (long)beams * naz) return -1;
   Scene sc;
   sc.seed = 1000ull * (uint64_t)model + 10ull * (uint64_t)seq;
   Pose P, P0;
-  pose_of(seq, frame, speed, P);
-  pose_of(seq, 0, speed, P0);
+  double pa[6], pb[6];
+  pose_params(seq, frame, speed, pa);
+  pose_params(seq, frame + 1, speed, pb);
+  // ground truth: rigid sweeps -> pose at `frame` relative to frame 0; moving sensor -> pose at the END of the sweep relative to
+  // the end of sweep 0 (what q_w_curr / t_w_curr accumulate when the clouds are moved to the sweep end, laserOdometry.cpp:176-191)
+  pose_of(seq, moving ? frame + 1 : frame, speed, P);
+  pose_of(seq, moving ? 1 : 0, speed, P0);
   if (gt_pose7) {
     // relative pose T0^-1 * T  (frame 0 is the odometry / map origin, laserOdometry.cpp:126-128)
     double Rr[9], tr[3], dt[3] = {P.t[0] - P0.t[0], P.t[1] - P0.t[1], P.t[2] - P0.t[2]};
@@ -199,7 +218,14 @@ long lvo_synth_sweep(int model, int seq, int frame, double speed, float* out_xyz
   const double min_keep = 0.05, max_range = 120.0, sigma = 0.01;
   long n = 0;
   P4* out = reinterpret_cast<P4*>(out_xyzi);
+  if (!moving) pose_from_params(pa, P);
   for (int j = 0; j < naz; ++j) {
+    if (moving) {
+      const double tau = (double)j / naz;
+      double pi[6];
+      for (int k = 0; k < 6; ++k) pi[k] = pa[k] + tau * (pb[k] - pa[k]);
+      pose_from_params(pi, P);
+    }
     double az = az0 - j * step;
     double ca = std::cos(az), sa = std::sin(az);
     for (int b = 0; b < beams; ++b) {
@@ -220,6 +246,16 @@ long lvo_synth_sweep(int model, int seq, int frame, double speed, float* out_xyz
     }
   }
   return n;
+}
+
+extern "C" {
+long lvo_synth_sweep(int model, int seq, int frame, double speed, float* out_xyzi, long cap, double* gt_pose7) {
+  return synth_sweep(model, seq, frame, speed, out_xyzi, cap, gt_pose7, false);
+}
+// Same scene and trajectory, but the sensor keeps moving while it spins: column j of the sweep is cast from the pose at time
+// frame + j / naz.  gt_pose7 = pose at the end of the sweep relative to the end of sweep 0.
+long lvo_synth_sweep_moving(int model, int seq, int frame, double speed, float* out_xyzi, long cap, double* gt_pose7) {
+  return synth_sweep(model, seq, frame, speed, out_xyzi, cap, gt_pose7, true);
 }
 
 }  // extern "C"

@@ -78,6 +78,23 @@ int lvo_oracle_eval_factor(const double* f, const double* x, double* r, double* 
   F.d = f[13];
   return eval_factor(F, x, r, J);
 }
+// same with the interpolation ratio s of LidarEdgeFactor / LidarPlaneFactor (DISTORTION 1)
+int lvo_oracle_eval_factor_s(const double* f, double s, const double* x, double* r, double* J) {
+  Factor F;
+  F.type = (int)f[0];
+  F.c = Vec3{f[1], f[2], f[3]}; F.a = Vec3{f[4], f[5], f[6]}; F.b = Vec3{f[7], f[8], f[9]}; F.m = Vec3{f[10], f[11], f[12]};
+  F.d = f[13]; F.s = s;
+  return eval_factor(F, x, r, J);
+}
+// TransformToStart / TransformToEnd (laserOdometry.cpp:154-191) of n points under (q_last_curr, t_last_curr) = qt[7]
+void lvo_oracle_transform(const Pt* in, long n, const double* qt, int distortion, int to_end, Pt* out) {
+  const Quat q{qt[0], qt[1], qt[2], qt[3]};
+  const Vec3 t{qt[4], qt[5], qt[6]};
+  for (long i = 0; i < n; ++i) {
+    if (to_end) LaserOdometry::transform_to_end(q, t, distortion, in[i], out[i]);
+    else LaserOdometry::transform_to_start(q, t, distortion, in[i], out[i]);
+  }
+}
 
 // LM solve on nf factors (14 doubles each); x[7] in/out; trace rows of 10 doubles (x7,cost,radius,flags); returns rows
 int lvo_oracle_solve(const double* f, long nf, double* x, int max_iters, double huber, double* trace, int trace_cap) {
@@ -127,6 +144,8 @@ void* lvo_oracle_create(int n_scans, double min_range, double line_res, double p
   return p;
 }
 void lvo_oracle_destroy(void* h) { delete (Pipeline*)h; }
+// 0 = DISTORTION 0 (laserOdometry.cpp:67 as shipped), 1 = DISTORTION 1 as written, 2 = DISTORTION 1 + the TransformToEnd block :610-625
+void lvo_oracle_set_distortion(void* h, int mode) { ((Pipeline*)h)->odo.distortion = mode; }
 
 int lvo_oracle_extract(void* h, const Pt* in, long n) {
   Pipeline* p = (Pipeline*)h;
@@ -170,6 +189,11 @@ int lvo_oracle_odometry(void* h, const Pt* sharp, long ns, const Pt* lsharp, lon
   }
   if (r == 0 && p->odo.few_corr) r = 2;
   return r;
+}
+// the "last" clouds after the frame (what :646-656 publishes): which 0 corner, 1 surf, 2 full (distortion 2 only)
+long lvo_oracle_odometry_last(void* h, int which, Pt* out, long cap) {
+  Pipeline* p = (Pipeline*)h;
+  return copy_out(which == 0 ? p->odo.laserCloudCornerLast : (which == 1 ? p->odo.laserCloudSurfLast : p->odo.fullOut), out, cap);
 }
 // what: 0 corner_corr(int) 1 plane_corr(int) 2 lm trace (double rows of 10) ; 3 counts [n_corner,n_plane,lm_iters] (int) ; 4 final cost (double[1])
 long lvo_oracle_odometry_log(void* h, int outer, int what, void* out, long cap) {
@@ -253,6 +277,13 @@ long lvo_oracle_map_export(void* h, int which, Pt* out, int* cube, long cap) {
   }
   return n;
 }
+// laserMapping.cpp:806-836: which 0 = surround cloud (valid cubes of the last frame, corner then surf per cube), 1 = whole map
+long lvo_oracle_map_cloud(void* h, int which, Pt* out, long cap) {
+  Pipeline* p = (Pipeline*)h;
+  Cloud c;
+  if (which == 0) p->map.surround_cloud(c); else p->map.whole_map_cloud(c);
+  return copy_out(c, out, cap);
+}
 void lvo_oracle_map_import(void* h, int which, const Pt* pts, const int* cube, long n) {
   Pipeline* p = (Pipeline*)h;
   std::vector<Cloud>& arr = which == 0 ? p->map.laserCloudCornerArray : p->map.laserCloudSurfArray;
@@ -272,11 +303,11 @@ int lvo_oracle_step(void* h, const Pt* in, long n, double* poses_out, int keep_l
   double t0 = now_ms();
   scan_registration(in, (size_t)n, p->n_scans, p->min_range, p->reg);
   double t1 = now_ms();
-  int r = p->odo.process(p->reg.sharp, p->reg.lessSharp, p->reg.flat, p->reg.lessFlat, keep_log != 0);
+  int r = p->odo.process(p->reg.sharp, p->reg.lessSharp, p->reg.flat, p->reg.lessFlat, keep_log != 0, &p->reg.full);
   double t2 = now_ms();
   // laserOdometry publishes laserCloudCornerLast/SurfLast (= this frame's less-sharp / less-flat) and the full cloud (:646-662)
-  p->map.process(p->odo.laserCloudCornerLast, p->odo.laserCloudSurfLast, &p->reg.full, p->odo.q_w_curr, p->odo.t_w_curr, &p->registered,
-                 keep_log != 0);
+  p->map.process(p->odo.laserCloudCornerLast, p->odo.laserCloudSurfLast, p->odo.distortion == 2 ? &p->odo.fullOut : &p->reg.full, p->odo.q_w_curr,
+                 p->odo.t_w_curr, &p->registered, keep_log != 0);
   double t3 = now_ms();
   p->ms_reg = t1 - t0; p->ms_odo = t2 - t1; p->ms_map = t3 - t2;
   if (poses_out) {

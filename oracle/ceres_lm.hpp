@@ -34,6 +34,7 @@ struct Factor {
   int type;
   Vec3 c, a, b, m;
   double d;
+  double s = 1.0;  // interpolation ratio of LidarEdgeFactor / LidarPlaneFactor (lidarFactor.hpp:15,60); 1.0 unless DISTORTION (laserOdometry.cpp:455-459,549-554)
 };
 
 struct LmTraceRow { double x[7]; double cost; double radius; int flags; };
@@ -68,6 +69,37 @@ inline void plus7(const double* x, const double* delta, double* xp) {
   xp[4] = x[4] + delta[3]; xp[5] = x[5] + delta[4]; xp[6] = x[6] + delta[5];
 }
 
+
+// Eigen 3.3.7 QuaternionBase::slerp (Eigen/src/Geometry/Quaternion.h:716-746) of Identity towards q at parameter s, as the
+// functors (lidarFactor.hpp:27-30,79-82) and TransformToStart (laserOdometry.cpp:163) call it.  Also returns the derivatives of
+// the two blend weights with respect to q.w (the only component they depend on: d = Identity.dot(q) = q.w), which is what
+// forward-mode autodiff of the functor propagates (abs: sign of the value; acos: -1 / sqrt(1 - a^2)).
+struct SlerpWeights { double scale0, scale1, ds0_dw, ds1_dw; };
+inline SlerpWeights slerp_identity_weights(double w, double s) {
+  SlerpWeights o{0, 0, 0, 0};
+  const double one = 1.0 - DBL_EPSILON;
+  const double d = w, absD = fabs(d);
+  if (absD >= one) { o.scale0 = 1.0 - s; o.scale1 = s; }
+  else {
+    const double theta = acos(absD), sinTheta = sin(theta), cosTheta = cos(theta);
+    const double a0 = (1.0 - s) * theta, a1 = s * theta;
+    o.scale0 = sin(a0) / sinTheta;
+    o.scale1 = sin(a1) / sinTheta;
+    const double dtheta_dw = (d < 0 ? 1.0 : -1.0) / sqrt(1.0 - absD * absD);
+    // d/dtheta [sin(k theta) / sin(theta)] = (k cos(k theta) sin(theta) - sin(k theta) cos(theta)) / sin^2(theta)
+    o.ds0_dw = ((1.0 - s) * cos(a0) * sinTheta - sin(a0) * cosTheta) / (sinTheta * sinTheta) * dtheta_dw;
+    o.ds1_dw = (s * cos(a1) * sinTheta - sin(a1) * cosTheta) / (sinTheta * sinTheta) * dtheta_dw;
+  }
+  if (d < 0) { o.scale1 = -o.scale1; o.ds1_dw = -o.ds1_dw; }
+  return o;
+}
+inline Quat slerp_identity(const Quat& q, double s) {
+  const SlerpWeights k = slerp_identity_weights(q.w, s);
+  return Quat{k.scale0 * 0.0 + k.scale1 * q.x, k.scale0 * 0.0 + k.scale1 * q.y, k.scale0 * 0.0 + k.scale1 * q.z, k.scale0 * 1.0 + k.scale1 * q.w};
+}
+
+inline int eval_factor_interp(const Factor& f, const double* x, double* r, double* J);
+
 // Residual (k = 3 or 1 rows) and local 6-column Jacobian of one block at x = (q xyzw, t), before the loss.
 inline int eval_factor(const Factor& f, const double* x, double* r, double* J /* k x 6 row-major, may be null */) {
 #ifdef LVO_ORACLE_USE_REFERENCE
@@ -77,8 +109,8 @@ inline int eval_factor(const Factor& f, const double* x, double* r, double* J /*
   for (int i = 0; i < 3; ++i) t[i] = JetT(x[4 + i], 4 + i);
   int k;
   Eigen::Vector3d c(f.c.x, f.c.y, f.c.z), a(f.a.x, f.a.y, f.a.z), b(f.b.x, f.b.y, f.b.z), m(f.m.x, f.m.y, f.m.z);
-  if (f.type == F_EDGE) { LidarEdgeFactor fn(c, a, b, 1.0); fn(q, t, res); k = 3; }
-  else if (f.type == F_PLANE) { LidarPlaneFactor fn(c, a, b, m, 1.0); fn(q, t, res); k = 1; }
+  if (f.type == F_EDGE) { LidarEdgeFactor fn(c, a, b, f.s); fn(q, t, res); k = 3; }
+  else if (f.type == F_PLANE) { LidarPlaneFactor fn(c, a, b, m, f.s); fn(q, t, res); k = 1; }
   else { LidarPlaneNormFactor fn(c, a, f.d); fn(q, t, res); k = 1; }
   // EigenQuaternionParameterization::ComputeJacobian (4x3, xyzw storage)
   const double P[4][3] = {{x[3], x[2], -x[1]}, {-x[2], x[3], x[0]}, {x[1], -x[0], x[3]}, {-x[0], -x[1], -x[2]}};
@@ -95,6 +127,7 @@ inline int eval_factor(const Factor& f, const double* x, double* r, double* J /*
   }
   return k;
 #else
+  if (f.type != F_PLANE_NORM && f.s != 1.0) return eval_factor_interp(f, x, r, J);
   Quat q{x[0], x[1], x[2], x[3]};
   Vec3 rc = rotate(q, f.c);
   Vec3 lp{rc.x + x[4], rc.y + x[5], rc.z + x[6]};
@@ -139,6 +172,63 @@ inline int eval_factor(const Factor& f, const double* x, double* r, double* J /*
   }
   return 1;
 #endif
+}
+
+// LidarEdgeFactor / LidarPlaneFactor with s != 1 (DISTORTION 1): lp = slerp(Identity, q; s) * c + s t, lidarFactor.hpp:27-33,79-85.
+// The global 3x4 Jacobian d lp / d(qx,qy,qz,qw) is taken through the functor exactly as written (slerp weights depend on q.w;
+// Eigen's _transformVector formula v + w uv + u x uv, uv = 2 u x v, differentiated without assuming |q_s| = 1), then multiplied
+// by the 4x3 plus-Jacobian of EigenQuaternionParameterization.
+inline int eval_factor_interp(const Factor& f, const double* x, double* r, double* J) {
+  const double s = f.s;
+  const SlerpWeights k = slerp_identity_weights(x[3], s);
+  const Vec3 u{k.scale1 * x[0], k.scale1 * x[1], k.scale1 * x[2]};
+  const double ws = k.scale0 + k.scale1 * x[3];
+  const Vec3 c = f.c;
+  const Vec3 rc = rotate(Quat{u.x, u.y, u.z, ws}, c);
+  const Vec3 lp{rc.x + s * x[4], rc.y + s * x[5], rc.z + s * x[6]};
+  double Jl[3][6];
+  if (J) {
+    const double uc = u.x * c.x + u.y * c.y + u.z * c.z;
+    const double cv[3] = {c.x, c.y, c.z}, uv_[3] = {u.x, u.y, u.z};
+    const double cx[3][3] = {{0, -c.z, c.y}, {c.z, 0, -c.x}, {-c.y, c.x, 0}};
+    double A[3][3];   // d lp / d u
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) A[i][j] = -2.0 * ws * cx[i][j] + 2.0 * ((i == j ? uc : 0.0) + uv_[i] * cv[j] - 2.0 * cv[i] * uv_[j]);
+    const Vec3 b2 = cross(u, c);
+    const double bw[3] = {2.0 * b2.x, 2.0 * b2.y, 2.0 * b2.z};  // d lp / d ws
+    double G[3][4];   // d lp / d (qx, qy, qz, qw)
+    const double dws_dw = k.ds0_dw + k.ds1_dw * x[3] + k.scale1;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) G[i][j] = A[i][j] * k.scale1;
+      G[i][3] = (A[i][0] * x[0] + A[i][1] * x[1] + A[i][2] * x[2]) * k.ds1_dw + bw[i] * dws_dw;
+    }
+    const double P[4][3] = {{x[3], x[2], -x[1]}, {-x[2], x[3], x[0]}, {x[1], -x[0], x[3]}, {-x[0], -x[1], -x[2]}};
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        Jl[i][j] = G[i][0] * P[0][j] + G[i][1] * P[1][j] + G[i][2] * P[2][j] + G[i][3] * P[3][j];
+        Jl[i][3 + j] = i == j ? s : 0.0;
+      }
+  }
+  if (f.type == F_EDGE) {
+    Vec3 uu{lp.x - f.a.x, lp.y - f.a.y, lp.z - f.a.z}, vv{lp.x - f.b.x, lp.y - f.b.y, lp.z - f.b.z};
+    Vec3 nu = cross(uu, vv);
+    Vec3 de{f.a.x - f.b.x, f.a.y - f.b.y, f.a.z - f.b.z};
+    double den = sqrt(de.x * de.x + de.y * de.y + de.z * de.z);
+    r[0] = nu.x / den; r[1] = nu.y / den; r[2] = nu.z / den;
+    if (J) {
+      const double D[3][3] = {{0, de.z / den, -de.y / den}, {-de.z / den, 0, de.x / den}, {de.y / den, -de.x / den, 0}};
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 6; ++j) J[i * 6 + j] = D[i][0] * Jl[0][j] + D[i][1] * Jl[1][j] + D[i][2] * Jl[2][j];
+    }
+    return 3;
+  }
+  Vec3 jl{f.a.x - f.b.x, f.a.y - f.b.y, f.a.z - f.b.z}, jm{f.a.x - f.m.x, f.a.y - f.m.y, f.a.z - f.m.z};
+  Vec3 n = cross(jl, jm);
+  double nn = sqrt(n.x * n.x + n.y * n.y + n.z * n.z);
+  n.x /= nn; n.y /= nn; n.z /= nn;
+  r[0] = (lp.x - f.a.x) * n.x + (lp.y - f.a.y) * n.y + (lp.z - f.a.z) * n.z;
+  if (J) for (int j = 0; j < 6; ++j) J[j] = n.x * Jl[0][j] + n.y * Jl[1][j] + n.z * Jl[2][j];
+  return 1;
 }
 
 // Program evaluation as ceres::internal::ProgramEvaluator + ResidualBlock::Evaluate:

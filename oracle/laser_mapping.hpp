@@ -39,6 +39,8 @@ class LaserMapping {
   std::vector<MapOuterLog> log;
   int centerCube[3] = {0, 0, 0};
   bool map_too_small = false;
+  int laserCloudValidInd[125];     // :85; in this fork laserCloudSurroundInd (:86) is filled with the same cubes (:524-525)
+  int laserCloudValidNum = 0;
 
   LaserMapping() : laserCloudCornerArray(laserCloudNum), laserCloudSurfArray(laserCloudNum) {}
 
@@ -96,8 +98,7 @@ class LaserMapping {
     while (centerCubeK >= laserCloudDepth - 3) { shift(laserCloudCornerArray, 2, -1); shift(laserCloudSurfArray, 2, -1); centerCubeK--; laserCloudCenDepth--; }  // :478-507
     centerCube[0] = centerCubeI; centerCube[1] = centerCubeJ; centerCube[2] = centerCubeK;
 
-    int laserCloudValidInd[125];
-    int laserCloudValidNum = 0;
+    laserCloudValidNum = 0;
     for (int i = centerCubeI - 2; i <= centerCubeI + 2; i++)      // :512-529
       for (int j = centerCubeJ - 2; j <= centerCubeJ + 2; j++)
         for (int k = centerCubeK - 1; k <= centerCubeK + 1; k++)
@@ -244,6 +245,24 @@ class LaserMapping {
     if (full && registered) {  // :838-842
       registered->resize(full->size());
       for (size_t i = 0; i < full->size(); ++i) pointAssociateToMap((*full)[i], (*registered)[i]);
+    }
+  }
+
+  // "publish surround map for every 5 frame" :806-815: the valid cubes of the last frame, corner then surf per cube
+  void surround_cloud(Cloud& out) const {
+    out.clear();
+    for (int i = 0; i < laserCloudValidNum; i++) {
+      const int ind = laserCloudValidInd[i];
+      out.insert(out.end(), laserCloudCornerArray[ind].begin(), laserCloudCornerArray[ind].end());
+      out.insert(out.end(), laserCloudSurfArray[ind].begin(), laserCloudSurfArray[ind].end());
+    }
+  }
+  // whole-map dump every 20 frames :823-836
+  void whole_map_cloud(Cloud& out) const {
+    out.clear();
+    for (int i = 0; i < laserCloudNum; i++) {
+      out.insert(out.end(), laserCloudCornerArray[i].begin(), laserCloudCornerArray[i].end());
+      out.insert(out.end(), laserCloudSurfArray[i].begin(), laserCloudSurfArray[i].end());
     }
   }
 

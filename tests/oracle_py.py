@@ -25,14 +25,17 @@ class Synth:
         self.lib.lvo_synth_rays.restype = C.c_long
         self.lib.lvo_synth_sweep.restype = C.c_long
         self.lib.lvo_synth_sweep.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_long, C.c_void_p]
+        self.lib.lvo_synth_sweep_moving.restype = C.c_long
+        self.lib.lvo_synth_sweep_moving.argtypes = self.lib.lvo_synth_sweep.argtypes
 
-    def sweep(self, model, seq, frame, speed=None):
+    def sweep(self, model, seq, frame, speed=None, moving=False):
+        """moving=True: the sensor keeps moving while it spins (intra-sweep motion distortion, the DISTORTION 1 input)."""
         if speed is None:
             speed = 1.0 if model == 64 else 0.2
         cap = self.lib.lvo_synth_rays(model)
         out = np.empty((cap, 4), np.float32)
         gt = np.empty(7, np.float64)
-        n = self.lib.lvo_synth_sweep(model, seq, frame, speed, _ptr(out), cap, _ptr(gt))
+        n = (self.lib.lvo_synth_sweep_moving if moving else self.lib.lvo_synth_sweep)(model, seq, frame, speed, _ptr(out), cap, _ptr(gt))
         assert n >= 0
         return out[:n].copy(), gt
 
@@ -41,7 +44,7 @@ class Oracle:
     """One stateful pipeline (scanRegistration + laserOdometry + laserMapping restated)."""
 
     def __init__(self, n_scans=64, min_range=5.0, line_res=0.4, plane_res=0.8, outer=10, lm_iters=4, huber=0.1, kdtree=True,
-                 reference_build=False):
+                 reference_build=False, distortion=0):
         path = os.path.join(ROOT, "oracle", "_ref", "liblvo_oracle_ref.so") if reference_build else os.path.join(ROOT, "oracle", "liblvo_oracle.so")
         self.lib = L = C.CDLL(path)
         L.lvo_oracle_create.restype = C.c_void_p
@@ -67,6 +70,13 @@ class Oracle:
         L.lvo_oracle_knn.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
         L.lvo_oracle_eval_factor.argtypes = [C.c_void_p] * 4
         L.lvo_oracle_solve.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int]
+        L.lvo_oracle_eval_factor_s.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.lvo_oracle_transform.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.lvo_oracle_set_distortion.argtypes = [C.c_void_p, C.c_int]
+        L.lvo_oracle_odometry_last.restype = C.c_long
+        L.lvo_oracle_odometry_last.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_long]
+        L.lvo_oracle_map_cloud.restype = C.c_long
+        L.lvo_oracle_map_cloud.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_long]
         L.lvo_oracle_atanf.restype = C.c_float
         L.lvo_oracle_atanf.argtypes = [C.c_float]
         L.lvo_oracle_atan2f.restype = C.c_float
@@ -77,6 +87,8 @@ class Oracle:
         L.lvo_oracle_plane_fit5.argtypes = [C.c_void_p] * 2
         self.outer = outer
         self.h = L.lvo_oracle_create(n_scans, min_range, line_res, plane_res, outer, lm_iters, huber, 1 if kdtree else 0)
+        if distortion:
+            L.lvo_oracle_set_distortion(self.h, distortion)
 
     def __del__(self):
         try:
@@ -161,6 +173,37 @@ class Oracle:
         poses = np.zeros(14)
         st = self.lib.lvo_oracle_step(self.h, _ptr(pts), len(pts), _ptr(poses), int(keep_log))
         return st, poses[:7].copy(), poses[7:].copy()
+
+    def odometry_last(self, which):
+        """The "last" clouds after the frame (what laserOdometry.cpp:646-656 publishes): 0 corner, 1 surf, 2 full (distortion 2)."""
+        n = self.lib.lvo_oracle_odometry_last(self.h, which, None, 0)
+        a = np.empty((n, 4), np.float32)
+        if n:
+            self.lib.lvo_oracle_odometry_last(self.h, which, _ptr(a), n)
+        return a
+
+    def map_cloud(self, which):
+        """0: surround cloud (laserMapping.cpp:806-815), 1: whole map (:823-836)."""
+        n = self.lib.lvo_oracle_map_cloud(self.h, which, None, 0)
+        a = np.empty((n, 4), np.float32)
+        if n:
+            self.lib.lvo_oracle_map_cloud(self.h, which, _ptr(a), n)
+        return a
+
+    def transform(self, pts, qt7, distortion, to_end=False):
+        pts = as_pts(pts)
+        qt7 = np.ascontiguousarray(qt7, np.float64)
+        out = np.empty_like(pts)
+        self.lib.lvo_oracle_transform(_ptr(pts), len(pts), _ptr(qt7), distortion, int(to_end), _ptr(out))
+        return out
+
+    def eval_factor_s(self, f14, s, x7):
+        f14 = np.ascontiguousarray(f14, np.float64)
+        x7 = np.ascontiguousarray(x7, np.float64)
+        r = np.zeros(3)
+        J = np.zeros(18)
+        k = self.lib.lvo_oracle_eval_factor_s(_ptr(f14), float(s), _ptr(x7), _ptr(r), _ptr(J))
+        return r[:k].copy(), J[:k * 6].reshape(k, 6).copy()
 
     def timings(self):
         t = np.zeros(3)

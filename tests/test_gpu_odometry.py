@@ -16,13 +16,13 @@ def rot_err(qa, qb):
     return 2 * np.arccos(min(1.0, d))
 
 
-def _run(lvo_mod, synth, model, cfg, nframes, seq):
+def _run(lvo_mod, synth, model, cfg, nframes, seq, distortion=0):
     L = lvo_mod
-    O = Oracle(*cfg)
-    lvo = L.Lvo(n_scans=cfg[0], minimum_range=cfg[1], line_res=cfg[2], plane_res=cfg[3])
+    O = Oracle(*cfg, distortion=distortion)
+    lvo = L.Lvo(n_scans=cfg[0], minimum_range=cfg[1], line_res=cfg[2], plane_res=cfg[3], distortion=distortion)
     flips_total = rows_total = 0
     for k in range(nframes):
-        pts, _ = synth.sweep(model, seq, k)
+        pts, _ = synth.sweep(model, seq, k, moving=distortion != 0)
         f = O.extract(pts)
         st_o, rel_o, w_o = O.odometry(f["sharp"], f["less_sharp"], f["flat"], f["less_flat"])
         st_g, rel_g, w_g = lvo.scan_to_scan(f["sharp"], f["less_sharp"], f["flat"], f["less_flat"])
@@ -61,6 +61,13 @@ def test_hdl64_scan_to_scan(lvo_mod, synth):
 
 def test_vlp16_scan_to_scan(lvo_mod, synth):
     _run(lvo_mod, synth, 16, (16, 0.3, 0.2, 0.4), 6, 1)
+
+
+@pytest.mark.parametrize("model,cfg,seq", [(64, (64, 5.0, 0.4, 0.8), 3), (16, (16, 0.3, 0.2, 0.4), 2)])
+def test_scan_to_scan_distortion_1(lvo_mod, synth, model, cfg, seq):
+    """DISTORTION 1 (laserOdometry.cpp:67): per-point interpolation ratio in TransformToStart (:157-163) and in the factors
+    (:455-459, :549-553; lidarFactor.hpp:27-30, 79-82), on sweeps cast from a moving sensor."""
+    _run(lvo_mod, synth, model, cfg, 6, seq, distortion=1)
 
 
 def test_few_correspondences_warning(lvo_mod, synth):
