@@ -338,6 +338,7 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
   LVO_TRY(dalloc(c, &ex.slot_cnt, nsec * 3));
   LVO_TRY(dalloc(c, &ex.lf_ring, (size_t)L * P)); LVO_TRY(dalloc(c, &ex.lf_cnt, (size_t)L * LVO_MAX_RINGS));
   LVO_TRY(dalloc(c, &ex.sort_scratch, (size_t)L * 2 * P, false));
+  LVO_TRY(dalloc(c, &ex.ring_done, (size_t)L * LVO_MAX_RINGS));
   LVO_TRY(dalloc(c, &ex.sharp, (size_t)L * c->cap_sharp)); LVO_TRY(dalloc(c, &ex.less_sharp, (size_t)L * c->cap_lsharp));
   LVO_TRY(dalloc(c, &ex.flat, (size_t)L * c->cap_flat)); LVO_TRY(dalloc(c, &ex.less_flat, (size_t)L * P));
   ex.cap_sharp = c->cap_sharp; ex.cap_lsharp = c->cap_lsharp; ex.cap_flat = c->cap_flat;

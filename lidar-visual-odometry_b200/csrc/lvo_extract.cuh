@@ -7,8 +7,9 @@
 //   k_ring_offsets  per-ring exclusive offsets, scanStartInd/scanEndInd :246-252               (A4)
 //   k_ring_scatter  :238-240 relTime/intensity + stable counting sort by ring                  (A3, A4)
 //   k_curvature     :256-266 11-tap curvature, plus the neighbour gap flags of :319-342         (A5)
-//   k_sector_pick   one CTA per ring: :277-399 sector sort + greedy sharp/flat picking, :392-407 less-flat
-//                   gather and the per-ring 0.2 m voxel filter (block bitonic sorts in shared memory) (A6-A10)
+//   k_sector_pick_fast / k_sector_pick   one CTA per ring: :277-399 sector sort + greedy sharp/flat picking, :392-407 less-flat
+//                   gather and the per-ring 0.2 m voxel filter.  Fast kernel: register / warp-shuffle bitonic sorts, picks out of
+//                   shared memory; generic kernel (block bitonic sorts in shared memory) for oversize rings       (A6-A10)
 //   k_feature_compact  concatenation of the per-sector / per-ring results in reference order   (A7-A9)
 //
 // Exactness: this TU is compiled with -fmad=false, every float expression is written in the
@@ -50,6 +51,7 @@ struct ExtractArgs {
   float4* lf_ring;   // per-ring voxel-filtered less-flat, stored at ring_start[ring]
   int* lf_cnt;       // [lanes][64]
   unsigned long long* sort_scratch;  // [lanes][2P] global fallback for oversize sorts
+  int* ring_done;                    // [lanes][64] 1 = k_sector_pick_fast handled the ring
   // outputs (stride P except sharp/flat which have their own caps)
   float4* sharp; float4* less_sharp; float4* flat; float4* less_flat;
   int cap_sharp, cap_lsharp, cap_flat;
@@ -311,6 +313,348 @@ __device__ __forceinline__ void mark_neighbours(const PickedRef& picked, const u
   __syncwarp();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path of k_sector_pick: rings of at most LVO_PICK_RING_SMEM points whose sectors hold at most 512 points (every ring of a
+// 16/32/64-beam sweep at 10 Hz).  Differences to the generic kernel below, same results bit for bit:
+//   * sorts run in REGISTERS: 16 keys per thread, a warp owns 512 keys (one sector), compare-exchanges between a thread's own
+//     registers for strides < 16, warp shuffles for strides 16..256, shared memory only for strides >= 512 (the ring-wide sort of
+//     the voxel filter, up to 4096 keys over 8 warps).  No block barrier inside a sector sort;
+//   * the six sector sorts run concurrently (one warp each);
+//   * the sequential greedy picks read (curvature, index) keys, picked flags, gap flags and labels from shared memory, so one
+//     pick costs a few shared-memory round trips instead of a chain of dependent global loads.
+#define LVO_SECSORT_THREADS (32 * LVO_SECTORS)   // k_sector_sort: one warp per sector
+#define LVO_PICKW_THREADS 128                    // k_sector_pick_warp: four rings per CTA
+#define LVO_PICKF_SEC_STRIDE 544                 // 512 keys + 1 pad slot per 16 (bank-conflict-free for the 16-per-thread layout)
+#define LVO_PICKF_KEYS (4096 + 256)              // padded capacity of the block-wide sort (34 KB)
+__device__ __forceinline__ int pad16(int e) { return e + (e >> 4); }
+__device__ __forceinline__ void ce64(unsigned long long& a, unsigned long long& b, bool up) {
+  const bool sw = (a > b) == up;
+  const unsigned long long x = sw ? b : a, y = sw ? a : b;
+  a = x; b = y;
+}
+// Ascending bitonic sort of npad (power of two, <= 4096) keys; element e = warp * 512 + lane * 16 + r lives in k[r] of that
+// thread.  npad <= 512: warp-local, no barrier (warps may call it independently).  npad > 512: every thread of the block must
+// call it with the same npad; xbuf is the padded exchange buffer (LVO_PICKF_KEYS keys).
+template <bool WARP_LOCAL>
+__device__ __forceinline__ void bitonic_regs16(unsigned long long (&k)[16], int npad, unsigned long long* xbuf) {
+  const unsigned ln = threadIdx.x & 31, w = WARP_LOCAL ? 0u : (threadIdx.x >> 5);   // warp-local sorts are all ascending
+  const int ebase = (int)((w << 9) | (ln << 4));
+  const bool active = WARP_LOCAL || ebase < npad;   // warps that hold only padding keep the barriers and skip the work
+  // K = 2, 4, 8: direction depends on the register index only
+#pragma unroll
+  for (int K = 2; K <= 8; K <<= 1) {
+    if (K > npad) return;
+    if (active) {
+#pragma unroll
+      for (int J = K >> 1; J > 0; J >>= 1)
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+          if ((r & J) == 0) ce64(k[r], k[r | J], (r & K) == 0);
+    }
+  }
+  for (int K = 16; K <= npad; K <<= 1) {
+    const bool up = (ebase & K) == 0;
+    for (int J = K >> 1; J >= 512; J >>= 1) {      // partner in another warp: through shared memory
+      if (active) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) xbuf[pad16(ebase + r)] = k[r];
+      }
+      __syncthreads();
+      if (active) {
+        const bool keep_min = ((ebase & J) == 0) == up;
+        const int pb = ebase ^ J;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const unsigned long long o = xbuf[pad16(pb + r)];
+          k[r] = keep_min ? (o < k[r] ? o : k[r]) : (o > k[r] ? o : k[r]);
+        }
+      }
+      __syncthreads();
+    }
+    if (!active) continue;
+    for (int J = min(K >> 1, 256); J >= 16; J >>= 1) {   // partner in another lane
+      const int lj = J >> 4;
+      const bool keep_min = ((ln & lj) == 0) == up;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, k[r], lj);
+        k[r] = keep_min ? (o < k[r] ? o : k[r]) : (o > k[r] ? o : k[r]);
+      }
+    }
+#pragma unroll
+    for (int J = 8; J > 0; J >>= 1)                       // partner in this thread
+#pragma unroll
+      for (int r = 0; r < 16; ++r)
+        if ((r & J) == 0) ce64(k[r], k[r | J], up);
+  }
+}
+
+// ---- fast path, kernel 1 of 3: the six sector sorts of one ring, one warp each, in registers (:288) -------------------------
+// Decides whether the ring takes the fast path (ring_done) and zeroes the ring's counters for either path.
+__global__ void __launch_bounds__(LVO_SECSORT_THREADS, 4) k_sector_sort(ExtractArgs a) {
+  __shared__ unsigned long long stage[LVO_SECTORS][LVO_PICKF_SEC_STRIDE];   // per-warp transpose buffer for coalesced stores
+  const int lane = blockIdx.y, ring = blockIdx.x;
+  const LaneState& s = a.ls[lane];
+  const size_t lo = (size_t)lane * a.P;
+  const unsigned ln = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int sbase = (lane * LVO_MAX_RINGS + ring) * LVO_SECTORS;
+  const int S = s.scan_start[ring], E = s.scan_end[ring];
+  if (threadIdx.x == 0) a.lf_cnt[lane * LVO_MAX_RINGS + ring] = 0;
+  if (threadIdx.x < LVO_SECTORS * 3) a.slot_cnt[sbase * 3 + threadIdx.x] = 0;
+  const int RL = (E + 6) - (S - 5) + 1;          // the ring occupies [S - 5, E + 6]
+  const int mmax = (E - S + 5) / 6 + 1;
+  const bool mine = E - S < 6 || (RL <= LVO_PICK_RING_SMEM && mmax <= 512);
+  if (threadIdx.x == 0) a.ring_done[lane * LVO_MAX_RINGS + ring] = mine ? 1 : 0;
+  if (!mine || E - S < 6) return;                // :279-280, or left to the generic kernel
+  const float* curv = a.curv + lo;
+  const int sp = S + (E - S) * (int)w / 6, ep = S + (E - S) * ((int)w + 1) / 6 - 1;   // :284-285
+  const int m = ep - sp + 1;
+  unsigned long long k[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int u = (int)ln * 16 + r;
+    k[r] = u < m ? (((unsigned long long)__float_as_uint(curv[sp + u]) << 32) | (unsigned)(sp + u)) : ~0ull;  // curvature >= 0: bit order == value order
+  }
+  bitonic_regs16<true>(k, 512, nullptr);
+#pragma unroll
+  for (int r = 0; r < 16; ++r) stage[w][pad16((int)ln * 16 + r)] = k[r];
+  __syncwarp();
+  unsigned long long* keys = a.sort_scratch + (size_t)lane * 2 * a.P;   // sorted (curvature, index) keys at the positions of cloudSortInd
+  for (int u = (int)ln; u < m; u += 32) {
+    const unsigned long long v = stage[w][pad16(u)];
+    keys[sp + u] = v;
+    a.sort_ind[lo + sp + u] = (int)(unsigned)(v & 0xffffffffull);         // cloudSortInd (parity probe)
+  }
+}
+
+// ---- fast path, kernel 2 of 3: the greedy picks of :291-390, ONE WARP per ring ----------------------------------------------------
+// The picks of a ring are sequential by definition (every pick suppresses its neighbours, :317-342); the parallelism is across
+// rings and lanes.  cloudNeighborPicked and the gap flags of the ring live in shared memory as bit masks (1 KB per warp), 32
+// candidates are examined per step, and no block barrier is involved, so an SM keeps up to 48 rings in flight.
+__device__ __forceinline__ void bits_set_range(volatile unsigned* bits, int lo_i, int hi_i) {   // set bits lo_i..hi_i (inclusive, at most 5)
+  if (hi_i < lo_i) return;
+  const int w0 = lo_i >> 5, w1 = hi_i >> 5;
+  const unsigned m_lo = 0xffffffffu << (lo_i & 31), m_hi = 0xffffffffu >> (31 - (hi_i & 31));
+  if (w0 == w1) bits[w0] |= (m_lo & m_hi);
+  else { bits[w0] |= m_lo; bits[w1] |= m_hi; }
+}
+__global__ void __launch_bounds__(LVO_PICKW_THREADS) k_sector_pick_warp(ExtractArgs a) {
+  __shared__ unsigned s_bits[LVO_PICKW_THREADS / 32][2][LVO_PICK_RING_SMEM / 32 + 1];   // [warp][picked | gap][word] (+1: the 10-bit gap window reads two words)
+  const int lane = blockIdx.y;
+  const unsigned ln = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int ring = blockIdx.x * (LVO_PICKW_THREADS / 32) + (int)w;
+  if (ring >= a.n_scans) return;
+  const LaneState& s = a.ls[lane];
+  const int S = s.scan_start[ring], E = s.scan_end[ring];
+  if (E - S < 6 || !a.ring_done[lane * LVO_MAX_RINGS + ring]) return;
+  const size_t lo = (size_t)lane * a.P;
+  const int sbase = (lane * LVO_MAX_RINGS + ring) * LVO_SECTORS;
+  const int R0 = S - 5, RL = (E + 6) - R0 + 1;
+  volatile unsigned* pk = s_bits[w][0];
+  unsigned* gap = s_bits[w][1];
+  for (int base = 0; base < RL; base += 32) {
+    const int t = base + (int)ln;
+    const unsigned g = __ballot_sync(0xffffffffu, t < RL && a.gapbig[lo + R0 + t] != 0);
+    if (ln == 0) { gap[base >> 5] = g; pk[base >> 5] = 0u; }
+  }
+  __syncwarp();
+  const unsigned long long* keys = a.sort_scratch + (size_t)lane * 2 * a.P;
+  int* label = a.label + lo;
+  // marks of :319-342 / :365-388 around `ind` (relative index i = ind - R0): forward l = 1..5 until the gap between ind+l-1 and
+  // ind+l is big, backward l = -1..-5 until the gap between ind+l and ind+l+1 is big.  Executed by lane 0.
+  auto mark = [&](int i) {
+    // bits i-5 .. i+4 of the gap mask -> 10-bit window (bit 5 + x <-> gap[i + x])
+    const int b0 = i - 5;
+    const unsigned long long two = ((unsigned long long)gap[(b0 >> 5) + 1] << 32) | gap[b0 >> 5];
+    const unsigned win = (unsigned)(two >> (b0 & 31)) & 0x3ffu;
+    const unsigned fw = win >> 5;                    // bit x: gap[i + x], x = 0..4  (gap between i+x and i+x+1)
+    const unsigned bw = __brev(win & 0x1fu) >> 27;   // bit x: gap[i - 1 - x], x = 0..4
+    const int stopf = fw ? (__ffs(fw) - 1) : 5, stopb = bw ? (__ffs(bw) - 1) : 5;
+    bits_set_range(pk, i + 1, i + stopf);
+    bits_set_range(pk, i - stopb, i - 1);
+  };
+  for (int j = 0; j < LVO_SECTORS; ++j) {
+    const int sp = S + (E - S) * j / 6;            // :284
+    const int ep = S + (E - S) * (j + 1) / 6 - 1;  // :285
+    int nsharp = 0, nls = 0, largest = 0;
+    int pos = ep;
+    while (pos >= sp) {  // :292-344, k = ep .. sp
+      const int k = pos - (int)ln;
+      const bool valid = k >= sp;
+      const unsigned long long key = valid ? __ldg(keys + k) : 0ull;
+      const int ind = (int)(unsigned)(key & 0xffffffffull);
+      const float c = __uint_as_float((unsigned)(key >> 32));
+      const bool big = valid && ((double)c > 0.1);
+      const bool ok = big && ((pk[(ind - R0) >> 5] >> ((ind - R0) & 31)) & 1u) == 0;
+      const unsigned bo = __ballot_sync(0xffffffffu, ok);
+      if (bo == 0) {
+        if (__ballot_sync(0xffffffffu, valid && !big)) break;  // sorted: nothing further can exceed 0.1
+        pos -= 32;
+        continue;
+      }
+      const int first = __ffs(bo) - 1;
+      const int sel = __shfl_sync(0xffffffffu, ind, first);
+      largest++;
+      if (largest <= 2) {
+        if (ln == 0) { label[sel] = 2; a.slot_sharp[sbase * 2 + j * 2 + nsharp] = sel; a.slot_lsharp[sbase * 20 + j * 20 + nls] = sel; }
+        nsharp++; nls++;
+      } else if (largest <= 20) {
+        if (ln == 0) { label[sel] = 1; a.slot_lsharp[sbase * 20 + j * 20 + nls] = sel; }
+        nls++;
+      } else {
+        break;
+      }
+      if (ln == 0) { bits_set_range(pk, sel - R0, sel - R0); mark(sel - R0); }
+      __syncwarp();
+      pos = pos - first - 1;
+    }
+    int nflat = 0;
+    pos = sp;
+    while (pos <= ep) {  // :347-390, k = sp .. ep
+      const int k = pos + (int)ln;
+      const bool valid = k <= ep;
+      const unsigned long long key = valid ? __ldg(keys + k) : 0ull;
+      const int ind = (int)(unsigned)(key & 0xffffffffull);
+      const float c = __uint_as_float((unsigned)(key >> 32));
+      const bool small = valid && ((double)c < 0.1);
+      const bool ok = small && ((pk[(ind - R0) >> 5] >> ((ind - R0) & 31)) & 1u) == 0;
+      const unsigned bo = __ballot_sync(0xffffffffu, ok);
+      if (bo == 0) {
+        if (__ballot_sync(0xffffffffu, valid && !small)) break;
+        pos += 32;
+        continue;
+      }
+      const int first = __ffs(bo) - 1;
+      const int sel = __shfl_sync(0xffffffffu, ind, first);
+      if (ln == 0) { label[sel] = -1; a.slot_flat[sbase * 4 + j * 4 + nflat] = sel; }
+      nflat++;
+      if (nflat >= 4) break;  // :359-362 before the marking
+      if (ln == 0) { bits_set_range(pk, sel - R0, sel - R0); mark(sel - R0); }
+      __syncwarp();
+      pos = pos + first + 1;
+    }
+    if (ln == 0) { a.slot_cnt[(sbase + j) * 3 + 0] = nsharp; a.slot_cnt[(sbase + j) * 3 + 1] = nls; a.slot_cnt[(sbase + j) * 3 + 2] = nflat; }
+    __syncwarp();
+  }
+  for (int t = (int)ln; t < RL; t += 32)   // cloudNeighborPicked (parity probe; zeroed by k_curvature)
+    if ((pk[t >> 5] >> (t & 31)) & 1u) a.picked[lo + R0 + t] = 1;
+}
+
+// ---- fast path, kernel 3 of 3: :392-398 less-flat candidates (label <= 0, index order) and :401-407 VoxelGrid(0.2) of one ring -----
+// NT threads x 16 keys: NT = 128 takes the rings with at most 2048 candidates, NT = 256 those with 2049..4096.
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 128 ? 5 : 3) k_lessflat_voxel(ExtractArgs a) {
+  extern __shared__ unsigned long long skeys[];  // NT * 17 keys (padded)
+  __shared__ float s_red[6][NT / 32];
+  __shared__ int s_i[2];
+  __shared__ unsigned s_scan[33];
+  const int lane = blockIdx.y, ring = blockIdx.x;
+  const LaneState& s = a.ls[lane];
+  const int S = s.scan_start[ring], E = s.scan_end[ring];
+  if (E - S < 6 || !a.ring_done[lane * LVO_MAX_RINGS + ring]) return;
+  if (NT == 256 && E - S <= 2048) return;       // candidates come from [S, E - 1]: at most 2048 of them, the other instantiation's ring
+  const size_t lo = (size_t)lane * a.P;
+  const float4* P = a.full + lo;
+  const int* label = a.label + lo;
+  const unsigned ln = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  int cnt = 0;
+  for (int k = S + threadIdx.x; k <= E - 1; k += NT) {
+    if (label[k] <= 0) {
+      const float4 p = P[k];
+      mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+      mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+      cnt++;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    for (int o = 16; o > 0; o >>= 1) { mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o)); mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o)); }
+    if (ln == 0) { s_red[c][w] = mn[c]; s_red[3 + c][w] = mx[c]; }
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (threadIdx.x == 0) s_i[0] = 0;
+  __syncthreads();
+  if (ln == 0) atomicAdd(&s_i[0], cnt);
+  __syncthreads();
+  const int ncand = s_i[0];
+  if (ncand == 0) return;
+  if (NT == 128 ? ncand > 2048 : ncand <= 2048) return;   // the other instantiation's ring
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float a0 = s_red[c][0], b0 = s_red[3 + c][0];
+    for (int ww = 1; ww < NT / 32; ++ww) { a0 = fminf(a0, s_red[c][ww]); b0 = fmaxf(b0, s_red[3 + c][ww]); }
+    mn[c] = a0; mx[c] = b0;
+  }
+  const float inv = 1.0f / 0.2f;  // inverse_leaf_size_ for setLeafSize(0.2, 0.2, 0.2)
+  const long long ddx = (long long)((mx[0] - mn[0]) * inv) + 1, ddy = (long long)((mx[1] - mn[1]) * inv) + 1, ddz = (long long)((mx[2] - mn[2]) * inv) + 1;
+  const bool passthrough = (ddx * ddy * ddz) > (long long)INT_MAX;
+  const int min_b0 = (int)floorf(mn[0] * inv), min_b1 = (int)floorf(mn[1] * inv), min_b2 = (int)floorf(mn[2] * inv);
+  const int max_b0 = (int)floorf(mx[0] * inv), max_b1 = (int)floorf(mx[1] * inv);
+  const int div0 = max_b0 - min_b0 + 1, div1 = max_b1 - min_b1 + 1;
+  // keys (voxel idx, offset of the point inside the ring): the offset makes the sort stable and addresses the point
+  const int npad = next_pow2(ncand);
+  int carry = 0;
+  for (int base = S; base <= E - 1; base += NT) {   // stable compaction of the candidates
+    const int k = base + threadIdx.x;
+    const bool c = (k <= E - 1) && label[k] <= 0;
+    unsigned tot;
+    const unsigned ex = block_excl_scan(c ? 1u : 0u, s_scan, &tot);
+    if (c) {
+      const float4 p = P[k];
+      unsigned idx;
+      if (passthrough) idx = (unsigned)(carry + ex);
+      else {
+        const int ijk0 = (int)(floorf(p.x * inv) - (float)min_b0);
+        const int ijk1 = (int)(floorf(p.y * inv) - (float)min_b1);
+        const int ijk2 = (int)(floorf(p.z * inv) - (float)min_b2);
+        idx = (unsigned)(ijk0 + ijk1 * div0 + ijk2 * div0 * div1);
+      }
+      skeys[pad16(carry + (int)ex)] = ((unsigned long long)idx << 32) | (unsigned)(k - S);
+    }
+    carry += (int)tot;
+  }
+  __syncthreads();
+  {
+    unsigned long long k[16];
+    const int e0 = (int)threadIdx.x * 16;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) k[r] = (e0 + r < ncand) ? skeys[pad16(e0 + r)] : ~0ull;
+    __syncthreads();
+    bitonic_regs16<false>(k, npad, skeys);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) if (e0 + r < npad) skeys[pad16(e0 + r)] = k[r];
+    __syncthreads();
+  }
+  // one centroid per run of equal voxel idx, accumulated in sorted order (float, as PCL's CentroidPoint)
+  float4* out = a.lf_ring + lo + s.ring_start[ring];
+  carry = 0;
+  for (int base = 0; base < ncand; base += NT) {
+    const int t = base + threadIdx.x;
+    bool head = false;
+    if (t < ncand) head = (t == 0) || ((skeys[pad16(t)] >> 32) != (skeys[pad16(t - 1)] >> 32));
+    unsigned tot;
+    const unsigned ex = block_excl_scan(head ? 1u : 0u, s_scan, &tot);
+    if (head) {
+      const unsigned long long v = skeys[pad16(t)] >> 32;
+      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+      int u = t;
+      for (; u < ncand; ++u) {
+        const unsigned long long ku = skeys[pad16(u)];
+        if ((ku >> 32) != v) break;
+        const float4 p = P[S + (int)(unsigned)(ku & 0xffffffffull)];
+        sx += p.x; sy += p.y; sz += p.z; si += p.w;
+      }
+      const float c = (float)(u - t);
+      out[carry + ex] = make_float4(sx / c, sy / c, sz / c, si / c);
+    }
+    carry += (int)tot;
+  }
+  if (threadIdx.x == 0) a.lf_cnt[lane * LVO_MAX_RINGS + ring] = carry;
+}
+
+// Generic kernel: any ring size (block bitonic sorts in shared memory, global scratch for oversize sorts).  Runs after the fast
+// kernel and only handles the rings that one left (ring_done == 0).
 __global__ void __launch_bounds__(LVO_PICK_THREADS) k_sector_pick(ExtractArgs a) {
   extern __shared__ unsigned long long skeys[];  // LVO_PICK_SMEM_KEYS
   __shared__ float s_red[6][LVO_PICK_THREADS / 32];
@@ -329,6 +673,7 @@ __global__ void __launch_bounds__(LVO_PICK_THREADS) k_sector_pick(ExtractArgs a)
   const unsigned ln = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int sbase = (lane * LVO_MAX_RINGS + ring) * LVO_SECTORS;
   const int S = s.scan_start[ring], E = s.scan_end[ring];
+  if (a.ring_done[lane * LVO_MAX_RINGS + ring]) return;   // handled by k_sector_pick_fast
   if (threadIdx.x == 0) a.lf_cnt[lane * LVO_MAX_RINGS + ring] = 0;
   if (threadIdx.x < LVO_SECTORS * 3) a.slot_cnt[sbase * 3 + threadIdx.x] = 0;
   if (E - S < 6) return;  // :279-280
@@ -583,7 +928,11 @@ static inline void lvo_launch_extract(cudaStream_t st, const ExtractArgs& a, int
   k_ring_offsets<<<lanes, LVO_MAX_RINGS, 0, st>>>(a);
   k_ring_scatter<<<gpts, LVO_EX_THREADS, 0, st>>>(a);
   k_curvature<<<gpts, LVO_EX_THREADS, 0, st>>>(a);
+  k_sector_sort<<<dim3(a.n_scans, lanes), LVO_SECSORT_THREADS, 0, st>>>(a);
+  k_sector_pick_warp<<<dim3(lvo_div_up(a.n_scans, LVO_PICKW_THREADS / 32), lanes), LVO_PICKW_THREADS, 0, st>>>(a);
+  k_lessflat_voxel<128><<<dim3(a.n_scans, lanes), 128, 128 * 17 * sizeof(unsigned long long), st>>>(a);
+  k_lessflat_voxel<256><<<dim3(a.n_scans, lanes), 256, 256 * 17 * sizeof(unsigned long long), st>>>(a);
   k_sector_pick<<<dim3(a.n_scans, lanes), LVO_PICK_THREADS, LVO_PICK_SMEM_KEYS * sizeof(unsigned long long), st>>>(a);
   k_feature_compact<<<lanes, 512, 0, st>>>(a);
-  if (launches) *launches += 8;
+  if (launches) *launches += 12;
 }
