@@ -21,6 +21,7 @@
 struct OdoArgs {
   LaneState* ls;
   int lanes, outer;
+  int lane0;         // first lane of an association launch (chunked outer loop, see lvo_launch_odometry)
   int distortion;    // 0 | 1 | 2, see the header comment
   // current features (stride caps)
   const float4* sharp; float4* less_sharp; const float4* flat; float4* less_flat;
@@ -223,7 +224,7 @@ __device__ __forceinline__ void scan_range4(const float4* __restrict__ pts, unsi
 
 __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
   __shared__ GridView gv[4];
-  const int lane = blockIdx.y;
+  const int lane = a.lane0 + blockIdx.y;
   LaneState& s = a.ls[lane];
   if (!s.odo_inited) return;
   if (threadIdx.x < 4) gv[threadIdx.x] = grid_view(a.grid, 8 * lane + threadIdx.x);
@@ -269,7 +270,8 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
         const int z = z0 + k / 3, y = y0 + k % 3;
         if (z <= z1 && y <= y1) row_bounds(g, z, y, x0, x1, rb[k], re[k]);
       }
-#pragma unroll
+      // one copy of the scan body (the kernel is instruction-fetch bound when these loops are unrolled: 129 KB of SASS)
+#pragma unroll 1
       for (int k = 0; k < 9; ++k) scan_range4(g.pts, rb[k], re[k], near);
       closest = id;
       pj = C[closest];
@@ -291,76 +293,67 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
       seed(pB, false, bB);
       const float rho = sqrtf(sel.x * sel.x + sel.y * sel.y);
       const int bq = az_bucket(sel.x, sel.y);
-      auto scan_windows = [&](int hA, int hB, int skipA, int skipB) {   // buckets with |offset| <= skip were scanned before
-        unsigned wb[10], we[10];   // (ring slot, side) -> part 0 of the bucket range; fetched together before any candidate
+      int dr_cur = 0;
+      auto cand = [&](float4 p) {
+        const int idx = __float_as_int(p.w);
+        if (idx == closest) return;
+        if ((idx > closest && dr_cur < 0) || (idx < closest && dr_cur > 0)) return;
+        const float dd = (p.x - sel.x) * (p.x - sel.x) + (p.y - sel.y) * (p.y - sel.y) + (p.z - sel.z) * (p.z - sel.z);
+        if (!(dd < 25.0f)) return;
+        const Best c{dd, idx > closest ? (idx - closest) : ((closest - idx) + (1 << 30)), idx};
+        if (dr_cur == 0) bA = best_min(bA, c); else bB = best_min(bB, c);
+      };
+      // window k = (ring slot r = k >> 1 <-> ring cid - 2 + r, side = k & 1); buckets with |offset| <= skip were scanned before
+      auto window = [&](int k, int hA, int hB, int skipA, int skipB, int& lo, int& hi) -> bool {
+        const int r = k >> 1, side = k & 1, ring = cid - 2 + r;
+        if (ring < 0 || ring >= LVO_AZ_RINGS || (r == 2 && corner)) return false;
+        const int h = r == 2 ? hA : hB, skip = r == 2 ? skipA : skipB;
+        if (h <= skip) return false;
+        if (skip < 0) { if (side) return false; lo = bq - h; hi = bq + h; }
+        else if (side == 0) { lo = bq - h; hi = bq - skip - 1; }
+        else { lo = bq + skip + 1; hi = bq + h; }
+        return true;
+      };
+      int sA = -1, sB = -1;   // half-widths already scanned
+      const bool first_needed = (!corner && bA.j < 0) || bB.j < 0;   // no seed for some target: first look at +-2 buckets
+#pragma unroll 1
+      for (int pass = first_needed ? 0 : 1; pass < 2; ++pass) {
+        int hA, hB, skipA, skipB;
+        if (pass == 0) {
+          const int wA = (!corner && bA.j < 0) ? 2 : -1, wB = bB.j < 0 ? 2 : -1;
+          hA = wA < 0 ? 0 : wA; hB = wB < 0 ? 0 : wB; skipA = wA < 0 ? 0 : -1; skipB = wB < 0 ? 0 : -1;
+          if (wA >= 0) sA = wA;
+          if (wB >= 0) sB = wB;
+        } else {
+          hA = corner ? 0 : (bA.j >= 0 ? az_halfwidth(bA.d, rho) : LVO_AZ_BUCKETS);
+          hB = bB.j >= 0 ? az_halfwidth(bB.d, rho) : LVO_AZ_BUCKETS;
+          if (hA > 6 || hB > 6) { fast = false; break; }   // a target has no candidate nearby or its window is wide: leave it to the cooperative kernel
+          skipA = corner ? hA : sA; skipB = sB;
+        }
+        unsigned wb[10], we[10];   // part 0 of every bucket range; fetched together before any candidate
 #pragma unroll
         for (int k = 0; k < 10; ++k) {
           wb[k] = we[k] = 0;
-          const int r = k >> 1, side = k & 1, ring = cid - 2 + r;
-          if (ring < 0 || ring >= LVO_AZ_RINGS || (r == 2 && corner)) continue;
-          const int h = r == 2 ? hA : hB, skip = r == 2 ? skipA : skipB;
-          if (h <= skip) continue;
           int lo, hi;
-          if (skip < 0) { if (side) continue; lo = bq - h; hi = bq + h; }
-          else if (side == 0) { lo = bq - h; hi = bq - skip - 1; }
-          else { lo = bq + skip + 1; hi = bq + h; }
-          az_bounds(gaz, ring, lo, hi, 0, wb[k], we[k]);
+          if (window(k, hA, hB, skipA, skipB, lo, hi)) az_bounds(gaz, cid - 2 + (k >> 1), lo, hi, 0, wb[k], we[k]);
         }
-#pragma unroll
-        for (int k = 0; k < 10; ++k) {
-          const int dr = (k >> 1) - 2;
-          auto cand = [&](float4 p) {
-            const int idx = __float_as_int(p.w);
-            if (idx == closest) return;
-            if ((idx > closest && dr < 0) || (idx < closest && dr > 0)) return;
-            const float dd = (p.x - sel.x) * (p.x - sel.x) + (p.y - sel.y) * (p.y - sel.y) + (p.z - sel.z) * (p.z - sel.z);
-            if (!(dd < 25.0f)) return;
-            const Best c{dd, idx > closest ? (idx - closest) : ((closest - idx) + (1 << 30)), idx};
-            if (dr == 0) bA = best_min(bA, c); else bB = best_min(bB, c);
-          };
-          scan_range4(gaz.pts, wb[k], we[k], cand);
-        }
+#pragma unroll 1
+        for (int k = 0; k < 10; ++k) { dr_cur = (k >> 1) - 2; scan_range4(gaz.pts, wb[k], we[k], cand); }
         // wrapped windows (the range crosses bucket 0): second part, rare
         const int hmax = max(hA, hB);
         if (bq - hmax < 0 || bq + hmax >= LVO_AZ_BUCKETS) {
+#pragma unroll 1
           for (int k = 0; k < 10; ++k) {
-            const int r = k >> 1, side = k & 1, ring = cid - 2 + r, dr = r - 2;
-            if (ring < 0 || ring >= LVO_AZ_RINGS || (r == 2 && corner)) continue;
-            const int h = r == 2 ? hA : hB, skip = r == 2 ? skipA : skipB;
-            if (h <= skip) continue;
             int lo, hi;
-            if (skip < 0) { if (side) continue; lo = bq - h; hi = bq + h; }
-            else if (side == 0) { lo = bq - h; hi = bq - skip - 1; }
-            else { lo = bq + skip + 1; hi = bq + h; }
+            if (!window(k, hA, hB, skipA, skipB, lo, hi)) continue;
             unsigned b, e;
-            az_bounds(gaz, ring, lo, hi, 1, b, e);
-            auto cand = [&](float4 p) {
-              const int idx = __float_as_int(p.w);
-              if (idx == closest) return;
-              if ((idx > closest && dr < 0) || (idx < closest && dr > 0)) return;
-              const float dd = (p.x - sel.x) * (p.x - sel.x) + (p.y - sel.y) * (p.y - sel.y) + (p.z - sel.z) * (p.z - sel.z);
-              if (!(dd < 25.0f)) return;
-              const Best c{dd, idx > closest ? (idx - closest) : ((closest - idx) + (1 << 30)), idx};
-              if (dr == 0) bA = best_min(bA, c); else bB = best_min(bB, c);
-            };
+            az_bounds(gaz, cid - 2 + (k >> 1), lo, hi, 1, b, e);
+            dr_cur = (k >> 1) - 2;
             scan_range4(gaz.pts, b, e, cand);
           }
         }
-      };
-      int sA = -1, sB = -1;   // half-widths already scanned
-      if ((!corner && bA.j < 0) || bB.j < 0) {   // no seed for some target: first look at +-2 buckets
-        const int wA = (!corner && bA.j < 0) ? 2 : -1, wB = bB.j < 0 ? 2 : -1;
-        scan_windows(wA < 0 ? 0 : wA, wB < 0 ? 0 : wB, wA < 0 ? 0 : -1, wB < 0 ? 0 : -1);
-        if (wA >= 0) sA = wA;
-        if (wB >= 0) sB = wB;
       }
-      const int hA = corner ? 0 : (bA.j >= 0 ? az_halfwidth(bA.d, rho) : LVO_AZ_BUCKETS);
-      const int hB = bB.j >= 0 ? az_halfwidth(bB.d, rho) : LVO_AZ_BUCKETS;
-      if (hA > 6 || hB > 6) fast = false;   // a target has no candidate nearby or its window is wide: leave it to the cooperative kernel
-      if (fast) {
-        scan_windows(hA, hB, corner ? hA : sA, sB);
-        same = bA.j; other = bB.j;
-      }
+      if (fast) { same = bA.j; other = bB.j; }
     }
     if (fast) {
       const int type = odo_emit(a, lane, f, ns, corner, true, pt, C, closest, pj, same, other);
@@ -379,7 +372,7 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
 template <int TW>
 __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
   __shared__ GridView gv[8];
-  const int lane = blockIdx.y;
+  const int lane = a.lane0 + blockIdx.y;
   LaneState& s = a.ls[lane];
   if (!s.odo_inited) return;
   if (threadIdx.x < 8) gv[threadIdx.x] = grid_view(a.grid, 8 * lane + threadIdx.x);
@@ -576,25 +569,40 @@ __global__ void k_odo_swap(OdoArgs a) {
   }
 }
 
+// lanes per chunk of the scan-to-scan outer loop; LVO_ODO_CHUNK overrides (tuning aid)
+static inline int lvo_odo_chunk(int lanes) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("LVO_ODO_CHUNK"); env = e ? atoi(e) : 0; }
+  if (env > 0) return env;
+  return lanes;
+}
 static inline void lvo_launch_odometry(cudaStream_t st, OdoArgs a, const SolveArgs& solve_proto, int outer_iters, int lanes, long long* launches) {
   k_odo_begin<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a);
   if (launches) *launches += 1;
   const int nfeat_cap = a.cap_sharp + a.cap_flat;
-  dim3 ga(max(1, lvo_div_up(nfeat_cap * 8, 256)), lanes);          // 8-lane tiles, every feature (outer iteration 0)
-  dim3 gs(max(1, lvo_div_up(nfeat_cap * 32 / 8, 256)), lanes);     // full-warp tiles for the slow list (an eighth of the features per pass, grid-strided)
-  dim3 gf(max(1, lvo_div_up(nfeat_cap, 128)), lanes);
-  for (int o = 0; o < outer_iters; ++o) {
-    a.outer = o;
-    cudaMemsetAsync(a.slow_cnt, 0, sizeof(int) * lanes, st);
-    k_odo_assoc_fast<<<gf, 128, 0, st>>>(a);
-    if (launches) *launches += 1;
-    if (o == 0) k_odo_assoc<8><<<ga, 256, 0, st>>>(a);   // first iteration: more features lack a nearby candidate
-    else k_odo_assoc<32><<<gs, 256, 0, st>>>(a);
-    SolveArgs sa = solve_proto;
-    sa.which = 0; sa.outer = o; sa.factors = a.factors; sa.factor_cap = a.factor_cap; sa.distort = a.distortion != 0;
-    lvo_launch_lm(st, sa, lanes, nfeat_cap);
-    if (launches) *launches += 2;
+  // The outer loop runs chunk by chunk of lanes: the ten association passes of a lane read the same two grids of its previous
+  // sweep (~1.4 MB per lane), so a chunk whose grids fit the 126 MB L2 pays DRAM for them once instead of ten times.
+  const int chunk = lvo_odo_chunk(lanes);
+  for (int l0 = 0; l0 < lanes; l0 += chunk) {
+    const int nl = min(chunk, lanes - l0);
+    a.lane0 = l0;
+    dim3 ga(max(1, lvo_div_up(nfeat_cap * 8, 256)), nl);          // 8-lane tiles, every feature (outer iteration 0)
+    dim3 gs(max(1, lvo_div_up(nfeat_cap * 32 / 8, 256)), nl);     // full-warp tiles for the slow list (an eighth of the features per pass, grid-strided)
+    dim3 gf(max(1, lvo_div_up(nfeat_cap, 128)), nl);
+    for (int o = 0; o < outer_iters; ++o) {
+      a.outer = o;
+      cudaMemsetAsync(a.slow_cnt + l0, 0, sizeof(int) * nl, st);
+      k_odo_assoc_fast<<<gf, 128, 0, st>>>(a);
+      if (launches) *launches += 1;
+      if (o == 0) k_odo_assoc<8><<<ga, 256, 0, st>>>(a);   // first iteration: more features lack a nearby candidate
+      else k_odo_assoc<32><<<gs, 256, 0, st>>>(a);
+      SolveArgs sa = solve_proto;
+      sa.which = 0; sa.outer = o; sa.factors = a.factors; sa.factor_cap = a.factor_cap; sa.distort = a.distortion != 0; sa.lane0 = l0;
+      lvo_launch_lm(st, sa, nl, nfeat_cap);
+      if (launches) *launches += 2;
+    }
   }
+  a.lane0 = 0;
   k_odo_integrate<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a, outer_iters);
   if (a.distortion == 2) { k_odo_to_end<<<dim3(64, lanes), 256, 0, st>>>(a); if (launches) *launches += 1; }
   k_odo_swap<<<dim3(32, lanes), 256, 0, st>>>(a);

@@ -278,6 +278,7 @@ struct SolveArgs {
   int max_iters;
   double huber;
   double* trace;              // [lanes][LVO_MAX_OUTER][LVO_MAX_LM + 1][LVO_TRACE_W] or null
+  int lane0;                  // first lane of this launch (lanes are processed in chunks, see lvo_launch_odometry)
   int distort;                // != 0: factors may carry an interpolation ratio s != 1 (scan-to-scan with DISTORTION 1)
 };
 
@@ -414,7 +415,7 @@ __global__ void __launch_bounds__(LVO_LM_THREADS, 2) k_lm_solve(SolveArgs a) {
   __shared__ LmCtl ctl;  // only thread 0 of CTA 0 touches it; shared to keep it out of its registers
   cg::cluster_group cluster = cg::this_cluster();
   const bool lead = cluster.block_rank() == 0 && threadIdx.x == 0;
-  const int lane = blockIdx.x / cluster.num_blocks();
+  const int lane = a.lane0 + blockIdx.x / cluster.num_blocks();
   LaneState& s = a.ls[lane];
   if (a.which == 0 ? (s.odo_inited == 0) : (s.map_too_small != 0)) return;
   const int nslots = a.which == 0 ? (s.n_sharp + s.n_flat) : (s.n_stack[0] + s.n_stack[1]);
