@@ -1,10 +1,12 @@
 #!/usr/bin/env python
 """bench.py — scan-to-map throughput of the B200 hot path (BASELINE.json metric) on synthetic HDL-64-shaped sweeps.
 
-A "step" advances every lane (independent sequence) of this rank's context by one sweep through the full per-frame
-path: lvo_extract_features -> lvo_scan_to_scan -> lvo_scan_to_map (device-resident chain, `lvo_step_batch_dev`).
-  value : scans/s, whole job (all ranks, all lanes), inputs already resident in HBM, timed with CUDA events on the
-          launching stream, one event pair per step with an L2 flush between steps, max over ranks.
+A "step" advances every lane (independent sequence) of this rank by one sweep through the full per-frame path:
+lvo_extract_features -> lvo_scan_to_scan -> lvo_scan_to_map (device-resident chain, `lvo_step_batch_dev`).  The lanes of a
+rank are split over `--groups` contexts, each with its own CUDA stream and host thread, so that the stages of different
+groups overlap on the GPU.
+  value : scans/s, whole job (all ranks, all lanes), inputs already resident in HBM, timed with one CUDA event pair on the
+          main stream around all K steps of all contexts (inputs larger than L2: every step reads new sweeps), max over ranks.
   e2e   : the same metric through `lvo_step_batch_pipelined` with HOST (pinned) sweep buffers: every step uploads one frame
           of sweeps (the next frame's, on a copy stream, overlapping this frame's compute) and reads the poses / lane state
           back, all inside the timed region.
@@ -279,7 +281,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("LVO_BENCH_LANES", "0")),
-                    help="independent sequences per GPU (0 = 256 when the GPU has >= 150 GB, else 128)")
+                    help="independent sequences per GPU (0 = 384 when the GPU has >= 150 GB, else 128)")
+    ap.add_argument("--groups", type=int, default=int(os.environ.get("LVO_BENCH_GROUPS", "0")),
+                    help="contexts per GPU, each with lanes/groups sequences, its own CUDA stream and host thread (0 = one per 128 lanes)")
     ap.add_argument("--ref-threads", type=int, default=0)
     ap.add_argument("--cpu-sample-frames", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -308,7 +312,11 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()   # early: nvidia-smi's start-up (NVML init takes a driver lock) must not fall into a timed region
     if args.lanes <= 0:
-        args.lanes = 256 if torch.cuda.get_device_properties(local_rank).total_memory >= 150e9 else 128
+        args.lanes = 384 if torch.cuda.get_device_properties(local_rank).total_memory >= 150e9 else 128
+    if args.groups <= 0:
+        args.groups = max(1, args.lanes // 128)
+    while args.lanes % args.groups:
+        args.groups -= 1
     L = load_pkg()
     if args.only_knn:
         print(json.dumps({"knn_throughput": knn_throughput(L, args.knn_frames, 5, local_rank)}), flush=True)
@@ -330,9 +338,14 @@ def main():
     t_gen = time.perf_counter() - t_gen
 
     stream = torch.cuda.current_stream()
-    mk = dict(n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, lanes=lanes, device=local_rank, max_points=131072, max_map_corner=1 << 18,
+    G = args.groups
+    per = lanes // G
+    mk = dict(n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, lanes=per, device=local_rank, max_points=131072, max_map_corner=1 << 18,
               max_map_surf=1 << 19)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    # One context per group of `per` lanes, each on its own CUDA stream and driven by its own host thread (include/lvo.h: a context
+    # is single-threaded, distinct contexts run concurrently — the reference's multi-sequence mechanism, SURVEY 8b "Threading").
+    # The stages of different groups overlap on the GPU (sort-bound extraction next to latency-bound association / LM).
+    gstreams = [torch.cuda.Stream(device=local_rank) for _ in range(G)]
 
     def barrier():
         torch.cuda.synchronize()
@@ -340,76 +353,107 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_run(step_fn, ctx):
-        """W warm-up steps, then K steps each bracketed by its own event pair (L2 flushed between steps)."""
-        launches, knn_ms, knn_launches, knn_bytes = 0, 0.0, 0, 0.0
-        for k in range(args.warmup):
-            step_fn(k)
+    def run_groups(fn, k0, k1, after=None):
+        """fn(g, k) for k in [k0, k1) on one host thread per group; after(g) runs on that thread at the end."""
+        errs = []
+
+        def work(g):
+            try:
+                torch.cuda.set_device(local_rank)
+                for k in range(k0, k1):
+                    fn(g, k)
+                if after:
+                    after(g)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        ths = [threading.Thread(target=work, args=(g,)) for g in range(G)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def timed_run(step_fn, ctxs):
+        """W warm-up steps, then K steps of every group inside ONE event pair on the main stream: the group streams wait for the
+        start event and the end event waits for every group's last kernel (device time of the whole region, all groups)."""
+        acc = {"launches": 0, "knn_ms": 0.0, "knn_launches": 0, "knn_bytes": 0.0}
+        lock = threading.Lock()
+
+        def timed_step(g, k):
+            step_fn(g, k)
+            t = ctxs[g].timings()
+            with lock:
+                acc["launches"] += t.kernel_launches
+                acc["knn_ms"] += t.knn_ms; acc["knn_launches"] += t.knn_launches; acc["knn_bytes"] += t.knn_bytes
+        run_groups(step_fn, 0, args.warmup)
         barrier()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        done = [torch.cuda.Event() for _ in range(G)]
         wall0 = time.perf_counter()
-        for i in range(args.steps):
-            flush.zero_()
-            evs[i][0].record(stream)
-            step_fn(args.warmup + i)
-            evs[i][1].record(stream)
-            t = ctx.timings()
-            launches += t.kernel_launches
-            knn_ms += t.knn_ms; knn_launches += t.knn_launches; knn_bytes += t.knn_bytes
+        e0.record(stream)
+        for gs in gstreams:
+            gs.wait_event(e0)
+        run_groups(timed_step, args.warmup, total, after=lambda g: done[g].record(gstreams[g]))
+        for d in done:
+            stream.wait_event(d)
+        e1.record(stream)
         barrier()
         wall = time.perf_counter() - wall0
-        ms = sum(a.elapsed_time(b) for a, b in evs)
-        return ms, wall, launches, knn_ms, knn_launches, knn_bytes
+        return e0.elapsed_time(e1), wall, acc["launches"], acc["knn_ms"], acc["knn_launches"], acc["knn_bytes"]
 
-    # ---- e2e arm: host (pinned) sweeps through lvo_step_batch ------------------------------------------------------
+    # ---- e2e arm: host (pinned) sweeps through lvo_step_batch_pipelined ------------------------------------------------
     pinned = {}
     for (s, f), a in sweeps.items():
         t = torch.from_numpy(a).pin_memory()
         pinned[(s, f)] = t
-    ctx_e = L.Lvo(**mk)
-    ctx_e.set_stream(stream.cuda_stream)
-    h2d = [0]
-
-    host_views = {}
-
-    def views_of(k):
-        if k not in host_views:
-            host_views[k] = [pinned[(s, k + o)].numpy() for s, o in plan]
-        return host_views[k]
-
-    def step_host(k):
-        # every step uploads exactly one frame of sweeps from pinned host memory: frame k+1 goes up on the copy stream
-        # while frame k computes (lvo_step_batch_pipelined), and the poses / lane state of frame k come back before it returns
-        views = views_of(k)
-        nxt = views_of(k + 1) if k + 1 < total else None
-        h2d[0] = sum(v.nbytes for v in views)
-        st, odo, mp = ctx_e.step_batch_pipelined(views, nxt)
-        assert st >= 0
-        host_views.pop(k - 1, None)
+    gplan = [plan[g * per:(g + 1) * per] for g in range(G)]
+    h2d = [0] * G
 
     if args.skip_e2e:
         ms_e, wall_e = float("nan"), float("nan")
     else:
+        ctx_e = [L.Lvo(**mk) for _ in range(G)]
+        for g in range(G):
+            ctx_e[g].set_stream(gstreams[g].cuda_stream)
+        host_views = [dict() for _ in range(G)]
+
+        def views_of(g, k):
+            if k not in host_views[g]:
+                host_views[g][k] = [pinned[(s, k + o)].numpy() for s, o in gplan[g]]
+            return host_views[g][k]
+
+        def step_host(g, k):
+            # every step uploads exactly one frame of sweeps from pinned host memory: frame k+1 goes up on the copy stream
+            # while frame k computes (lvo_step_batch_pipelined), and the poses / lane state of frame k come back before it returns
+            views = views_of(g, k)
+            nxt = views_of(g, k + 1) if k + 1 < total else None
+            h2d[g] = sum(v.nbytes for v in views)
+            st, odo, mp = ctx_e[g].step_batch_pipelined(views, nxt)
+            assert st >= 0
+            host_views[g].pop(k - 1, None)
+
         ms_e, wall_e, _, _, _, _ = timed_run(step_host, ctx_e)
-    ctx_e.close()
+        for c in ctx_e:
+            c.close()
 
     # ---- device-resident arm ------------------------------------------------------------------------------------------
     dev = {j: torch.from_numpy(a).cuda() for j, a in sweeps.items()}
-    ctx_d = L.Lvo(**mk)
-    ctx_d.set_stream(stream.cuda_stream)
-    last_pose = [None]
+    ctx_d = [L.Lvo(**mk) for _ in range(G)]
+    for g in range(G):
+        ctx_d[g].set_stream(gstreams[g].cuda_stream)
 
-    def step_dev(k):
-        ptrs = [dev[(s, k + o)].data_ptr() for s, o in plan]
-        ns = [dev[(s, k + o)].shape[0] for s, o in plan]
-        st, odo, mp = ctx_d.step_batch_dev(ptrs, ns)
+    def step_dev(g, k):
+        ptrs = [dev[(s, k + o)].data_ptr() for s, o in gplan[g]]
+        ns = [dev[(s, k + o)].shape[0] for s, o in gplan[g]]
+        st, odo, mp = ctx_d[g].step_batch_dev(ptrs, ns)
         assert st >= 0
-        last_pose[0] = mp
 
     ms_d, wall_d, launches, knn_ms, knn_launches, knn_bytes = timed_run(step_dev, ctx_d)
     clocks = sampler.stop()
-    st0 = ctx_d.stats(0)
-    ctx_d.close()
+    st0 = ctx_d[0].stats(0)
+    for c in ctx_d:
+        c.close()
 
     # max over ranks
     ms_d, ms_e = max_over_ranks([ms_d, ms_e], world)
@@ -447,16 +491,21 @@ def main():
         line = {"metric": "scan-to-map scans/sec (HDL-64 synthetic)", "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_d / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32+f64", "data": "synthetic",
-                "config": {"workload": f"HDL-64 full pipeline (extract + scan-to-scan + scan-to-map), {lanes} independent sequences per GPU in lock-step",
-                           "lanes_per_gpu": lanes, "points_per_sweep": 120000, "outer_iters": 10, "lm_iters": 4, "map_points_lane0": [st0.map_corner_from_map, st0.map_surf_from_map],
-                           "l2": "256 MB flush between timed steps; every step reads new sweeps", "timing": "CUDA events on the launching stream, one pair per step"},
-                "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": h2d[0], "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / args.steps},
+                "config": {"workload": f"HDL-64 full pipeline (extract + scan-to-scan + scan-to-map), {lanes} independent sequences per GPU "
+                                       f"in {G} contexts of {per} lanes (one CUDA stream + host thread each)",
+                           "lanes_per_gpu": lanes, "contexts_per_gpu": G, "points_per_sweep": 120000, "outer_iters": 10, "lm_iters": 4,
+                           "map_points_lane0": [st0.map_corner_from_map, st0.map_surf_from_map],
+                           "l2": f"inputs larger than L2: every step reads {lanes} new sweeps ({lanes * 1.92:.0f} MB) and rebuilds every grid; no flush",
+                           "timing": "one CUDA event pair on the main stream around all K steps of all contexts (context streams wait for the start event, "
+                                     "the end event waits for every context's last kernel)"},
+                "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": sum(h2d), "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / args.steps},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": "k_map_knn (5-NN grid search, thread per query)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak if peak else None,
                              # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full`, 128 lanes, 5th step
                              # (profiles/r1_final_hot_kernels_l128_ncu.csv); null for other lane counts
-                             "traffic": 41.0e6 if lanes == 128 else None,  # the capture was taken at 128 lanes "peak_source": peak_src, "launches": knn_launches,
+                             "traffic": 41.0e6 if per == 128 else None,  # the capture was taken with 128 lanes per context
+                             "peak_source": peak_src, "launches": knn_launches,
                              "avg_launch_us": 1e3 * knn_ms / max(knn_launches, 1), "algorithmic_bytes_per_launch": knn_bytes / max(knn_launches, 1)},
                 "knn_throughput": knn_tp, "other_configs": extras, "cpu_baseline": cpu, "clocks": clocks,
                 "host": {"wall_ms_per_step_dev": 1e3 * wall_d / args.steps, "wall_ms_per_step_e2e": 1e3 * wall_e / args.steps, "gen_s": t_gen, "cores": host_threads}}
