@@ -257,14 +257,16 @@ __device__ __forceinline__ void accumulate_factor(const LvoFactor& f, const doub
   if (s > b) { const double rr = sqrt(s); rho0 = 2 * huber * rr - b; rho1 = fmax(DBL_MIN, huber / rr); }
   else { rho0 = s; rho1 = 1.0; }
   acc[27] += 0.5 * rho0;
+  // explicit FMAs (the TU is compiled with -fmad=false for the float paths that must match the x86 reference bit for bit; these
+  // double accumulations are summed in a different order than Ceres anyway and are covered by the pose tolerance)
   for (int i = 0; i < k; ++i) {
     int t = 0;
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
       const double wa = rho1 * J[i][a];
 #pragma unroll
-      for (int c = a; c < 6; ++c) acc[t++] += wa * J[i][c];
-      acc[21 + a] += wa * r[i];
+      for (int c = a; c < 6; ++c) { acc[t] = fma(wa, J[i][c], acc[t]); ++t; }
+      acc[21 + a] = fma(wa, r[i], acc[21 + a]);
     }
   }
 }

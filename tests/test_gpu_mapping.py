@@ -163,6 +163,7 @@ def test_cube_window_shifts_match_oracle(lvo_mod, synth):
             (0, 200, 0), (0, 395, 0), (0, 520, 60), (0, 520, 130), (0, 520, 210), (0, 0, 0), (0, -400, -130), (0, -560, -260), (300, 300, 100)]
     shifted = 0
     prev_cen = [10, 10, 5]
+    exact = True   # until an optimised frame inserts points with a pose that agrees to ~1e-13 m rather than to the last bit
     for k, t in enumerate(path):
         odom = np.array([0, 0, 0, 1, t[0], t[1], t[2]], float)
         st_o, pose_o, corr_o = O.mapping(f["less_sharp"], f["less_flat"], None, odom)
@@ -180,10 +181,13 @@ def test_cube_window_shifts_match_oracle(lvo_mod, synth):
             pg, cg = lvo.map_export(0, which)
             po, co = O.map_export(which)
             assert len(pg) == len(po) and np.array_equal(cg, co), (k, which, len(pg), len(po))
-            if st_o == 3:   # no optimisation ran: identical pose -> identical floats
+            if st_o != 3:
+                exact = False
+            if exact:       # no optimisation ran so far: identical poses -> identical floats
                 assert np.array_equal(_bits(pg), _bits(po)), (k, which)
-            else:
+            else:           # same points in the same cubes and order; float noise in at most a handful of coordinates
                 assert np.abs(pg[:, :3] - po[:, :3]).max() < 1e-3
+                assert (_bits(pg) != _bits(po)).mean() < 1e-3, (k, which)
         assert (s.map_corner_total, s.map_surf_total) == (info[6], info[7])
     assert shifted >= 8   # the window really moved, in both directions on all three axes
     lvo.close()
