@@ -331,7 +331,8 @@ def main():
     # distinct data per rank: sequence ids are offset by 8 * rank
     from oracle_py import Synth
     synth = Synth()
-    jobs = [(s, f) for s in range(n_seq) for f in range(total + max_off)]
+    iso_extra = 4   # frames after the timed region for the isolated kernel timing
+    jobs = [(s, f) for s in range(n_seq) for f in range(total + max_off + iso_extra)]
     with ThreadPoolExecutor(max_workers=host_threads) as ex:
         res = list(ex.map(lambda j: synth.sweep(64, rank_sequence_base(rank) + j[0], j[1])[0], jobs))
     sweeps = {j: r for j, r in zip(jobs, res)}
@@ -449,9 +450,21 @@ def main():
         st, odo, mp = ctx_d[g].step_batch_dev(ptrs, ns)
         assert st >= 0
 
-    ms_d, wall_d, launches, knn_ms, knn_launches, knn_bytes = timed_run(step_dev, ctx_d)
+    ms_d, wall_d, launches, knn_ms_situ, knn_launches_situ, knn_bytes_situ = timed_run(step_dev, ctx_d)
     clocks = sampler.stop()
     st0 = ctx_d[0].stats(0)
+    # Roofline of the graded kernel: inside the timed region the contexts overlap, so a per-launch event time of k_map_knn includes
+    # whatever the other streams were running.  It is therefore taken from context 0 advancing ALONE for a few more frames right
+    # after the timed region (same maps, same library path, per-launch CUDA events inside the library); the in-situ average is
+    # reported next to it.
+    knn_ms = knn_bytes = 0.0
+    knn_launches = 0
+    iso_frames = 0
+    for k in range(total, total + iso_extra):
+        step_dev(0, k)
+        t = ctx_d[0].timings()
+        knn_ms += t.knn_ms; knn_launches += t.knn_launches; knn_bytes += t.knn_bytes
+        iso_frames += 1
     for c in ctx_d:
         c.close()
 
@@ -506,7 +519,11 @@ def main():
                              # (profiles/r1_final_hot_kernels_l128_ncu.csv); null for other lane counts
                              "traffic": 41.0e6 if per == 128 else None,  # the capture was taken with 128 lanes per context
                              "peak_source": peak_src, "launches": knn_launches,
-                             "avg_launch_us": 1e3 * knn_ms / max(knn_launches, 1), "algorithmic_bytes_per_launch": knn_bytes / max(knn_launches, 1)},
+                             "avg_launch_us": 1e3 * knn_ms / max(knn_launches, 1), "algorithmic_bytes_per_launch": knn_bytes / max(knn_launches, 1),
+                             "lanes_per_launch": per,
+                             "how": f"context 0 alone for {iso_frames} frames after the timed region (per-launch CUDA events inside the library)",
+                             "in_situ_avg_launch_us": 1e3 * knn_ms_situ / max(knn_launches_situ, 1),
+                             "in_situ_note": "inside the timed region the launch overlaps the other contexts' kernels"},
                 "knn_throughput": knn_tp, "other_configs": extras, "cpu_baseline": cpu, "clocks": clocks,
                 "host": {"wall_ms_per_step_dev": 1e3 * wall_d / args.steps, "wall_ms_per_step_e2e": 1e3 * wall_e / args.steps, "gen_s": t_gen, "cores": host_threads}}
         print(json.dumps(line), flush=True)
