@@ -21,6 +21,7 @@
 struct OdoArgs {
   LaneState* ls;
   int lanes, outer;
+  int fast_h;        // widest azimuth half-window (buckets) the thread-per-feature kernel scans itself (16; LVO_FAST_H overrides)
   int lane0;         // first lane of an association launch (chunked outer loop, see lvo_launch_odometry)
   int distortion;    // 0 | 1 | 2, see the header comment
   // current features (stride caps)
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
         } else {
           hA = corner ? 0 : (bA.j >= 0 ? az_halfwidth(bA.d, rho) : LVO_AZ_BUCKETS);
           hB = bB.j >= 0 ? az_halfwidth(bB.d, rho) : LVO_AZ_BUCKETS;
-          if (hA > 6 || hB > 6) { fast = false; break; }   // a target has no candidate nearby or its window is wide: leave it to the cooperative kernel
+          if (hA > a.fast_h || hB > a.fast_h) { fast = false; break; }   // a target has no candidate nearby or its window is wide: leave it to the cooperative kernel
           skipA = corner ? hA : sA; skipB = sB;
         }
         unsigned wb[10], we[10];   // part 0 of every bucket range; fetched together before any candidate
@@ -583,6 +584,7 @@ static inline void lvo_launch_odometry(cudaStream_t st, OdoArgs a, const SolveAr
   // The outer loop runs chunk by chunk of lanes: the ten association passes of a lane read the same two grids of its previous
   // sweep (~1.4 MB per lane), so a chunk whose grids fit the 126 MB L2 pays DRAM for them once instead of ten times.
   const int chunk = lvo_odo_chunk(lanes);
+  { static int fh = -1; if (fh < 0) { const char* e = getenv("LVO_FAST_H"); fh = e ? atoi(e) : 16; } a.fast_h = fh; }
   for (int l0 = 0; l0 < lanes; l0 += chunk) {
     const int nl = min(chunk, lanes - l0);
     a.lane0 = l0;
