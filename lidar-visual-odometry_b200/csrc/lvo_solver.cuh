@@ -191,8 +191,28 @@ __device__ __forceinline__ d3 interp_point_jacobian(const double* x, double s, c
 
 template <bool DISTORT>
 __device__ __forceinline__ void accumulate_factor(const LvoFactor& f, const double* x, double huber, double* acc) {
-  double J[3][6], r[3];
-  int k;
+  // Corrector weight of a block with squared norm s (A18); adds rho / 2 to the cost
+  auto loss = [&](double s) -> double {
+    const double b = huber * huber;
+    double rho0, rho1;
+    if (s > b) { const double rr = sqrt(s); rho0 = 2 * huber * rr - b; rho1 = fmax(DBL_MIN, huber / rr); }
+    else { rho0 = s; rho1 = 1.0; }
+    acc[27] += 0.5 * rho0;
+    return rho1;
+  };
+  // one Jacobian row: every index below is a compile-time constant, so J rows and accumulators stay in registers (a row loop with
+  // a run-time trip count puts them in local memory).  Explicit FMAs: the TU is compiled with -fmad=false for the float paths
+  // that must match the x86 reference bit for bit; these double sums are ordered differently from Ceres anyway.
+  auto add_row = [&](const double (&Jr)[6], double ri, double rho1) {
+    int t = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const double wa = rho1 * Jr[a];
+#pragma unroll
+      for (int c = a; c < 6; ++c) { acc[t] = fma(wa, Jr[c], acc[t]); ++t; }
+      acc[21 + a] = fma(wa, ri, acc[21 + a]);
+    }
+  };
   if (DISTORT && f.type <= 1 && f.d != 1.0) {
     double Jl[3][6];
     const d3 lp = interp_point_jacobian(x, f.d, d3{f.c[0], f.c[1], f.c[2]}, Jl);
@@ -201,20 +221,26 @@ __device__ __forceinline__ void accumulate_factor(const LvoFactor& f, const doub
       const d3 nu = d3cross(u, v);
       const d3 de{f.a[0] - f.b[0], f.a[1] - f.b[1], f.a[2] - f.b[2]};
       const double den = sqrt(de.x * de.x + de.y * de.y + de.z * de.z);
-      r[0] = nu.x / den; r[1] = nu.y / den; r[2] = nu.z / den;
+      const double r[3] = {nu.x / den, nu.y / den, nu.z / den};
+      const double rho1 = loss(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
       const double D[3][3] = {{0, de.z / den, -de.y / den}, {-de.z / den, 0, de.x / den}, {de.y / den, -de.x / den, 0}};
 #pragma unroll
-      for (int i = 0; i < 3; ++i)
+      for (int i = 0; i < 3; ++i) {
+        double Jr[6];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) J[i][c] = D[i][0] * Jl[0][c] + D[i][1] * Jl[1][c] + D[i][2] * Jl[2][c];
-      k = 3;
+        for (int c = 0; c < 6; ++c) Jr[c] = D[i][0] * Jl[0][c] + D[i][1] * Jl[1][c] + D[i][2] * Jl[2][c];
+        add_row(Jr, r[i], rho1);
+      }
     } else {
-      r[0] = (lp.x - f.a[0]) * f.b[0] + (lp.y - f.a[1]) * f.b[1] + (lp.z - f.a[2]) * f.b[2];
+      const double r0 = (lp.x - f.a[0]) * f.b[0] + (lp.y - f.a[1]) * f.b[1] + (lp.z - f.a[2]) * f.b[2];
+      const double rho1 = loss(r0 * r0);
+      double Jr[6];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) J[0][c] = f.b[0] * Jl[0][c] + f.b[1] * Jl[1][c] + f.b[2] * Jl[2][c];
-      k = 1;
+      for (int c = 0; c < 6; ++c) Jr[c] = f.b[0] * Jl[0][c] + f.b[1] * Jl[1][c] + f.b[2] * Jl[2][c];
+      add_row(Jr, r0, rho1);
     }
-  } else {
+    return;
+  }
   const d3 rc = quat_rotate(x, d3{f.c[0], f.c[1], f.c[2]});
   const d3 lp{rc.x + x[4], rc.y + x[5], rc.z + x[6]};
   if (f.type == 0) {
@@ -222,52 +248,33 @@ __device__ __forceinline__ void accumulate_factor(const LvoFactor& f, const doub
     const d3 nu = d3cross(u, v);
     const d3 de{f.a[0] - f.b[0], f.a[1] - f.b[1], f.a[2] - f.b[2]};
     const double den = sqrt(de.x * de.x + de.y * de.y + de.z * de.z);
-    r[0] = nu.x / den; r[1] = nu.y / den; r[2] = nu.z / den;
+    const double r[3] = {nu.x / den, nu.y / den, nu.z / den};
+    const double rho1 = loss(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
     const double D[3][3] = {{0, de.z / den, -de.y / den}, {-de.z / den, 0, de.x / den}, {de.y / den, -de.x / den, 0}};
     const double Jp[3][3] = {{0, 2 * rc.z, -2 * rc.y}, {-2 * rc.z, 0, 2 * rc.x}, {2 * rc.y, -2 * rc.x, 0}};
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 3; ++i) {
+      double Jr[6];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        J[i][c] = D[i][0] * Jp[0][c] + D[i][1] * Jp[1][c] + D[i][2] * Jp[2][c];
-        J[i][3 + c] = D[i][c];
+        Jr[c] = D[i][0] * Jp[0][c] + D[i][1] * Jp[1][c] + D[i][2] * Jp[2][c];
+        Jr[3 + c] = D[i][c];
       }
-    k = 3;
+      add_row(Jr, r[i], rho1);
+    }
   } else {
-    double n[3];
+    double n[3], r0;
     if (f.type == 1) {  // LidarPlaneFactor: b holds ljm_norm
       n[0] = f.b[0]; n[1] = f.b[1]; n[2] = f.b[2];
-      r[0] = (lp.x - f.a[0]) * n[0] + (lp.y - f.a[1]) * n[1] + (lp.z - f.a[2]) * n[2];
+      r0 = (lp.x - f.a[0]) * n[0] + (lp.y - f.a[1]) * n[1] + (lp.z - f.a[2]) * n[2];
     } else {            // LidarPlaneNormFactor
       n[0] = f.a[0]; n[1] = f.a[1]; n[2] = f.a[2];
-      r[0] = (n[0] * lp.x + n[1] * lp.y + n[2] * lp.z) + f.d;
+      r0 = (n[0] * lp.x + n[1] * lp.y + n[2] * lp.z) + f.d;
     }
+    const double rho1 = loss(r0 * r0);
     // n^T * (-2 [rc]_x)
-    J[0][0] = -2 * (n[1] * rc.z - n[2] * rc.y);
-    J[0][1] = -2 * (n[2] * rc.x - n[0] * rc.z);
-    J[0][2] = -2 * (n[0] * rc.y - n[1] * rc.x);
-    J[0][3] = n[0]; J[0][4] = n[1]; J[0][5] = n[2];
-    k = 1;
-  }
-  }
-  double s = 0;
-  for (int i = 0; i < k; ++i) s += r[i] * r[i];
-  double rho0, rho1;
-  const double b = huber * huber;
-  if (s > b) { const double rr = sqrt(s); rho0 = 2 * huber * rr - b; rho1 = fmax(DBL_MIN, huber / rr); }
-  else { rho0 = s; rho1 = 1.0; }
-  acc[27] += 0.5 * rho0;
-  // explicit FMAs (the TU is compiled with -fmad=false for the float paths that must match the x86 reference bit for bit; these
-  // double accumulations are summed in a different order than Ceres anyway and are covered by the pose tolerance)
-  for (int i = 0; i < k; ++i) {
-    int t = 0;
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      const double wa = rho1 * J[i][a];
-#pragma unroll
-      for (int c = a; c < 6; ++c) { acc[t] = fma(wa, J[i][c], acc[t]); ++t; }
-      acc[21 + a] = fma(wa, r[i], acc[21 + a]);
-    }
+    const double Jr[6] = {-2 * (n[1] * rc.z - n[2] * rc.y), -2 * (n[2] * rc.x - n[0] * rc.z), -2 * (n[0] * rc.y - n[1] * rc.x), n[0], n[1], n[2]};
+    add_row(Jr, r0, rho1);
   }
 }
 
