@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblvo.so")
+LIB_PATH = os.environ.get("LVO_LIB_PATH") or os.path.join(HERE, "liblvo.so")  # LVO_LIB_PATH: another BUILD of the same library (A/B timing)
 
 LVO_OK, LVO_E_BADARG, LVO_E_CAPACITY, LVO_E_CUDA, LVO_E_STATE = 0, -1, -2, -3, -4
 LVO_W_FIRST_FRAME, LVO_W_FEW_CORR, LVO_W_MAP_TOO_SMALL = 1, 2, 3
