@@ -271,10 +271,31 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": "scans/s", "cores": threads, "kind": "port",
                              "sample": f"{threads} sequences x {args.steps} frames after {args.warmup} warm-up frames; restated reference (own kd-tree + own LM), not the PCL/Ceres binaries"},
             "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+def quiet_stdout():
+    """fd 1 -> fd 2 for everything else (NCCL prints its version banner on stdout, torchrun children share it)."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -290,6 +311,10 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: only the device-resident arm")
     ap.add_argument("--knn-frames", type=int, default=128, help="throughput-mode 5-NN: number of config-3 frames in one launch (0 = skip)")
     ap.add_argument("--no-extras", action="store_true", help="skip the config-2 / config-5 side measurements")
+    ap.add_argument("--e2e-order", default=os.environ.get("LVO_BENCH_E2E_ORDER", "first"), choices=["first", "last"],
+                    help="run the host-buffer arm before or after the device-resident arm")
+    ap.add_argument("--graphs", type=int, default=int(os.environ.get("LVO_BENCH_GRAPHS", "-1")),
+                    help="LVO_OPT_GRAPHS for the timed contexts: 1 = replay each frame from a CUDA graph, 0 = plain launches, -1 = graphs in the e2e arm only")
     ap.add_argument("--only-knn", action="store_true", help="profiling aid: only the throughput-mode 5-NN measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -319,7 +344,7 @@ def main():
         args.groups -= 1
     L = load_pkg()
     if args.only_knn:
-        print(json.dumps({"knn_throughput": knn_throughput(L, args.knn_frames, 5, local_rank)}), flush=True)
+        emit({"knn_throughput": knn_throughput(L, args.knn_frames, 5, local_rank)})
         return
     lanes = args.lanes
     total = args.warmup + args.steps
@@ -347,6 +372,10 @@ def main():
     # is single-threaded, distinct contexts run concurrently — the reference's multi-sequence mechanism, SURVEY 8b "Threading").
     # The stages of different groups overlap on the GPU (sort-bound extraction next to latency-bound association / LM).
     gstreams = [torch.cuda.Stream(device=local_rank) for _ in range(G)]
+    # LVO_OPT_GRAPHS: the host-buffer arm replays each frame from a CUDA graph (the host thread is free for the per-lane uploads);
+    # the device-resident arm uses plain launches because the in-situ per-launch kNN events need them (same device time either way)
+    graphs_e2e = args.graphs if args.graphs >= 0 else 1
+    graphs_dev = args.graphs if args.graphs >= 0 else 0
 
     def barrier():
         torch.cuda.synchronize()
@@ -411,12 +440,11 @@ def main():
     gplan = [plan[g * per:(g + 1) * per] for g in range(G)]
     h2d = [0] * G
 
-    if args.skip_e2e:
-        ms_e, wall_e = float("nan"), float("nan")
-    else:
+    def run_e2e():
         ctx_e = [L.Lvo(**mk) for _ in range(G)]
         for g in range(G):
             ctx_e[g].set_stream(gstreams[g].cuda_stream)
+            ctx_e[g].set_option(L.LVO_OPT_GRAPHS, graphs_e2e)
         host_views = [dict() for _ in range(G)]
 
         def views_of(g, k):
@@ -434,15 +462,21 @@ def main():
             assert st >= 0
             host_views[g].pop(k - 1, None)
 
-        ms_e, wall_e, _, _, _, _ = timed_run(step_host, ctx_e)
+        ms, wall, _, _, _, _ = timed_run(step_host, ctx_e)
         for c in ctx_e:
             c.close()
+        return ms, wall
+
+    ms_e, wall_e = float("nan"), float("nan")
+    if not args.skip_e2e and args.e2e_order == "first":
+        ms_e, wall_e = run_e2e()
 
     # ---- device-resident arm ------------------------------------------------------------------------------------------
     dev = {j: torch.from_numpy(a).cuda() for j, a in sweeps.items()}
     ctx_d = [L.Lvo(**mk) for _ in range(G)]
     for g in range(G):
         ctx_d[g].set_stream(gstreams[g].cuda_stream)
+        ctx_d[g].set_option(L.LVO_OPT_GRAPHS, graphs_dev)
 
     def step_dev(g, k):
         ptrs = [dev[(s, k + o)].data_ptr() for s, o in gplan[g]]
@@ -451,7 +485,6 @@ def main():
         assert st >= 0
 
     ms_d, wall_d, launches, knn_ms_situ, knn_launches_situ, knn_bytes_situ = timed_run(step_dev, ctx_d)
-    clocks = sampler.stop()
     st0 = ctx_d[0].stats(0)
     # Roofline of the graded kernel: inside the timed region the contexts overlap, so a per-launch event time of k_map_knn includes
     # whatever the other streams were running.  It is therefore taken from context 0 advancing ALONE for a few more frames right
@@ -460,6 +493,7 @@ def main():
     knn_ms = knn_bytes = 0.0
     knn_launches = 0
     iso_frames = 0
+    ctx_d[0].set_option(L.LVO_OPT_GRAPHS, 0)   # the per-launch events need plain launches
     for k in range(total, total + iso_extra):
         step_dev(0, k)
         t = ctx_d[0].timings()
@@ -467,6 +501,9 @@ def main():
         iso_frames += 1
     for c in ctx_d:
         c.close()
+    if not args.skip_e2e and args.e2e_order == "last":
+        ms_e, wall_e = run_e2e()
+    clocks = sampler.stop()
 
     # max over ranks
     ms_d, ms_e = max_over_ranks([ms_d, ms_e], world)
@@ -506,12 +543,13 @@ def main():
                 "dtype": "f32+f64", "data": "synthetic",
                 "config": {"workload": f"HDL-64 full pipeline (extract + scan-to-scan + scan-to-map), {lanes} independent sequences per GPU "
                                        f"in {G} contexts of {per} lanes (one CUDA stream + host thread each)",
-                           "lanes_per_gpu": lanes, "contexts_per_gpu": G, "points_per_sweep": 120000, "outer_iters": 10, "lm_iters": 4,
+                           "lanes_per_gpu": lanes, "contexts_per_gpu": G, "cuda_graphs": {"e2e_arm": graphs_e2e, "device_arm": graphs_dev}, "points_per_sweep": 120000, "outer_iters": 10, "lm_iters": 4,
                            "map_points_lane0": [st0.map_corner_from_map, st0.map_surf_from_map],
                            "l2": f"inputs larger than L2: every step reads {lanes} new sweeps ({lanes * 1.92:.0f} MB) and rebuilds every grid; no flush",
                            "timing": "one CUDA event pair on the main stream around all K steps of all contexts (context streams wait for the start event, "
                                      "the end event waits for every context's last kernel)"},
-                "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": sum(h2d), "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / args.steps},
+                "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": sum(h2d) * world, "d2h_bytes_per_step": d2h * world, "per_gpu_h2d_bytes_per_step": sum(h2d),
+                        "ms_per_step": ms_e / args.steps},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": "k_map_knn (5-NN grid search, thread per query)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak if peak else None,
@@ -526,7 +564,7 @@ def main():
                              "in_situ_note": "inside the timed region the launch overlaps the other contexts' kernels"},
                 "knn_throughput": knn_tp, "other_configs": extras, "cpu_baseline": cpu, "clocks": clocks,
                 "host": {"wall_ms_per_step_dev": 1e3 * wall_d / args.steps, "wall_ms_per_step_e2e": 1e3 * wall_e / args.steps, "gen_s": t_gen, "cores": host_threads}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

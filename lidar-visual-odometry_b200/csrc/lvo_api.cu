@@ -33,6 +33,7 @@ struct lvo_ctx {
   GridProblem* d_knn_prob = nullptr;
   int* d_knn_n = nullptr;
   unsigned char* d_raw = nullptr;   // [lanes][P * 32] raw sweep records
+  const lvo_cloud_view* pending_next = nullptr;  // lvo_step_batch_pipelined: frame to prefetch once this frame is enqueued
   unsigned char* d_raw2 = nullptr;  // second staging buffer for lvo_step_batch_pipelined (allocated on first use)
   cudaStream_t copy_st = nullptr;
   cudaEvent_t copy_ev = nullptr, compute_ev = nullptr;
@@ -538,6 +539,21 @@ int lvo_scan_to_map(lvo_ctx* c, lvo_cloud_view corner_last, lvo_cloud_view surf_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Upload of the next frame into the staging buffer that is not in use, on the copy stream (lvo_step_batch_pipelined).  That buffer
+// was last read by the previous frame's kernels, which have completed (every call ends synchronised).
+static int enqueue_prefetch(lvo_ctx* c) {
+  const lvo_cloud_view* next = c->pending_next;
+  c->pending_next = nullptr;
+  if (!next) return LVO_OK;
+  unsigned char* bufs[2] = {c->d_raw, c->d_raw2};
+  unsigned char* nb = bufs[c->raw_cur ^ 1];
+  for (int l = 0; l < c->lanes; ++l)
+    if (next[l].n) LVO_CUDA_OK(c, cudaMemcpyAsync(nb + c->raw_lane_bytes * l, next[l].data, next[l].n * next[l].stride, cudaMemcpyHostToDevice, c->copy_st));
+  LVO_CUDA_OK(c, cudaEventRecord(c->copy_ev, c->copy_st));
+  c->prefetched.assign(next, next + c->lanes);
+  return LVO_OK;
+}
+
 static int step_common(lvo_ctx* c, int stride, int off_xyz, int max_n, lvo_pose* T_wodom, lvo_pose* T_wmap) {
   c->launches = 0;
   LVO_TRY(set_inputs(c));
@@ -570,6 +586,7 @@ static int step_common(lvo_ctx* c, int stride, int off_xyz, int max_n, lvo_pose*
     c->have_knn_events = false;
     cudaEventRecord(c->ev[3], c->st);
     c->frame++;
+    LVO_TRY(enqueue_prefetch(c));
     LVO_TRY(sync_state(c));
     c->tim.extract_ms = c->tim.odometry_ms = 0.f;     // per-stage times are only available with plain launches
     cudaEventElapsedTime(&c->tim.mapping_ms, c->ev[0], c->ev[3]);
@@ -584,6 +601,7 @@ static int step_common(lvo_ctx* c, int stride, int off_xyz, int max_n, lvo_pose*
     if (do_map) { c->solve.trace = c->d_trace[1]; enqueue_mapping(c, 1, true, true); }
     cudaEventRecord(c->ev[3], c->st);
     c->frame++;
+    LVO_TRY(enqueue_prefetch(c));
     LVO_TRY(sync_state(c));
     cudaEventElapsedTime(&c->tim.extract_ms, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&c->tim.odometry_ms, c->ev[1], c->ev[2]);
@@ -660,15 +678,12 @@ int lvo_step_batch_pipelined(lvo_ctx* c, const lvo_cloud_view* sweeps, const lvo
   }
   c->prefetched.clear();
   for (int l = 0; l < c->lanes; ++l) { c->h_in_ptr[l] = bufs[c->raw_cur] + c->raw_lane_bytes * l; c->h_in_n[l] = (int)sweeps[l].n; }
-  if (next) {
-    // the other buffer was last read by the previous frame's kernels, which have completed (every call ends synchronised)
-    unsigned char* nb = bufs[c->raw_cur ^ 1];
-    for (int l = 0; l < c->lanes; ++l)
-      if (next[l].n) LVO_CUDA_OK(c, cudaMemcpyAsync(nb + c->raw_lane_bytes * l, next[l].data, next[l].n * next[l].stride, cudaMemcpyHostToDevice, c->copy_st));
-    LVO_CUDA_OK(c, cudaEventRecord(c->copy_ev, c->copy_st));
-    c->prefetched.assign(next, next + c->lanes);
-  }
-  return step_common(c, (int)sweeps[0].stride, (int)sweeps[0].off_xyz, max_n, T_wodom, T_wmap);
+  // the prefetch of `next` is enqueued by step_common AFTER this frame's kernels (enqueue_prefetch), so that the compute stream
+  // does not sit idle while the host issues one copy per lane
+  c->pending_next = next;
+  const int r = step_common(c, (int)sweeps[0].stride, (int)sweeps[0].off_xyz, max_n, T_wodom, T_wmap);
+  c->pending_next = nullptr;  // an early error return must not leave a pointer for a later call
+  return r;
 }
 
 int lvo_step_batch_dev(lvo_ctx* c, const lvo_point* const* d_sweeps, const size_t* n, lvo_pose* T_wodom, lvo_pose* T_wmap) {

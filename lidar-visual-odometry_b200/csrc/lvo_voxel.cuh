@@ -162,30 +162,57 @@ __global__ void k_vx_heads(VoxelEngine e) {
   }
 }
 
+// One thread per sorted item: every lane gathers its own point (independent loads), then the head of each run adds the points
+// of the following lanes IN ORDER through warp shuffles — the same sequential float sum as a serial walk, without its chain of
+// dependent loads.  A run that reaches the end of the warp's 32 items is continued from memory by its head.
 __global__ void k_vx_centroid(VoxelEngine e) {
   const int n = *e.d_n;
   const int vb = *e.d_vbits;
   const int p = lvo_sort_passes(*e.d_bits) & 1;
   const unsigned long long* keys = e.sort.keys[p];
   const unsigned* vals = e.sort.vals[p];
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-    const unsigned long long k = keys[t];
+  const unsigned lane = threadIdx.x & 31;
+  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < n; base += gridDim.x * blockDim.x) {
+    const int t = base + (int)lane;
+    const bool in = t < n;
+    const unsigned long long k = in ? keys[t] : 0ull;
+    const unsigned v = in ? vals[t] : 0u;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in) q = e.in_pts[v];
+    unsigned long long kprev = __shfl_up_sync(0xffffffffu, k, 1);
+    if (lane == 0 && in && t > 0) kprev = keys[t - 1];
     const int seg = (int)(k >> vb);
-    const bool pseudo = e.seg_mode[seg] == 2;
-    const bool head = (t == 0) || (k != keys[t - 1]) || pseudo;
-    if (!head) continue;
-    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-    int u = t;
-    do {
-      const float4 q = e.in_pts[vals[u]];
-      sx += q.x; sy += q.y; sz += q.z; si += q.w;
-      ++u;
-    } while (!pseudo && u < n && keys[u] == k);
-    const float c = (float)(u - t);
-    const unsigned o = e.outpos[t];
-    e.out_pts[o] = make_float4(sx / c, sy / c, sz / c, si / c);
-    e.out_aux[o] = e.in_aux[vals[t]];
-    atomicAdd(&e.seg_out_cnt[seg], 1u);
+    const bool pseudo = in && e.seg_mode[seg] == 2;
+    const bool head = in && (t == 0 || k != kprev || pseudo);
+    const unsigned stops = __ballot_sync(0xffffffffu, head || !in);
+    const unsigned above = stops & ~((2u << lane) - 1u);
+    const int end = above ? __ffs(above) - 1 : 32;        // first lane after this lane that is not part of its run
+    const int len = head ? end - (int)lane : 0;
+    const int maxlen = __reduce_max_sync(0xffffffffu, len);
+    float sx = 0.f + q.x, sy = 0.f + q.y, sz = 0.f + q.z, si = 0.f + q.w;   // 0 + x as in the serial sum (-0 becomes +0)
+    for (int d = 1; d < maxlen; ++d) {
+      const float nx = __shfl_down_sync(0xffffffffu, q.x, d), ny = __shfl_down_sync(0xffffffffu, q.y, d);
+      const float nz = __shfl_down_sync(0xffffffffu, q.z, d), ni = __shfl_down_sync(0xffffffffu, q.w, d);
+      if (d < len) { sx += nx; sy += ny; sz += nz; si += ni; }
+    }
+    if (head) {
+      int cnt = len;
+      if (end == 32 && !pseudo) {   // the run may go on in the next 32 items
+        int u = base + 32;
+        while (u < n && keys[u] == k) {
+          const float4 r = e.in_pts[vals[u]];
+          sx += r.x; sy += r.y; sz += r.z; si += r.w;
+          ++u;
+        }
+        cnt = u - t;
+      }
+      const float c = (float)cnt;
+      const unsigned o = e.outpos[t];
+      e.out_pts[o] = make_float4(sx / c, sy / c, sz / c, si / c);
+      e.out_aux[o] = e.in_aux[v];
+      const unsigned same = __match_any_sync(__activemask(), seg);   // heads of one segment in this warp: one atomic
+      if (lane == (unsigned)(__ffs(same) - 1)) atomicAdd(&e.seg_out_cnt[seg], (unsigned)__popc(same));
+    }
   }
 }
 
