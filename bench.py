@@ -315,6 +315,10 @@ def main():
                     help="run the host-buffer arm before or after the device-resident arm")
     ap.add_argument("--graphs", type=int, default=int(os.environ.get("LVO_BENCH_GRAPHS", "-1")),
                     help="LVO_OPT_GRAPHS for the timed contexts: 1 = replay each frame from a CUDA graph, 0 = plain launches, -1 = graphs in the e2e arm only")
+    ap.add_argument("--fixpoint-skip", type=int, default=int(os.environ.get("LVO_BENCH_FIXPOINT_SKIP", "1")),
+                    help="LVO_OPT_FIXPOINT_SKIP of the timed contexts (library default 1): outer iterations after a bit-exact fixed point of the pose "
+                         "are exact repeats and are not run; 0 = always run all ten")
+    ap.add_argument("--no-full-schedule", action="store_true", help="skip the extra device-resident arm with LVO_OPT_FIXPOINT_SKIP = 0")
     ap.add_argument("--only-knn", action="store_true", help="profiling aid: only the throughput-mode 5-NN measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -445,6 +449,7 @@ def main():
         for g in range(G):
             ctx_e[g].set_stream(gstreams[g].cuda_stream)
             ctx_e[g].set_option(L.LVO_OPT_GRAPHS, graphs_e2e)
+            ctx_e[g].set_option(L.LVO_OPT_FIXPOINT_SKIP, args.fixpoint_skip)
         host_views = [dict() for _ in range(G)]
 
         def views_of(g, k):
@@ -473,19 +478,30 @@ def main():
 
     # ---- device-resident arm ------------------------------------------------------------------------------------------
     dev = {j: torch.from_numpy(a).cuda() for j, a in sweeps.items()}
-    ctx_d = [L.Lvo(**mk) for _ in range(G)]
-    for g in range(G):
-        ctx_d[g].set_stream(gstreams[g].cuda_stream)
-        ctx_d[g].set_option(L.LVO_OPT_GRAPHS, graphs_dev)
+    def make_dev_contexts(fixpoint_skip):
+        cs = [L.Lvo(**mk) for _ in range(G)]
+        for g in range(G):
+            cs[g].set_stream(gstreams[g].cuda_stream)
+            cs[g].set_option(L.LVO_OPT_GRAPHS, graphs_dev)
+            cs[g].set_option(L.LVO_OPT_FIXPOINT_SKIP, fixpoint_skip)
+        return cs
 
-    def step_dev(g, k):
-        ptrs = [dev[(s, k + o)].data_ptr() for s, o in gplan[g]]
-        ns = [dev[(s, k + o)].shape[0] for s, o in gplan[g]]
-        st, odo, mp = ctx_d[g].step_batch_dev(ptrs, ns)
-        assert st >= 0
+    def dev_stepper(cs):
+        def step_dev(g, k):
+            ptrs = [dev[(s, k + o)].data_ptr() for s, o in gplan[g]]
+            ns = [dev[(s, k + o)].shape[0] for s, o in gplan[g]]
+            st, odo, mp = cs[g].step_batch_dev(ptrs, ns)
+            assert st >= 0
+        return step_dev
+
+    ctx_d = make_dev_contexts(args.fixpoint_skip)
+    step_dev = dev_stepper(ctx_d)
 
     ms_d, wall_d, launches, knn_ms_situ, knn_launches_situ, knn_bytes_situ = timed_run(step_dev, ctx_d)
     st0 = ctx_d[0].stats(0)
+    # outer iterations that ran in the last timed frame, mean over all lanes (10 = the reference's full schedule)
+    ex = [(c.stats(l).odo_outer_executed, c.stats(l).map_outer_executed) for c in ctx_d for l in range(per)]
+    outer_ran = [float(np.mean([e[0] for e in ex])), float(np.mean([e[1] for e in ex]))]
     # Roofline of the graded kernel: inside the timed region the contexts overlap, so a per-launch event time of k_map_knn includes
     # whatever the other streams were running.  It is therefore taken from context 0 advancing ALONE for a few more frames right
     # after the timed region (same maps, same library path, per-launch CUDA events inside the library); the in-situ average is
@@ -494,6 +510,7 @@ def main():
     knn_launches = 0
     iso_frames = 0
     ctx_d[0].set_option(L.LVO_OPT_GRAPHS, 0)   # the per-launch events need plain launches
+    ctx_d[0].set_option(L.LVO_OPT_FIXPOINT_SKIP, 0)   # ... and every one of the ten launches should search all lanes (kernel property)
     for k in range(total, total + iso_extra):
         step_dev(0, k)
         t = ctx_d[0].timings()
@@ -501,12 +518,19 @@ def main():
         iso_frames += 1
     for c in ctx_d:
         c.close()
+    # the same device-resident arm with the reference's full schedule (every lane runs all ten outer iterations), for comparison
+    ms_f = float("nan")
+    if args.fixpoint_skip and not args.no_full_schedule:
+        ctx_f = make_dev_contexts(0)
+        ms_f = timed_run(dev_stepper(ctx_f), ctx_f)[0]
+        for c in ctx_f:
+            c.close()
     if not args.skip_e2e and args.e2e_order == "last":
         ms_e, wall_e = run_e2e()
     clocks = sampler.stop()
 
     # max over ranks
-    ms_d, ms_e = max_over_ranks([ms_d, ms_e], world)
+    ms_d, ms_e, ms_f = max_over_ranks([ms_d, ms_e, ms_f], world)
     scans = lanes * args.steps * world
     value = scans / (ms_d * 1e-3)
     e2e = scans / (ms_e * 1e-3)
@@ -545,12 +569,18 @@ def main():
                                        f"in {G} contexts of {per} lanes (one CUDA stream + host thread each)",
                            "lanes_per_gpu": lanes, "contexts_per_gpu": G, "cuda_graphs": {"e2e_arm": graphs_e2e, "device_arm": graphs_dev}, "points_per_sweep": 120000, "outer_iters": 10, "lm_iters": 4,
                            "map_points_lane0": [st0.map_corner_from_map, st0.map_surf_from_map],
+                           "fixpoint_skip": {"enabled": args.fixpoint_skip, "outer_iterations_run_mean": {"scan_to_scan": outer_ran[0], "scan_to_map": outer_ran[1]},
+                                             "what": "LVO_OPT_FIXPOINT_SKIP (include/lvo.h): an outer iteration that returns the pose bit for bit unchanged makes "
+                                                     "the remaining ones exact repeats; they are not run. Poses / maps / counters are bitwise those of the full "
+                                                     "schedule (tests/test_gpu_mapping.py::test_fixpoint_skip_is_bitwise_identical)"},
                            "l2": f"inputs larger than L2: every step reads {lanes} new sweeps ({lanes * 1.92:.0f} MB) and rebuilds every grid; no flush",
                            "timing": "one CUDA event pair on the main stream around all K steps of all contexts (context streams wait for the start event, "
                                      "the end event waits for every context's last kernel)"},
                 "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": sum(h2d) * world, "d2h_bytes_per_step": d2h * world, "per_gpu_h2d_bytes_per_step": sum(h2d),
                         "ms_per_step": ms_e / args.steps},
                 "gpu_launches": launches,
+                "full_schedule": None if ms_f != ms_f else {"value": scans / (ms_f * 1e-3), "unit": "scans/s", "ms_per_step": ms_f / args.steps,
+                                                            "what": "device-resident arm with LVO_OPT_FIXPOINT_SKIP = 0: all ten outer iterations run for every lane"},
                 "roofline": {"bound": "hbm", "kernel": "k_map_knn (5-NN grid search, thread per query)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak if peak else None,
                              # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full`, 128 lanes, 5th step
@@ -559,7 +589,8 @@ def main():
                              "peak_source": peak_src, "launches": knn_launches,
                              "avg_launch_us": 1e3 * knn_ms / max(knn_launches, 1), "algorithmic_bytes_per_launch": knn_bytes / max(knn_launches, 1),
                              "lanes_per_launch": per,
-                             "how": f"context 0 alone for {iso_frames} frames after the timed region (per-launch CUDA events inside the library)",
+                             "how": f"context 0 alone for {iso_frames} frames after the timed region, LVO_OPT_FIXPOINT_SKIP = 0 so that every launch searches "
+                                    "all lanes (per-launch CUDA events inside the library)",
                              "in_situ_avg_launch_us": 1e3 * knn_ms_situ / max(knn_launches_situ, 1),
                              "in_situ_note": "inside the timed region the launch overlaps the other contexts' kernels"},
                 "knn_throughput": knn_tp, "other_configs": extras, "cpu_baseline": cpu, "clocks": clocks,

@@ -94,6 +94,9 @@ typedef struct lvo_stats {
   double map_final_cost[16];
   int map_corner_total, map_surf_total; /* points in all 4851 cubes after insertion + re-filter */
   int center_cube[3], cen[3];           /* centerCubeI/J/K and laserCloudCen{Width,Height,Depth} after shifting */
+  /* outer iterations that actually ran (== outer_iters unless LVO_OPT_FIXPOINT_SKIP cut the loop short; the per-iteration
+   * entries above are then filled with the values of the last iteration that ran, which every later one would reproduce) */
+  int odo_outer_executed, map_outer_executed;
 } lvo_stats;
 
 typedef struct lvo_ctx lvo_ctx; /* one per (GPU, group of lanes); owns streams, device arenas, cross-frame state */
@@ -236,6 +239,14 @@ int lvo_set_stream(lvo_ctx* ctx, void* cuda_stream);
  * mapping-on/off state and map generation; all data-dependent sizes live on the device, so the sequence is static),
  * 0 = plain launches (needed for the per-kernel timings of lvo_get_timings), -1 = automatic: graphs when lanes <= 8. */
 #define LVO_OPT_GRAPHS 1
+/* LVO_OPT_FIXPOINT_SKIP (default 1).  The reference runs a fixed number of outer iterations (laserOdometry.cpp:364,
+ * laserMapping.cpp:562), each a function of (pose, clouds) only: a fresh ceres::Problem, correspondences recomputed from the
+ * pose.  When an outer iteration returns the pose BIT FOR BIT unchanged (Ceres stopped on a tolerance and discarded its
+ * candidate), every remaining iteration of that frame has identical inputs and therefore identical outputs; with
+ * 1 the kernels of those iterations return immediately for that lane, with 0 they run.  Poses, maps, statuses and lvo_stats
+ * are bitwise the same either way (tests/test_gpu_mapping.py::test_fixpoint_skip_is_bitwise_identical); the per-iteration
+ * probes of skipped iterations are filled from the last iteration that ran. */
+#define LVO_OPT_FIXPOINT_SKIP 2
 int lvo_set_option(lvo_ctx* ctx, int option, int value);
 /* Bytes copied device->host per lane at the end of every synchronous call (poses, counters, status). */
 size_t lvo_state_bytes(void);

@@ -262,7 +262,7 @@ void collect_knn_timing(lvo_ctx* c) {
     if (s.map_too_small) continue;
     const double M = (double)s.from_off[0][LVO_MAX_VALID] + (double)s.from_off[1][LVO_MAX_VALID];
     const double Q = (double)s.n_stack[0] + (double)s.n_stack[1];
-    c->tim.knn_bytes += c->cfg.outer_iters * (16.0 * M + 56.0 * Q);
+    c->tim.knn_bytes += s.stats.map_outer_executed * (16.0 * M + 56.0 * Q);   // iterations skipped at a fixed point search nothing
   }
 }
 
@@ -348,6 +348,7 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
   SolveArgs& so = c->solve;
   memset(&so, 0, sizeof(so));
   so.ls = c->d_ls; so.max_iters = cfg->lm_max_iters; so.huber = cfg->huber;
+  so.n_outer = cfg->outer_iters; so.fixpoint_skip = 1;
   const size_t trace_n = (size_t)L * LVO_MAX_OUTER * (LVO_MAX_LM + 1) * LVO_TRACE_W;
   LVO_TRY(dalloc(c, &c->d_trace[0], trace_n)); LVO_TRY(dalloc(c, &c->d_trace[1], trace_n));
 
@@ -443,6 +444,12 @@ size_t lvo_state_bytes(void) { return sizeof(LaneState); }
 int lvo_set_option(lvo_ctx* c, int option, int value) {
   if (!c) return LVO_E_BADARG;
   if (option == LVO_OPT_GRAPHS) { c->opt_graphs = value; return LVO_OK; }
+  if (option == LVO_OPT_FIXPOINT_SKIP) {   // a kernel argument: captured graphs hold the old value
+    if (c->st) cudaStreamSynchronize(c->st);
+    destroy_graphs(c);
+    c->solve.fixpoint_skip = value ? 1 : 0;
+    return LVO_OK;
+  }
   return LVO_E_BADARG;
 }
 int lvo_set_stream(lvo_ctx* c, void* cuda_stream) {
@@ -845,6 +852,12 @@ int lvo_probe_fetch(lvo_ctx* c, int lane, int what, void* out, size_t cap_bytes,
   if (bytes == 0) return LVO_OK;
   if (row_bytes) {
     LVO_CUDA_OK(c, cudaMemcpy2D(out, row_bytes, src, row_stride, row_bytes, rows, cudaMemcpyDeviceToHost));
+    // LVO_OPT_FIXPOINT_SKIP: the outer iterations after a fixed point did not run; each of them would have reproduced the last
+    // one that did, so its rows are that iteration's rows
+    const bool odo = what == LVO_P_ODO_CORNER_CORR || what == LVO_P_ODO_PLANE_CORR || what == LVO_P_ODO_LM_TRACE;
+    const int ran = odo ? s.stats.odo_outer_executed : s.stats.map_outer_executed;
+    if (ran >= 1 && ran < rows)   // 0: the stage did not run at all (first frame / map too small)
+      for (int o = ran; o < rows; ++o) memcpy((char*)out + (size_t)o * row_bytes, (const char*)out + (size_t)(ran - 1) * row_bytes, row_bytes);
   } else {
     LVO_CUDA_OK(c, cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
   }

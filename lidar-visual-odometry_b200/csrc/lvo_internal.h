@@ -69,6 +69,9 @@ struct LaneState {
   int map_too_small;
   // ---- solver bookkeeping
   int n_factors;
+  // LVO_OPT_FIXPOINT_SKIP: set by k_lm_solve when an outer iteration left the pose bit-for-bit unchanged; the association / fit /
+  // solve kernels of the remaining outer iterations of this frame return at once for the lane (reset by k_odo_begin / k_map_begin)
+  int odo_done, map_done;
   lvo_stats stats;
   int status;
 };

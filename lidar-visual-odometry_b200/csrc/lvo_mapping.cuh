@@ -100,6 +100,7 @@ __global__ void k_map_begin(MapArgs a) {
   s.stats.map_surf_from_map = s.from_off[1][LVO_MAX_VALID];
   s.map_too_small = !(s.from_off[0][LVO_MAX_VALID] > 10 && s.from_off[1][LVO_MAX_VALID] > 50);  // :554
   s.map_status = s.map_too_small ? LVO_W_MAP_TOO_SMALL : LVO_OK;
+  s.map_done = 0; s.stats.map_outer_executed = 0;
   for (int o = 0; o < LVO_MAX_OUTER; ++o) { s.stats.map_corner_corr[o] = 0; s.stats.map_surf_corr[o] = 0; s.stats.map_lm_iters[o] = 0; s.stats.map_final_cost[o] = 0; }
   for (int c = 0; c < 3; ++c) { s.stats.center_cube[c] = s.center[c]; s.stats.cen[c] = s.cen[c]; }
 }
@@ -216,7 +217,7 @@ __device__ __forceinline__ void fit_factor(int t, const float4 ori, const float4
 __global__ void __launch_bounds__(128) k_map_knn(MapArgs a) {
   const int lane = blockIdx.y;
   const LaneState& s = a.ls[lane];
-  if (s.map_too_small) return;
+  if (s.map_too_small || s.map_done) return;   // :554 / fixed point reached (LVO_OPT_FIXPOINT_SKIP)
   const int n0 = s.n_stack[0], ntot = n0 + s.n_stack[1];
   const GridView g0 = grid_view(a.grid, 2 * lane), g1 = grid_view(a.grid, 2 * lane + 1);
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < ntot; f += gridDim.x * blockDim.x) {
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(128) k_map_knn(MapArgs a) {
 __global__ void __launch_bounds__(128) k_map_fit(MapArgs a) {
   const int lane = blockIdx.y;
   LaneState& s = a.ls[lane];
-  if (s.map_too_small) return;
+  if (s.map_too_small || s.map_done) return;   // :554 / fixed point reached (LVO_OPT_FIXPOINT_SKIP)
   const int n0 = s.n_stack[0], ntot = n0 + s.n_stack[1];
   const float4* M0 = a.from_map[0] + (size_t)lane * a.map_cap[0];
   const float4* M1 = a.from_map[1] + (size_t)lane * a.map_cap[1];
@@ -446,7 +447,7 @@ static inline void lvo_launch_mapping(cudaStream_t st, MapArgs a, const SolveArg
     k_map_fit<<<ga, 128, 0, st>>>(a);
     if (launches) *launches += 1;
     SolveArgs sa = solve_proto;
-    sa.which = 1; sa.outer = o; sa.factors = a.factors; sa.factor_cap = a.factor_cap; sa.distort = 0; sa.lane0 = 0;  // LidarEdgeFactor(..., 1.0), :610
+    sa.which = 1; sa.outer = o; sa.n_outer = outer_iters; sa.factors = a.factors; sa.factor_cap = a.factor_cap; sa.distort = 0; sa.lane0 = 0;  // LidarEdgeFactor(..., 1.0), :610
     lvo_launch_lm(st, sa, lanes, 16384);
     if (launches) *launches += 2;
   }

@@ -43,6 +43,7 @@ __global__ void k_odo_begin(OdoArgs a) {
   if (lane >= a.lanes) return;
   LaneState& s = a.ls[lane];
   s.odo_status = s.odo_inited ? LVO_OK : LVO_W_FIRST_FRAME;
+  s.odo_done = 0; s.stats.odo_outer_executed = 0;
   for (int o = 0; o < LVO_MAX_OUTER; ++o) { s.stats.odo_corner_corr[o] = 0; s.stats.odo_plane_corr[o] = 0; s.stats.odo_lm_iters[o] = 0; s.stats.odo_final_cost[o] = 0; }
 }
 
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
   __shared__ GridView gv[4];
   const int lane = a.lane0 + blockIdx.y;
   LaneState& s = a.ls[lane];
-  if (!s.odo_inited) return;
+  if (!s.odo_inited || s.odo_done) return;   // first frame / fixed point reached (LVO_OPT_FIXPOINT_SKIP)
   if (threadIdx.x < 4) gv[threadIdx.x] = grid_view(a.grid, 8 * lane + threadIdx.x);
   __syncthreads();
   const int ns = s.n_sharp, nf = s.n_flat;
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
   __shared__ GridView gv[8];
   const int lane = a.lane0 + blockIdx.y;
   LaneState& s = a.ls[lane];
-  if (!s.odo_inited) return;
+  if (!s.odo_inited || s.odo_done) return;   // first frame / fixed point reached (LVO_OPT_FIXPOINT_SKIP)
   if (threadIdx.x < 8) gv[threadIdx.x] = grid_view(a.grid, 8 * lane + threadIdx.x);
   __syncthreads();
   const int ns = s.n_sharp, nf = s.n_flat;
@@ -599,7 +600,7 @@ static inline void lvo_launch_odometry(cudaStream_t st, OdoArgs a, const SolveAr
       if (o == 0) k_odo_assoc<8><<<ga, 256, 0, st>>>(a);   // first iteration: more features lack a nearby candidate
       else k_odo_assoc<32><<<gs, 256, 0, st>>>(a);
       SolveArgs sa = solve_proto;
-      sa.which = 0; sa.outer = o; sa.factors = a.factors; sa.factor_cap = a.factor_cap; sa.distort = a.distortion != 0; sa.lane0 = l0;
+      sa.which = 0; sa.outer = o; sa.n_outer = outer_iters; sa.factors = a.factors; sa.factor_cap = a.factor_cap; sa.distort = a.distortion != 0; sa.lane0 = l0;
       lvo_launch_lm(st, sa, nl, nfeat_cap);
       if (launches) *launches += 2;
     }

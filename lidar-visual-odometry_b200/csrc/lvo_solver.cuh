@@ -289,6 +289,8 @@ struct SolveArgs {
   double* trace;              // [lanes][LVO_MAX_OUTER][LVO_MAX_LM + 1][LVO_TRACE_W] or null
   int lane0;                  // first lane of this launch (lanes are processed in chunks, see lvo_launch_odometry)
   int distort;                // != 0: factors may carry an interpolation ratio s != 1 (scan-to-scan with DISTORTION 1)
+  int n_outer;                // outer iterations of the frame (stats slots to fill when the loop is cut short)
+  int fixpoint_skip;          // LVO_OPT_FIXPOINT_SKIP
 };
 
 struct LmShared {
@@ -348,7 +350,7 @@ __device__ __forceinline__ void lm_broadcast(LmShared& sh, cg::cluster_group& cl
 
 // State of the trust-region loop, owned by thread 0.
 struct LmCtl {
-  double x[7], H[21], g[6], cost, x_norm;
+  double x[7], x0[7], H[21], g[6], cost, x_norm;
   double scale[6], diag[6], radius, decrease;
   double xc[7], model_cost_change;
   bool reuse_diag;
@@ -426,7 +428,7 @@ __global__ void __launch_bounds__(LVO_LM_THREADS, 2) k_lm_solve(SolveArgs a) {
   const bool lead = cluster.block_rank() == 0 && threadIdx.x == 0;
   const int lane = a.lane0 + blockIdx.x / cluster.num_blocks();
   LaneState& s = a.ls[lane];
-  if (a.which == 0 ? (s.odo_inited == 0) : (s.map_too_small != 0)) return;
+  if (a.which == 0 ? (s.odo_inited == 0 || s.odo_done != 0) : (s.map_too_small != 0 || s.map_done != 0)) return;
   const int nslots = a.which == 0 ? (s.n_sharp + s.n_flat) : (s.n_stack[0] + s.n_stack[1]);
   const LvoFactor* F = a.factors + (size_t)lane * a.factor_cap;
   double* xg = a.which == 0 ? s.para_q : s.map_x;  // para_q[4], para_t[3] are contiguous
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(LVO_LM_THREADS, 2) k_lm_solve(SolveArgs a) {
   lm_evaluate<DISTORT>(a, F, nslots, sh.xeval, sh, cluster);
   if (lead) {
     LmCtl& c = ctl;
-    for (int i = 0; i < 7; ++i) c.x[i] = sh.xeval[i];
+    for (int i = 0; i < 7; ++i) c.x[i] = c.x0[i] = sh.xeval[i];
     for (int i = 0; i < 21; ++i) c.H[i] = sh.sum[i];
     for (int i = 0; i < 6; ++i) c.g[i] = sh.sum[21 + i];
     c.cost = sh.sum[27];
@@ -500,8 +502,33 @@ __global__ void __launch_bounds__(LVO_LM_THREADS, 2) k_lm_solve(SolveArgs a) {
   if (lead) {
     LmCtl& c = ctl;
     for (int i = 0; i < 7; ++i) xg[i] = c.x[i];
-    if (a.which == 0) { s.stats.odo_lm_iters[a.outer] = c.iter; s.stats.odo_final_cost[a.outer] = c.nfactors ? c.cost : 0.0; }
-    else { s.stats.map_lm_iters[a.outer] = c.iter; s.stats.map_final_cost[a.outer] = c.nfactors ? c.cost : 0.0; }
+    // Fixed point: no step was accepted, the pose is bit for bit the one this outer iteration started from.  The next outer
+    // iteration would see the same pose and the same clouds, build the same correspondences and the same problem and stop the
+    // same way (every kernel on the path is deterministic), and so would all the others: their results are this iteration's.
+    bool fixed = a.fixpoint_skip != 0;
+    for (int i = 0; i < 7; ++i) fixed = fixed && __double_as_longlong(c.x[i]) == __double_as_longlong(c.x0[i]);
+    const double fc = c.nfactors ? c.cost : 0.0;
+    if (a.which == 0) {
+      s.stats.odo_lm_iters[a.outer] = c.iter; s.stats.odo_final_cost[a.outer] = fc;
+      s.stats.odo_outer_executed = a.outer + 1;
+      if (fixed) {
+        s.odo_done = 1;
+        for (int o = a.outer + 1; o < a.n_outer; ++o) {
+          s.stats.odo_corner_corr[o] = s.stats.odo_corner_corr[a.outer]; s.stats.odo_plane_corr[o] = s.stats.odo_plane_corr[a.outer];
+          s.stats.odo_lm_iters[o] = c.iter; s.stats.odo_final_cost[o] = fc;
+        }
+      }
+    } else {
+      s.stats.map_lm_iters[a.outer] = c.iter; s.stats.map_final_cost[a.outer] = fc;
+      s.stats.map_outer_executed = a.outer + 1;
+      if (fixed) {
+        s.map_done = 1;
+        for (int o = a.outer + 1; o < a.n_outer; ++o) {
+          s.stats.map_corner_corr[o] = s.stats.map_corner_corr[a.outer]; s.stats.map_surf_corr[o] = s.stats.map_surf_corr[a.outer];
+          s.stats.map_lm_iters[o] = c.iter; s.stats.map_final_cost[o] = fc;
+        }
+      }
+    }
   }
 }
 

@@ -210,3 +210,49 @@ def test_graph_replay_matches_plain_launches(lvo_mod, synth):
             assert np.array_equal(oa, ob) and np.array_equal(ma, mb), (skip, k)
         assert a.timings().kernel_launches == b.timings().kernel_launches
         a.close(); b.close()
+
+
+def test_fixpoint_skip_is_bitwise_identical(lvo_mod, synth):
+    """LVO_OPT_FIXPOINT_SKIP (default on): once an outer iteration returns the pose bit for bit unchanged, the remaining outer
+    iterations (laserOdometry.cpp:364, laserMapping.cpp:562) are exact repeats and are not run.  Poses, statuses, every
+    per-iteration counter, the correspondence / kNN probes of ALL ten iterations and the maps must equal the full schedule's."""
+    L = lvo_mod
+    mk = dict(lanes=2, max_map_corner=1 << 18, max_map_surf=1 << 19)
+    a, b = L.Lvo(**mk), L.Lvo(**mk)
+    for c, v in ((a, 1), (b, 0)):
+        c.set_option(L.LVO_OPT_GRAPHS, 0)
+        c.set_option(L.LVO_OPT_FIXPOINT_SKIP, v)
+    arrays = ("odo_corner_corr", "odo_plane_corr", "odo_lm_iters", "odo_final_cost", "map_corner_corr", "map_surf_corr", "map_lm_iters", "map_final_cost")
+    probes = (L.P_ODO_CORNER_CORR, L.P_ODO_PLANE_CORR, L.P_MAP_CORNER_KNN, L.P_MAP_SURF_KNN, L.P_MAP_CORNER_VALID, L.P_MAP_SURF_VALID)
+    cut = 0
+    for k in range(8):
+        sws = [synth.sweep(64, 0, k)[0], synth.sweep(64, 3, k)[0]]
+        sa, oa, ma = a.step_batch(sws)
+        sb, ob, mb = b.step_batch(sws)
+        assert sa == sb and np.array_equal(oa, ob) and np.array_equal(ma, mb), k
+        for lane in range(2):
+            x, y = a.stats(lane), b.stats(lane)
+            assert a.lane_status(lane) == b.lane_status(lane)
+            assert y.odo_outer_executed == (10 if k else 0)
+            assert y.map_outer_executed in (0, 10) and 0 <= x.map_outer_executed <= 10 and (x.odo_outer_executed >= 1) == (k > 0)
+            for name in arrays:
+                assert list(getattr(x, name)) == list(getattr(y, name)), (k, lane, name)
+            for what in probes:
+                assert np.array_equal(a.probe(what, lane), b.probe(what, lane)), (k, lane, what)
+            cut += (y.odo_outer_executed - x.odo_outer_executed) + (y.map_outer_executed - x.map_outer_executed)
+    assert cut > 20   # the shortcut really fired (typically after 3-6 of the 10 iterations)
+    for lane in range(2):
+        for which in (0, 1):
+            pa, ca = a.map_export(lane, which)
+            pb, cb = b.map_export(lane, which)
+            assert np.array_equal(ca, cb) and np.array_equal(_bits(pa), _bits(pb))
+    # the option also holds under graph replay (the flag is a kernel argument: graphs are re-captured when it changes)
+    a.set_option(L.LVO_OPT_GRAPHS, 1)
+    b.set_option(L.LVO_OPT_GRAPHS, 1)
+    for k in range(8, 11):
+        sws = [synth.sweep(64, 0, k)[0], synth.sweep(64, 3, k)[0]]
+        _, oa, ma = a.step_batch(sws)
+        _, ob, mb = b.step_batch(sws)
+        assert np.array_equal(oa, ob) and np.array_equal(ma, mb), k
+    assert a.stats(0).odo_outer_executed < 10 and b.stats(0).odo_outer_executed == 10
+    a.close(); b.close()
