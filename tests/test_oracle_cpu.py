@@ -328,3 +328,29 @@ def test_depth_association_oracle_against_numpy():
     ok = v == 1
     zs = dc[nn[ok]][:, :, 3]
     assert np.all(d[ok] >= zs.min(1) - 0.2001) and np.all(d[ok] <= zs.max(1) + 0.2001)   # the +-0.2 clamp
+
+
+def test_outer_loop_repeats_exactly_after_a_fixed_point():
+    """The premise of LVO_OPT_FIXPOINT_SKIP (include/lvo.h), checked on the restated reference: an outer iteration
+    (laserOdometry.cpp:364, laserMapping.cpp:562) whose solve returns the pose bit for bit unchanged is repeated identically by every
+    later one — same correspondences / kNN sets, same factor flags, same LM trace, same counters."""
+    from oracle_py import Oracle, Synth
+    synth = Synth()
+    o = Oracle(64, 5.0, 0.4, 0.8)
+    fixed = {"odo": 0, "map": 0}
+    for k in range(6):
+        o.step(synth.sweep(64, 2, k)[0], keep_log=True)
+        if k == 0:
+            continue
+        for name, logf, keys in (("odo", o.odometry_log, ("corner_corr", "plane_corr", "lm", "counts", "cost")),
+                                 ("map", o.mapping_log, ("corner_knn", "surf_knn", "corner_valid", "surf_valid", "lm", "counts", "cost"))):
+            logs = [logf(it) for it in range(10)]
+            fix = next((i for i, lg in enumerate(logs) if np.array_equal(lg["lm"][0, :7].view(np.uint64), lg["lm"][-1, :7].view(np.uint64))), None)
+            if fix is None:
+                continue
+            fixed[name] += 1
+            for it in range(fix + 1, 10):
+                for key in keys:
+                    a, b = logs[fix][key], logs[it][key]
+                    assert a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8)), (k, name, fix, it, key)
+    assert fixed["odo"] >= 3 and fixed["map"] >= 3, fixed
