@@ -354,3 +354,32 @@ def test_outer_loop_repeats_exactly_after_a_fixed_point():
                     a, b = logs[fix][key], logs[it][key]
                     assert a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8)), (k, name, fix, it, key)
     assert fixed["odo"] >= 3 and fixed["map"] >= 3, fixed
+
+
+def test_oracle_reproduces_hdl64_golden_fixture():
+    """tests/golden/hdl64_seq0.npz (make_golden_hdl64.py): generator inputs by SHA-256, every stage of four HDL-64 frames."""
+    from oracle_py import Synth
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hdl64_seq0.npz"))
+    synth = Synth()
+    o = Oracle(64, 5.0, 0.4, 0.8)
+    for k in range(int(g["frames"])):
+        pts, gt = synth.sweep(64, 0, k)
+        assert len(pts) == int(g[f"sweep{k}_n"]) and np.array_equal(sha(pts), g[f"sweep{k}_sha"]) and np.array_equal(gt, g[f"gt{k}"])
+        f = o.extract(pts)
+        for name in ("full", "sharp", "less_sharp", "flat", "less_flat"):
+            assert len(f[name]) == int(g[f"f{k}_{name}_n"]) and np.array_equal(sha(f[name]), g[f"f{k}_{name}_sha"]), (k, name)
+        for name in ("label", "sort_ind", "curvature", "picked", "scan_start", "scan_end"):
+            assert np.array_equal(sha(f[name]), g[f"f{k}_{name}_sha"]), (k, name)
+        st, rel, w = o.odometry(f["sharp"], f["less_sharp"], f["flat"], f["less_flat"])
+        assert st == int(g[f"odo{k}_status"]) and np.allclose(rel, g[f"odo{k}_rel"], atol=1e-12) and np.allclose(w, g[f"odo{k}_world"], atol=1e-12)
+        if k > 0:
+            assert np.array_equal(np.stack([o.odometry_log(it)["counts"] for it in range(10)]), g[f"odo{k}_counts"])
+        st, pose, _ = o.mapping(f["less_sharp"], f["less_flat"], f["full"], w)
+        assert st == int(g[f"map{k}_status"]) and np.allclose(pose, g[f"map{k}_pose"], atol=1e-12)
+        info = o.mapping_info()
+        assert np.array_equal(sha(info["corner_stack"]), g[f"map{k}_corner_stack_sha"]) and np.array_equal(sha(info["surf_stack"]), g[f"map{k}_surf_stack_sha"])
+        if st == 0:
+            assert np.array_equal(np.stack([o.mapping_log(it)["counts"] for it in range(10)]), g[f"map{k}_counts"])
+        assert [len(o.map_export(0)[0]), len(o.map_export(1)[0])] == g[f"map{k}_totals"].tolist()
+        # the pipeline tracks the generator's ground truth (sanity of the fixture itself)
+        assert np.linalg.norm(pose[4:] - gt[4:]) < 0.15
