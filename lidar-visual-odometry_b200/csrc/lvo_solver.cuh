@@ -539,6 +539,11 @@ static inline void lvo_launch_lm(cudaStream_t st, const SolveArgs& sa, int lanes
   while (csize > 1 && lanes * csize > 296) csize >>= 1;
   // small problems (scan-to-scan: < 2.4 k slots) do not amortise the cluster barriers: at most 4 slots per thread is enough
   while (csize > 1 && max_slots <= csize * LVO_LM_THREADS * 2) csize >>= 1;
+  { // LVO_LM_CLUSTER = 1 | 2 | 4 | 8 overrides the choice (tuning aid, like LVO_ODO_CHUNK / LVO_FAST_H)
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("LVO_LM_CLUSTER"); env = e ? atoi(e) : 0; }
+    if (env == 1 || env == 2 || env == 4 || env == 8) csize = env;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(lanes * csize, 1, 1);
   cfg.blockDim = dim3(LVO_LM_THREADS, 1, 1);
