@@ -69,7 +69,8 @@ int dalloc(lvo_ctx* c, T** p, size_t n, bool zero = true) {
   size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
   cudaError_t e = cudaMalloc(&q, bytes);
   if (e != cudaSuccess) { lvo_set_error(c, std::string("cudaMalloc: ") + cudaGetErrorString(e)); return LVO_E_CUDA; }
-  if (zero) cudaMemset(q, 0, bytes);
+  // stream-ordered with the kernels that follow (the context's stream is non-blocking: the legacy stream would not order with it)
+  if (zero) { e = cudaMemsetAsync(q, 0, bytes, c->st); if (e != cudaSuccess) { cudaFree(q); lvo_set_error(c, std::string("cudaMemsetAsync: ") + cudaGetErrorString(e)); return LVO_E_CUDA; } }
   c->allocs.push_back(q);
   *p = (T*)q;
   return LVO_OK;
@@ -719,8 +720,9 @@ int lvo_map_import(lvo_ctx* c, int lane, const lvo_point* corner, const int* cor
     std::vector<lvo_point> sorted(ns[t]);
     std::vector<unsigned> cur(start.begin(), start.end() - 1);
     for (size_t i = 0; i < ns[t]; ++i) sorted[cur[cubes[t][i]]++] = pts[t][i];  // stable inside a cube
-    if (ns[t]) LVO_CUDA_OK(c, cudaMemcpy(c->map.map_pts[c->map.gen][t] + (size_t)lane * c->map.map_cap[t], sorted.data(), ns[t] * sizeof(lvo_point), cudaMemcpyHostToDevice));
-    LVO_CUDA_OK(c, cudaMemcpy(c->map.cube_start[c->map.gen][t] + (size_t)lane * (LVO_NCUBES + 1), start.data(), sizeof(unsigned) * (LVO_NCUBES + 1), cudaMemcpyHostToDevice));
+    if (ns[t]) LVO_CUDA_OK(c, cudaMemcpyAsync(c->map.map_pts[c->map.gen][t] + (size_t)lane * c->map.map_cap[t], sorted.data(), ns[t] * sizeof(lvo_point), cudaMemcpyHostToDevice, c->st));
+    LVO_CUDA_OK(c, cudaMemcpyAsync(c->map.cube_start[c->map.gen][t] + (size_t)lane * (LVO_NCUBES + 1), start.data(), sizeof(unsigned) * (LVO_NCUBES + 1), cudaMemcpyHostToDevice, c->st));
+    LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));   // `sorted` / `start` die at the end of this iteration
   }
   SetCounts sc; memset(&sc, 0, sizeof(sc));
   sc.what = 5; sc.v[0] = (int)n_corner; sc.v[1] = (int)n_surf;
@@ -733,11 +735,15 @@ int lvo_map_export(lvo_ctx* c, int lane, int which, lvo_cloud_out* pts, int* cub
   if (!c || lane < 0 || lane >= c->lanes || which < 0 || which > 1 || !pts) return LVO_E_BADARG;
   LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
   std::vector<unsigned> start(LVO_NCUBES + 1);
-  LVO_CUDA_OK(c, cudaMemcpy(start.data(), c->map.cube_start[c->map.gen][which] + (size_t)lane * (LVO_NCUBES + 1), sizeof(unsigned) * (LVO_NCUBES + 1), cudaMemcpyDeviceToHost));
+  LVO_CUDA_OK(c, cudaMemcpyAsync(start.data(), c->map.cube_start[c->map.gen][which] + (size_t)lane * (LVO_NCUBES + 1), sizeof(unsigned) * (LVO_NCUBES + 1), cudaMemcpyDeviceToHost, c->st));
+  LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
   const size_t n = start[LVO_NCUBES];
   pts->n = n;
   if (n > pts->cap) return LVO_E_CAPACITY;
-  if (n) LVO_CUDA_OK(c, cudaMemcpy(pts->data, c->map.map_pts[c->map.gen][which] + (size_t)lane * c->map.map_cap[which], n * sizeof(lvo_point), cudaMemcpyDeviceToHost));
+  if (n) {
+    LVO_CUDA_OK(c, cudaMemcpyAsync(pts->data, c->map.map_pts[c->map.gen][which] + (size_t)lane * c->map.map_cap[which], n * sizeof(lvo_point), cudaMemcpyDeviceToHost, c->st));
+    LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  }
   if (cube_out) for (int k = 0; k < LVO_NCUBES; ++k) for (unsigned i = start[k]; i < start[k + 1]; ++i) cube_out[i] = k;
   return LVO_OK;
 }
@@ -851,7 +857,8 @@ int lvo_probe_fetch(lvo_ctx* c, int lane, int what, void* out, size_t cap_bytes,
   if (cap_bytes < bytes) return LVO_E_CAPACITY;
   if (bytes == 0) return LVO_OK;
   if (row_bytes) {
-    LVO_CUDA_OK(c, cudaMemcpy2D(out, row_bytes, src, row_stride, row_bytes, rows, cudaMemcpyDeviceToHost));
+    LVO_CUDA_OK(c, cudaMemcpy2DAsync(out, row_bytes, src, row_stride, row_bytes, rows, cudaMemcpyDeviceToHost, c->st));
+    LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
     // LVO_OPT_FIXPOINT_SKIP: the outer iterations after a fixed point did not run; each of them would have reproduced the last
     // one that did, so its rows are that iteration's rows
     const bool odo = what == LVO_P_ODO_CORNER_CORR || what == LVO_P_ODO_PLANE_CORR || what == LVO_P_ODO_LM_TRACE;
@@ -859,7 +866,8 @@ int lvo_probe_fetch(lvo_ctx* c, int lane, int what, void* out, size_t cap_bytes,
     if (ran >= 1 && ran < rows)   // 0: the stage did not run at all (first frame / map too small)
       for (int o = ran; o < rows; ++o) memcpy((char*)out + (size_t)o * row_bytes, (const char*)out + (size_t)(ran - 1) * row_bytes, row_bytes);
   } else {
-    LVO_CUDA_OK(c, cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
+    LVO_CUDA_OK(c, cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, c->st));
+    LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
   }
   return LVO_OK;
 }
@@ -1017,10 +1025,11 @@ int lvo_knn5_throughput(lvo_ctx* c, const lvo_point* d_maps, const int* map_coun
             talloc((void**)&d_mcnt, 4 * (size_t)S) == cudaSuccess;
   if (!ok) { cleanup(); lvo_set_error(c, "lvo_knn5_throughput: out of device memory"); return LVO_E_CUDA; }
   g.scan.cap_tiles = lvo_div_up((long long)table_n, LVO_SCAN_TILE) + 2;
-  cudaMemcpyAsync(d_moff, moff.data(), 4 * (size_t)(S + 1), cudaMemcpyHostToDevice, c->st);
-  cudaMemcpyAsync(d_qoff, qoff.data(), 4 * (size_t)(S + 1), cudaMemcpyHostToDevice, c->st);
-  cudaMemcpyAsync(d_mcnt, map_counts, 4 * (size_t)S, cudaMemcpyHostToDevice, c->st);
-  cudaStreamSynchronize(c->st);  // host vectors above must outlive the copies
+  cudaError_t ce = cudaMemcpyAsync(d_moff, moff.data(), 4 * (size_t)(S + 1), cudaMemcpyHostToDevice, c->st);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_qoff, qoff.data(), 4 * (size_t)(S + 1), cudaMemcpyHostToDevice, c->st);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_mcnt, map_counts, 4 * (size_t)S, cudaMemcpyHostToDevice, c->st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->st);  // host vectors above must outlive the copies
+  if (ce != cudaSuccess) { cleanup(); lvo_set_error(c, std::string("lvo_knn5_throughput: ") + cudaGetErrorString(ce)); return LVO_E_CUDA; }
   k_setup_batch_problems<<<lvo_div_up(S, 64), 64, 0, c->st>>>(g.prob, S, (const float4*)d_maps, d_moff, d_mcnt, 1.0f);
   c->launches = 0;
   lvo_grid_build(c->st, g, &c->launches);

@@ -194,14 +194,16 @@ __device__ __forceinline__ void fit_factor(int t, const float4 ori, const float4
     double A[15], b[5] = {-1, -1, -1, -1, -1}, n[3];
 #pragma unroll
     for (int j = 0; j < 5; ++j) { A[j * 3 + 0] = nb[j].x; A[j * 3 + 1] = nb[j].y; A[j * 3 + 2] = nb[j].z; }
-    if (!lsq_qr_5x3(A, b, n)) { n[0] = n[1] = n[2] = 0; }
+    // a rank-deficient 5x3 (Eigen's colPivHouseholderQr would still return a finite vector) gives no usable normal: no factor
+    if (!lsq_qr_5x3(A, b, n)) return;
     const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    if (!(nn > 0.0) || !isfinite(nn)) return;
     const double negOA = 1 / nn;
     n[0] /= nn; n[1] /= nn; n[2] /= nn;
     bool planeValid = true;
 #pragma unroll
     for (int j = 0; j < 5; ++j)
-      if (fabs(n[0] * nb[j].x + n[1] * nb[j].y + n[2] * nb[j].z + negOA) > 0.2) { planeValid = false; }  // :672-678
+      if (!(fabs(n[0] * nb[j].x + n[1] * nb[j].y + n[2] * nb[j].z + negOA) <= 0.2)) { planeValid = false; }  // :672-678 (a NaN never passes)
     if (planeValid) {
       fac.type = 2;
       fac.c[0] = ori.x; fac.c[1] = ori.y; fac.c[2] = ori.z;
@@ -368,14 +370,17 @@ __global__ void __launch_bounds__(256) k_rebuild_offsets(MapArgs a) {
     }
     unsigned tot;
     const unsigned ex = block_excl_scan(cnt, sm, &tot);
-    if (c < LVO_NCUBES) ncs[c] = carry + ex;
+    // capacity overflow: the offsets are clamped to map_cap, so the cubes past the capacity lose their tail CONSISTENTLY (table,
+    // n_map and the copy below agree) and the lane stays safe for the following frames; the frame reports LVO_E_CAPACITY
+    if (c < LVO_NCUBES) ncs[c] = min(carry + ex, (unsigned)a.map_cap[t]);
     carry += tot;
   }
   if (threadIdx.x == 0) {
-    ncs[LVO_NCUBES] = carry;
-    s.n_map[t] = (int)carry;
-    if (t == 0) s.stats.map_corner_total = (int)carry; else s.stats.map_surf_total = (int)carry;
-    if ((int)carry > a.map_cap[t]) s.map_status = LVO_E_CAPACITY;
+    const unsigned kept = min(carry, (unsigned)a.map_cap[t]);
+    ncs[LVO_NCUBES] = kept;
+    s.n_map[t] = (int)kept;
+    if (t == 0) s.stats.map_corner_total = (int)kept; else s.stats.map_surf_total = (int)kept;
+    if (carry > (unsigned)a.map_cap[t]) s.map_status = LVO_E_CAPACITY;
   }
 }
 // destination-parallel gather into the other generation

@@ -256,3 +256,36 @@ def test_fixpoint_skip_is_bitwise_identical(lvo_mod, synth):
         assert np.array_equal(oa, ob) and np.array_equal(ma, mb), k
     assert a.stats(0).odo_outer_executed < 10 and b.stats(0).odo_outer_executed == 10
     a.close(); b.close()
+
+
+def test_map_capacity_overflow_keeps_lanes_safe(lvo_mod, synth):
+    """A lane whose map outgrows max_map_* reports LVO_E_CAPACITY, loses the tail of its map consistently (offset table, n_map and
+    the stored points agree) and keeps stepping; its neighbour lane is untouched (bitwise equal to a context of its own)."""
+    import ctypes as C
+    L = lvo_mod
+    caps = dict(max_map_corner=3000, max_map_surf=6000)
+    a = L.Lvo(lanes=2, **caps)
+    b = L.Lvo(lanes=1, **caps)
+    overflowed = 0
+    for k in range(8):
+        big = synth.sweep(64, 0, k)[0]
+        small = np.ascontiguousarray(synth.sweep(64, 1, k)[0][::24])     # sparse sweep: its map stays far below the caps
+        views = [L.view_of(big), L.view_of(small)]
+        arr = (L.CloudView * 2)(*[v[0] for v in views])
+        po, pm = (L.Pose * 2)(), (L.Pose * 2)()
+        r = a.lib.lvo_step_batch(a.h, arr, po, pm)
+        assert r in (L.LVO_OK, L.LVO_W_FIRST_FRAME, L.LVO_W_FEW_CORR, L.LVO_W_MAP_TOO_SMALL, L.LVO_E_CAPACITY), (k, r, a.lib.lvo_last_error(a.h))
+        overflowed += r == L.LVO_E_CAPACITY
+        s0, s1 = a.stats(0), a.stats(1)
+        assert 0 <= s0.map_corner_total <= caps["max_map_corner"] and 0 <= s0.map_surf_total <= caps["max_map_surf"]
+        assert s0.map_corner_from_map <= caps["max_map_corner"] and s0.map_surf_from_map <= caps["max_map_surf"]
+        for which in (0, 1):
+            pts, cube = a.map_export(0, which)
+            assert len(pts) == (s0.map_corner_total, s0.map_surf_total)[which] and np.isfinite(pts).all()
+            assert (np.diff(cube) >= 0).all()
+        assert a.lane_status(1) >= 0, (k, a.lane_status(1))
+        _, ob, mb = b.step_batch([small])
+        assert np.array_equal(L.pose_to_np(po[1]), ob[0]) and np.array_equal(L.pose_to_np(pm[1]), mb[0]), k
+        assert (s1.map_corner_total, s1.map_surf_total) == (b.stats(0).map_corner_total, b.stats(0).map_surf_total)
+    assert overflowed >= 1
+    a.close(); b.close()
