@@ -339,7 +339,10 @@ template <bool WARP_LOCAL>
 __device__ __forceinline__ void bitonic_regs16(unsigned long long (&k)[16], int npad, unsigned long long* xbuf) {
   const unsigned ln = threadIdx.x & 31, w = WARP_LOCAL ? 0u : (threadIdx.x >> 5);   // warp-local sorts are all ascending
   const int ebase = (int)((w << 9) | (ln << 4));
-  const bool active = WARP_LOCAL || ebase < npad;   // warps that hold only padding keep the barriers and skip the work
+  // warps that hold only padding keep the barriers and skip the work.  The test is per WARP: a warp that holds any key below npad runs
+  // the network with all 32 lanes (the full-mask shuffles below need every lane; lanes past npad hold ~0ull padding and only ever
+  // exchange with each other, npad being a power of two) — a per-thread test deadlocks the shuffles when npad < 512 (sparse rings).
+  const bool active = WARP_LOCAL || (int)(w << 9) < npad;
   // K = 2, 4, 8: direction depends on the register index only
 #pragma unroll
   for (int K = 2; K <= 8; K <<= 1) {

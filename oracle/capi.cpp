@@ -22,6 +22,9 @@ struct Pipeline {
   LaserMapping map;
   Cloud registered;
   double ms_reg = 0, ms_odo = 0, ms_map = 0;
+  int skip_frame = 1;   // mapping_skip_frame (laserOdometry.cpp:274)
+  int frame_count = 0;  // frameCount of laserOdometry.cpp:307,643-645,669
+  int last_mapped = 0;
 };
 double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -296,8 +299,14 @@ void lvo_oracle_set_map_correction(void* h, const double* qt) {
   p->map.t_wmap_wodom = Vec3{qt[4], qt[5], qt[6]};
 }
 
-// Full per-frame chain as the three ROS nodes would run it (skipFrameNum = 1): extract -> odometry -> mapping.
-// poses_out = [q_wodom(4), t_wodom(3), q_wmap(4), t_wmap(3)].  Returns the odometry status.
+void lvo_oracle_set_skip_frame(void* h, int skip) { ((Pipeline*)h)->skip_frame = skip < 1 ? 1 : skip; }
+int lvo_oracle_last_frame_mapped(void* h) { return ((Pipeline*)h)->last_mapped; }
+
+// Full per-frame chain as the three ROS nodes would run it: extract -> odometry -> (every mapping_skip_frame-th frame,
+// laserOdometry.cpp:643-663) mapping.  poses_out[21] = [q_wodom(4), t_wodom(3)], [/aft_mapped_to_init of this frame if it was mapped,
+// else the high-frequency pose], [the high-frequency pose /aft_mapped_to_init_high_frec that laserOdometryHandler publishes when the
+// odometry message arrives, i.e. with the correction of the PREVIOUS mapped frame (laserMapping.cpp:197-229)].
+// Returns the odometry status.
 int lvo_oracle_step(void* h, const Pt* in, long n, double* poses_out, int keep_log) {
   Pipeline* p = (Pipeline*)h;
   double t0 = now_ms();
@@ -305,15 +314,26 @@ int lvo_oracle_step(void* h, const Pt* in, long n, double* poses_out, int keep_l
   double t1 = now_ms();
   int r = p->odo.process(p->reg.sharp, p->reg.lessSharp, p->reg.flat, p->reg.lessFlat, keep_log != 0, &p->reg.full);
   double t2 = now_ms();
-  // laserOdometry publishes laserCloudCornerLast/SurfLast (= this frame's less-sharp / less-flat) and the full cloud (:646-662)
-  p->map.process(p->odo.laserCloudCornerLast, p->odo.laserCloudSurfLast, p->odo.distortion == 2 ? &p->odo.fullOut : &p->reg.full, p->odo.q_w_curr,
-                 p->odo.t_w_curr, &p->registered, keep_log != 0);
+  // laserMapping.cpp:214-215
+  const Quat hq = qmul(p->map.q_wmap_wodom, p->odo.q_w_curr);
+  const Vec3 hr = rotate(p->map.q_wmap_wodom, p->odo.t_w_curr);
+  const double hf[7] = {hq.x, hq.y, hq.z, hq.w, hr.x + p->map.t_wmap_wodom.x, hr.y + p->map.t_wmap_wodom.y, hr.z + p->map.t_wmap_wodom.z};
+  const bool do_map = (p->frame_count % p->skip_frame) == 0;   // :643
+  if (do_map) {
+    p->frame_count = 0;                                        // :644
+    // laserOdometry publishes laserCloudCornerLast/SurfLast (= this frame's less-sharp / less-flat) and the full cloud (:646-662)
+    p->map.process(p->odo.laserCloudCornerLast, p->odo.laserCloudSurfLast, p->odo.distortion == 2 ? &p->odo.fullOut : &p->reg.full, p->odo.q_w_curr,
+                   p->odo.t_w_curr, &p->registered, keep_log != 0);
+  }
+  p->frame_count++;                                            // :669
+  p->last_mapped = do_map ? 1 : 0;
   double t3 = now_ms();
   p->ms_reg = t1 - t0; p->ms_odo = t2 - t1; p->ms_map = t3 - t2;
   if (poses_out) {
     poses_out[0] = p->odo.q_w_curr.x; poses_out[1] = p->odo.q_w_curr.y; poses_out[2] = p->odo.q_w_curr.z; poses_out[3] = p->odo.q_w_curr.w;
     poses_out[4] = p->odo.t_w_curr.x; poses_out[5] = p->odo.t_w_curr.y; poses_out[6] = p->odo.t_w_curr.z;
-    for (int k = 0; k < 7; ++k) poses_out[7 + k] = p->map.parameters[k];
+    for (int k = 0; k < 7; ++k) poses_out[7 + k] = do_map ? p->map.parameters[k] : hf[k];
+    for (int k = 0; k < 7; ++k) poses_out[14 + k] = hf[k];
   }
   if (r == 0 && p->odo.few_corr) r = 2;
   return r;

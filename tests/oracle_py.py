@@ -65,6 +65,8 @@ class Oracle:
         L.lvo_oracle_set_map_correction.argtypes = [C.c_void_p, C.c_void_p]
         L.lvo_oracle_step.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_int]
         L.lvo_oracle_timings.argtypes = [C.c_void_p, C.c_void_p]
+        L.lvo_oracle_set_skip_frame.argtypes = [C.c_void_p, C.c_int]
+        L.lvo_oracle_last_frame_mapped.argtypes = [C.c_void_p]
         L.lvo_oracle_voxel_grid.restype = C.c_long
         L.lvo_oracle_voxel_grid.argtypes = [C.c_void_p, C.c_long, C.c_float, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
         L.lvo_oracle_knn.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
@@ -170,9 +172,17 @@ class Oracle:
     # -- all three
     def step(self, pts, keep_log=False):
         pts = as_pts(pts)
-        poses = np.zeros(14)
+        poses = np.zeros(21)
         st = self.lib.lvo_oracle_step(self.h, _ptr(pts), len(pts), _ptr(poses), int(keep_log))
-        return st, poses[:7].copy(), poses[7:].copy()
+        self.high_freq = poses[14:].copy()   # /aft_mapped_to_init_high_frec of this frame (laserMapping.cpp:197-229)
+        return st, poses[:7].copy(), poses[7:14].copy()
+
+    def set_skip_frame(self, skip):
+        """mapping_skip_frame (laserOdometry.cpp:274,643): map every skip-th frame; step() then returns the high-frequency pose for the others."""
+        self.lib.lvo_oracle_set_skip_frame(self.h, int(skip))
+
+    def last_frame_mapped(self):
+        return bool(self.lib.lvo_oracle_last_frame_mapped(self.h))
 
     def odometry_last(self, which):
         """The "last" clouds after the frame (what laserOdometry.cpp:646-656 publishes): 0 corner, 1 surf, 2 full (distortion 2)."""

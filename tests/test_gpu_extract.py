@@ -84,6 +84,10 @@ def test_edge_cases(lvo_mod, synth):
     # a sweep small enough that most rings have < 6 usable points (:279-280)
     tiny = pts[np.sort(rng.choice(len(pts), 700, replace=False))]
     _compare_extract(L, lvo, O, tiny, "tiny")
+    # sparse sweeps: rings of ~40 .. ~600 points (less-flat candidate counts between 16 and 512 take the partial-warp path of the
+    # register sort; a per-thread activity test there once deadlocked the full-mask shuffles)
+    for step in (48, 24, 11, 7, 3):
+        _compare_extract(L, lvo, O, np.ascontiguousarray(pts[::step]), f"sparse/{step}")
     # consecutive calls on one context must not leak state
     _compare_extract(L, lvo, O, pts, "after-tiny")
     lvo.close()
