@@ -45,7 +45,9 @@ typedef struct lvo_point { float x, y, z, intensity; } lvo_point; /* device + ou
 typedef struct lvo_cloud_view { /* borrowed for the duration of the call */
   const void* data;
   size_t n;             /* number of points */
-  size_t stride;        /* bytes between points: 32 for pcl::PointXYZI, 16 for lvo_point */
+  size_t stride;        /* bytes between points: 32 for pcl::PointXYZI, 16 for lvo_point; raw sweeps (lvo_extract_features,
+                         * lvo_step_batch*) may also be packed x,y,z records of 12 bytes: the path never reads a sweep's intensity
+                         * (scanRegistration.cpp:132-133 converts the message to pcl::PointXYZ), off_intensity is then ignored */
   size_t off_xyz;       /* byte offset of x (y, z follow) */
   size_t off_intensity; /* byte offset of intensity */
 } lvo_cloud_view;
@@ -79,6 +81,10 @@ typedef struct lvo_config {
                           *     lidarFactor.hpp:27-30, 79-82); the TransformToEnd block (:610-625) stays off (`if (0)`);
                           * 2 = 1 plus that block: less-sharp, less-flat and full clouds are moved to the sweep end (:176-191)
                           *     before they become the "last" clouds and the mapping input.                                   */
+  int debug_probes;      /* 1 = keep the per-outer-iteration parity probes (LVO_P_ODO_*_CORR, LVO_P_MAP_*_KNN / _VALID) of ALL outer
+                          * iterations (16 slots per lane: ~50 MB per lane at the default capacities); 0 (default) = only what the path
+                          * itself needs (the current and the previous iteration), and lvo_probe_fetch of those probes returns
+                          * LVO_E_STATE.  Results are identical either way.                                                         */
 } lvo_config;
 
 /* Per-call counters, also the parity probes (SURVEY §5 "Metrics / logging").  One record per lane. */
@@ -139,6 +145,15 @@ int lvo_step_batch(lvo_ctx* ctx, const lvo_cloud_view* sweeps, lvo_pose* T_wodom
  * The buffers of next_sweeps must stay valid and unchanged until the next call. */
 int lvo_step_batch_pipelined(lvo_ctx* ctx, const lvo_cloud_view* sweeps, const lvo_cloud_view* next_sweeps_or_null, lvo_pose* T_wodom_curr,
                              lvo_pose* T_wmap_curr);
+
+/* Asynchronous forms (SURVEY §8b "Threading": `_async` + lvo_wait, for pipelining a host loop the way the reference's three ROS
+ * processes overlap): lvo_step_batch_async copies and enqueues one frame for every lane and returns without waiting for the GPU;
+ * lvo_wait blocks until that frame is done and delivers its poses / statuses (same return value as lvo_step_batch).  The sweep
+ * buffers must stay valid and unchanged until lvo_wait returns; exactly one step may be in flight per context; every other entry
+ * point returns LVO_E_STATE while one is.  Lanes whose host buffers are adjacent in memory (one slab) are uploaded in one copy. */
+int lvo_step_batch_async(lvo_ctx* ctx, const lvo_cloud_view* sweeps);
+int lvo_step_batch_dev_async(lvo_ctx* ctx, const lvo_point* const* d_sweeps, const size_t* n);
+int lvo_wait(lvo_ctx* ctx, lvo_pose* T_wodom_curr, lvo_pose* T_wmap_curr);
 
 /* Same, with sweeps already resident in device memory as packed lvo_point arrays (d_sweeps[l] is a device
  * pointer with n[l] points).  This is what bench.py's device-resident `value` times. */
@@ -230,6 +245,22 @@ typedef struct lvo_timings {
   int knn_launches;
   int kernel_launches;    /* kernels launched by the last call (for bench.py's gpu_launches) */
   double knn_bytes;       /* algorithmic bytes of those 5-NN launches: 16 M + 56 Q each */
+  /* sub-stages under the reference's TicToc printf names (CUDA events between the kernels of plain-launch calls; 0 when the frame
+   * was replayed from a CUDA graph or LVO_OPT_STAGE_TIMING is off).  Per-iteration stages are summed over the outer iterations. */
+  float reg_prepare_ms;      /* "prepare time"                    scanRegistration.cpp:254 : filter, ring ids, ring concat, curvature */
+  float reg_sort_ms;         /* "sort q time"                     :409 : the sector sorts                                             */
+  float reg_separate_ms;     /* "seperate points time"            :410 : picks, less-flat voxel filter, compaction (excl. the sorts)  */
+  float odo_association_ms;  /* "data association time"           laserOdometry.cpp:564                                               */
+  float odo_solver_ms;       /* "solver time"                     :577                                                                */
+  float odo_rest_ms;         /* pose integration, cloud swap, kd-tree (grid) rebuild  :581-641 ("publication time" :664 has no analogue) */
+  float map_prepare_ms;      /* "map prepare time"                laserMapping.cpp:552 : cube window, 75-cube gather, stack downsample */
+  float map_build_tree_ms;   /* "build tree time"                 :560 : the two search grids                                         */
+  float map_association_ms;  /* "mapping data assosiation time"   :710 : 5-NN (= knn_ms) + line / plane fits                          */
+  float map_solver_ms;       /* "mapping solver time"             :721                                                                */
+  float map_optimization_ms; /* "mapping optimization time"       :728 : association + solver of all outer iterations                 */
+  float map_add_points_ms;   /* "add points time"                 :784 : transformUpdate + insertion keys                             */
+  float map_filter_ms;       /* "filter time"                     :802 : per-cube re-filter + map rebuild                             */
+  float map_pub_ms;          /* "mapping pub time"                :850 : the registered cloud                                         */
 } lvo_timings;
 int lvo_get_timings(const lvo_ctx* ctx, lvo_timings* out);
 /* Enqueue all work of this context on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL restores the
@@ -247,6 +278,9 @@ int lvo_set_stream(lvo_ctx* ctx, void* cuda_stream);
  * are bitwise the same either way (tests/test_gpu_mapping.py::test_fixpoint_skip_is_bitwise_identical); the per-iteration
  * probes of skipped iterations are filled from the last iteration that ran. */
 #define LVO_OPT_FIXPOINT_SKIP 2
+/* LVO_OPT_STAGE_TIMING (default 1): record the sub-stage CUDA events of lvo_timings in plain-launch lvo_step_batch* calls (~100
+ * cudaEventRecord per frame); 0 = only the three whole-stage times.  The three per-stage entry points always record them. */
+#define LVO_OPT_STAGE_TIMING 3
 int lvo_set_option(lvo_ctx* ctx, int option, int value);
 /* Bytes copied device->host per lane at the end of every synchronous call (poses, counters, status). */
 size_t lvo_state_bytes(void);

@@ -18,6 +18,7 @@ LVO_OK, LVO_E_BADARG, LVO_E_CAPACITY, LVO_E_CUDA, LVO_E_STATE = 0, -1, -2, -3, -
 LVO_W_FIRST_FRAME, LVO_W_FEW_CORR, LVO_W_MAP_TOO_SMALL = 1, 2, 3
 LVO_OPT_GRAPHS = 1
 LVO_OPT_FIXPOINT_SKIP = 2
+LVO_OPT_STAGE_TIMING = 3
 
 # enum lvo_probe
 (P_FULL, P_CURVATURE, P_SORT_IND, P_LABEL, P_PICKED, P_SCAN_START, P_SCAN_END, P_SHARP, P_LESS_SHARP, P_FLAT, P_LESS_FLAT,
@@ -40,7 +41,7 @@ class Pose(C.Structure):
 class Config(C.Structure):
     _fields_ = [("n_scans", C.c_int), ("minimum_range", C.c_double), ("line_res", C.c_double), ("plane_res", C.c_double),
                 ("skip_frame", C.c_int), ("outer_iters", C.c_int), ("lm_max_iters", C.c_int), ("huber", C.c_double), ("device", C.c_int),
-                ("lanes", C.c_int), ("max_points", C.c_int), ("max_map_corner", C.c_int), ("max_map_surf", C.c_int), ("distortion", C.c_int)]
+                ("lanes", C.c_int), ("max_points", C.c_int), ("max_map_corner", C.c_int), ("max_map_surf", C.c_int), ("distortion", C.c_int), ("debug_probes", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -63,16 +64,27 @@ KITTI00_CAMERA = dict(fx=718.856, fy=718.856, cx=607.1928, cy=185.2157, width=12
                                  0.9999738645903, 0.0004859485810390, -0.007206933692422, -0.2921968648686])
 
 
+# sub-stage fields of lvo_timings and the reference's TicToc printf they correspond to (scanRegistration.cpp:254,409,410;
+# laserOdometry.cpp:564,577; laserMapping.cpp:552,560,710,721,728,784,802,850)
+STAGE_FIELDS = ["reg_prepare_ms", "reg_sort_ms", "reg_separate_ms", "odo_association_ms", "odo_solver_ms", "odo_rest_ms", "map_prepare_ms",
+                "map_build_tree_ms", "map_association_ms", "map_solver_ms", "map_optimization_ms", "map_add_points_ms", "map_filter_ms", "map_pub_ms"]
+STAGE_NAMES = {"reg_prepare_ms": "prepare time", "reg_sort_ms": "sort q time", "reg_separate_ms": "seperate points time",
+               "odo_association_ms": "data association time", "odo_solver_ms": "solver time", "odo_rest_ms": "(pose integration + kd-tree rebuild)",
+               "map_prepare_ms": "map prepare time", "map_build_tree_ms": "build tree time", "map_association_ms": "mapping data assosiation time",
+               "map_solver_ms": "mapping solver time", "map_optimization_ms": "mapping optimization time", "map_add_points_ms": "add points time",
+               "map_filter_ms": "filter time", "map_pub_ms": "mapping pub time"}
+
+
 class Timings(C.Structure):
     _fields_ = [("extract_ms", C.c_float), ("odometry_ms", C.c_float), ("mapping_ms", C.c_float), ("knn_ms", C.c_float), ("knn_launches", C.c_int),
-                ("kernel_launches", C.c_int), ("knn_bytes", C.c_double)]
+                ("kernel_launches", C.c_int), ("knn_bytes", C.c_double)] + [(n, C.c_float) for n in STAGE_FIELDS]
 
 
 EXPORTS = ["lvo_default_config", "lvo_create", "lvo_destroy", "lvo_last_error", "lvo_get_stats", "lvo_extract_features", "lvo_scan_to_scan",
            "lvo_scan_to_map", "lvo_step_batch", "lvo_step_batch_dev", "lvo_lane_status", "lvo_map_import", "lvo_map_export",
            "lvo_get_map_correction", "lvo_set_map_correction", "lvo_set_odometry_state", "lvo_probe_fetch", "lvo_voxel_downsample", "lvo_knn",
            "lvo_knn5_throughput", "lvo_get_timings", "lvo_set_stream", "lvo_state_bytes", "lvo_depth_associate", "lvo_step_batch_pipelined", "lvo_set_option", "lvo_voxel_downsample_dev",
-           "lvo_map_cloud", "lvo_transform_cloud"]
+           "lvo_map_cloud", "lvo_transform_cloud", "lvo_step_batch_async", "lvo_step_batch_dev_async", "lvo_wait"]
 
 
 def load_library():
@@ -94,6 +106,9 @@ def load_library():
     L.lvo_step_batch_pipelined.argtypes = [vp, C.POINTER(CloudView), C.POINTER(CloudView), C.POINTER(Pose), C.POINTER(Pose)]
     L.lvo_step_batch_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(Pose), C.POINTER(Pose)]
     L.lvo_lane_status.argtypes = [vp, ip]
+    L.lvo_step_batch_async.argtypes = [vp, C.POINTER(CloudView)]
+    L.lvo_step_batch_dev_async.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.lvo_wait.argtypes = [vp, C.POINTER(Pose), C.POINTER(Pose)]
     L.lvo_map_import.argtypes = [vp, ip, vp, vp, C.c_size_t, vp, vp, C.c_size_t]
     L.lvo_map_export.argtypes = [vp, ip, ip, C.POINTER(CloudOut), vp]
     L.lvo_map_cloud.argtypes = [vp, ip, ip, C.POINTER(CloudOut)]
@@ -115,11 +130,14 @@ def load_library():
 
 
 def view_of(a):
-    """CloudView over an (n,4) float32 array (packed lvo_point) or an (n,8) float32 array (pcl::PointXYZI layout)."""
+    """CloudView over an (n,4) float32 array (packed lvo_point), an (n,8) float32 array (pcl::PointXYZI layout) or, for raw sweeps
+    only, an (n,3) float32 array (packed x, y, z)."""
     if a is None:
         return CloudView(None, 0, 16, 0, 12), None
     a = np.ascontiguousarray(a, dtype=np.float32)
-    assert a.ndim == 2 and a.shape[1] in (4, 8)
+    assert a.ndim == 2 and a.shape[1] in (3, 4, 8)
+    if a.shape[1] == 3:
+        return CloudView(a.ctypes.data, a.shape[0], 12, 0, 0), a
     if a.shape[1] == 4:
         return CloudView(a.ctypes.data, a.shape[0], 16, 0, 12), a
     return CloudView(a.ctypes.data, a.shape[0], 32, 0, 16), a
@@ -156,7 +174,8 @@ class Lvo:
     """One lvo_ctx."""
 
     def __init__(self, n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, skip_frame=1, outer_iters=10, lm_max_iters=4, huber=0.1,
-                 device=0, lanes=1, max_points=0, max_map_corner=0, max_map_surf=0, distortion=0):
+                 device=0, lanes=1, max_points=0, max_map_corner=0, max_map_surf=0, distortion=0, debug_probes=1):
+        """debug_probes defaults to 1 HERE (the parity tests read every outer iteration's probes); lvo_default_config and bench.py use 0."""
         self.lib = load_library()
         cfg = Config()
         self.lib.lvo_default_config(C.byref(cfg))
@@ -164,6 +183,7 @@ class Lvo:
         cfg.skip_frame, cfg.outer_iters, cfg.lm_max_iters, cfg.huber, cfg.device, cfg.lanes = skip_frame, outer_iters, lm_max_iters, huber, device, lanes
         cfg.max_points, cfg.max_map_corner, cfg.max_map_surf = max_points, max_map_corner, max_map_surf
         cfg.distortion = distortion
+        cfg.debug_probes = debug_probes
         self.cfg = cfg
         self.h = C.c_void_p()
         r = self.lib.lvo_create(C.byref(cfg), C.byref(self.h))
@@ -225,6 +245,25 @@ class Lvo:
         po, pm = (Pose * self.lanes)(), (Pose * self.lanes)()
         r = self._check(self.lib.lvo_step_batch(self.h, arr, po, pm))
         return r, np.stack([pose_to_np(p) for p in po]), np.stack([pose_to_np(p) for p in pm])
+
+    def step_batch_async(self, sweeps):
+        """Enqueue one frame and return; the arrays must stay alive and unchanged until wait()."""
+        self._async_keep = [view_of(s) for s in sweeps]
+        arr = (CloudView * self.lanes)(*[v[0] for v in self._async_keep])
+        return self._check(self.lib.lvo_step_batch_async(self.h, arr))
+
+    def wait(self):
+        po, pm = (Pose * self.lanes)(), (Pose * self.lanes)()
+        r = self._check(self.lib.lvo_wait(self.h, po, pm))
+        self._async_keep = None
+        return r, np.stack([pose_to_np(p) for p in po]), np.stack([pose_to_np(p) for p in pm])
+
+    def stage_timings(self):
+        """{reference TicToc name: milliseconds} of the last plain-launch call, plus the three whole-stage times."""
+        t = self.timings()
+        d = {STAGE_NAMES[f]: float(getattr(t, f)) for f in STAGE_FIELDS}
+        d.update({"scan registration time": float(t.extract_ms), "whole laserOdometry time": float(t.odometry_ms), "whole mapping time": float(t.mapping_ms)})
+        return d
 
     def step_batch_pipelined(self, sweeps, next_sweeps=None):
         """Like step_batch, but uploads next_sweeps on a copy stream while this frame computes.  The arrays of next_sweeps

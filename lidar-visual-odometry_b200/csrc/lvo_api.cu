@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cstring>
 #include <new>
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges under the reference's stage names show up in Nsight timelines
 
 struct lvo_ctx {
   lvo_config cfg;
@@ -38,6 +39,8 @@ struct lvo_ctx {
   cudaStream_t copy_st = nullptr;
   cudaEvent_t copy_ev = nullptr, compute_ev = nullptr;
   std::vector<lvo_cloud_view> prefetched;  // the sweep set sitting in the "next" staging buffer
+  std::vector<const unsigned char*> next_in_ptr;  // its per-lane device pointers
+  int opt_stage_timing = 1;         // LVO_OPT_STAGE_TIMING: sub-stage events in plain-launch steps
   int raw_cur = 0;                  // which staging buffer the current frame reads
   size_t raw_lane_bytes = 0;
   const unsigned char** d_in_ptr = nullptr; const unsigned char** h_in_ptr = nullptr;
@@ -49,9 +52,14 @@ struct lvo_ctx {
   long long frame = 0;
   std::vector<int> lane_status;
   cudaEvent_t ev[8];
-  std::vector<cudaEvent_t> knn_ev;
+  LvoStageTimer stage_tm;           // sub-stage CUDA events of plain-launch calls (reference TicToc names)
   lvo_timings tim;
-  bool have_knn_events = false;
+  // lvo_step_batch*_async: what lvo_wait has to finish
+  bool pending = false, pending_do_map = false, pending_graph = false;
+  // merged host->device uploads (one copy per run of lanes that are adjacent in host memory)
+  struct Span { const unsigned char* host; size_t bytes; size_t dev_off; };
+  std::vector<Span> spans;
+  std::vector<int> span_order;
   // CUDA graphs of the fused per-frame sequence: [mapping on/off][map generation]
   cudaGraphExec_t graph_exec[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   long long graph_launches[2][2] = {{0, 0}, {0, 0}};
@@ -91,16 +99,19 @@ int alloc_scan(lvo_ctx* c, LvoScanScratch* s, size_t n_cap) {
   s->cap_tiles = lvo_div_up((long long)n_cap, LVO_SCAN_TILE) + 2;
   return dalloc(c, &s->partial, (size_t)s->cap_tiles);
 }
-int alloc_grid(lvo_ctx* c, GridSet* g, int nprob, int cells_cap, size_t pts_total, int pts_per_problem) {
+// table_cells: cells of the whole set (0 = nprob * cells_cap; smaller when the problems carry their own GridProblem::cells_cap shares)
+int alloc_grid(lvo_ctx* c, GridSet* g, int nprob, int cells_cap, size_t pts_total, int pts_per_problem, size_t table_cells = 0) {
   g->nprob = nprob; g->cells_cap_per_problem = cells_cap; g->pts_cap_per_problem = pts_per_problem;
+  if (table_cells == 0) table_cells = (size_t)nprob * cells_cap;
+  g->table_cap_total = (long long)table_cells;
   LVO_TRY(dalloc(c, &g->prob, (size_t)nprob));
-  LVO_TRY(dalloc(c, &g->table, (size_t)nprob * cells_cap + 1));
+  LVO_TRY(dalloc(c, &g->table, table_cells + 1));
   LVO_TRY(dalloc(c, &g->d_table_len, 1));
   LVO_TRY(dalloc(c, &g->rank, pts_total));
   LVO_TRY(dalloc(c, &g->pt_off, (size_t)nprob + 1));
   LVO_TRY(dalloc(c, &g->sorted_pts, pts_total));
   LVO_TRY(dalloc(c, &g->sorted_id, pts_total));
-  LVO_TRY(alloc_scan(c, &g->scan, (size_t)nprob * cells_cap + 1));
+  LVO_TRY(alloc_scan(c, &g->scan, table_cells + 1));
   return LVO_OK;
 }
 
@@ -145,11 +156,14 @@ __global__ void k_setup_grid_problems(GridProblem* prob, int nprob, const float4
   prob[p].want_cell = which == 0 ? (k >= 6 ? 8.0f : (k >= 4 ? 2.0f : (k == 1 ? 0.5f : 1.0f))) : cell;
   prob[p].want_cell_z = which == 0 ? (k >= 6 ? 8.0f : 2.0f) : 0.f;
   prob[p].mode = (which == 0 && (k == 2 || k == 3)) ? 1 : 0;
+  // share of the cell table (lvo_odo_cells_cap): the fine grids get 4 M cells, the (ring, azimuth) grids their fixed size, the 2 m
+  // and 8 m grids 1/8 and 1/64 of the fine share; a grid that does not fit doubles its cell edge (k_grid_setup)
+  prob[p].cells_cap = which == 0 ? (k < 2 ? (1 << 22) : (k < 4 ? LVO_AZ_BUCKETS * LVO_AZ_RINGS : (k < 6 ? (1 << 19) : (1 << 16)))) : 0;
   prob[p].clamp_xy = 0.f;
   prob[p].bbox_from = (which == 0 && k >= 4) ? p - k + (k & 1) : -1;   // middle / coarse grids reuse the fine grid's box
 }
 __global__ void k_setup_one_problem(GridProblem* prob, const float4* pts, const int* d_n, float cell, float clamp = 0.f) {
-  prob[0].pts = pts; prob[0].d_n = d_n; prob[0].want_cell = cell; prob[0].want_cell_z = 0.f; prob[0].mode = 0; prob[0].clamp_xy = clamp; prob[0].bbox_from = -1;
+  prob[0].pts = pts; prob[0].d_n = d_n; prob[0].want_cell = cell; prob[0].want_cell_z = 0.f; prob[0].mode = 0; prob[0].cells_cap = 0; prob[0].clamp_xy = clamp; prob[0].bbox_from = -1;
 }
 __global__ void k_vx_single_setup(VoxelEngine e, int n, float leaf) {
   if (blockIdx.x == 0 && threadIdx.x == 0) { *e.d_n = n; *e.d_nsegs = 1; e.seg_leaf[0] = leaf; }
@@ -198,10 +212,14 @@ __global__ void k_mapcloud_copy(MapArgs a, int lane, int surround, const unsigne
   }
 }
 
-int check_view(lvo_ctx* c, const lvo_cloud_view& v, size_t cap) {
+// xyz_only: the cloud is a raw sweep, whose intensity the path never reads (scanRegistration.cpp:132-133 converts to pcl::PointXYZ):
+// records of 12 bytes (packed x, y, z) are accepted and off_intensity is ignored.
+int check_view(lvo_ctx* c, const lvo_cloud_view& v, size_t cap, bool xyz_only = false) {
   if (v.n == 0) return LVO_OK;
-  if (!v.data || v.stride < 16 || v.stride > 64 || (v.stride & 3) || (v.off_xyz & 3) || (v.off_intensity & 3) || v.off_xyz + 12 > v.stride ||
-      v.off_intensity + 4 > v.stride) { lvo_set_error(c, "bad cloud view"); return LVO_E_BADARG; }
+  const bool bad_i = !xyz_only && ((v.off_intensity & 3) || v.off_intensity + 4 > v.stride);
+  if (!v.data || v.stride < (xyz_only ? 12u : 16u) || v.stride > 64 || (v.stride & 3) || (v.off_xyz & 3) || v.off_xyz + 12 > v.stride || bad_i) {
+    lvo_set_error(c, "bad cloud view"); return LVO_E_BADARG;
+  }
   if (v.n > cap) { lvo_set_error(c, "input cloud exceeds context capacity"); return LVO_E_CAPACITY; }
   return LVO_OK;
 }
@@ -237,34 +255,91 @@ int set_inputs(lvo_ctx* c) {
   LVO_CUDA_OK(c, cudaMemcpyAsync(c->d_in_n, c->h_in_n, sizeof(int) * c->lanes, cudaMemcpyHostToDevice, c->st));
   return LVO_OK;
 }
-void enqueue_extract(lvo_ctx* c, int stride, int off_xyz, int max_n) {
+void enqueue_extract(lvo_ctx* c, int stride, int off_xyz, int max_n, LvoStageTimer* tm) {
   ExtractArgs a = c->ex;
   a.in_stride = stride; a.in_off_xyz = off_xyz;
-  lvo_launch_extract(c->st, a, c->lanes, max_n, &c->launches);
+  nvtxRangePushA("scan registration");
+  lvo_launch_extract(c->st, a, c->lanes, max_n, &c->launches, tm);
+  nvtxRangePop();
 }
-void enqueue_odometry(lvo_ctx* c) { lvo_launch_odometry(c->st, c->odo, c->solve, c->cfg.outer_iters, c->lanes, &c->launches); }
-void enqueue_mapping(lvo_ctx* c, int from_odo, bool want_registered, bool time_knn) {
+void enqueue_odometry(lvo_ctx* c, LvoStageTimer* tm) {
+  nvtxRangePushA("laserOdometry");
+  lvo_launch_odometry(c->st, c->odo, c->solve, c->cfg.outer_iters, c->lanes, &c->launches, tm);
+  nvtxRangePop();
+}
+void enqueue_mapping(lvo_ctx* c, int from_odo, bool want_registered, LvoStageTimer* tm) {
   MapArgs a = c->map;
   a.from_odo = from_odo;
-  lvo_launch_mapping(c->st, a, c->solve, c->cfg.outer_iters, c->lanes, want_registered, &c->launches, time_knn ? c->knn_ev.data() : nullptr);
+  nvtxRangePushA("laserMapping");
+  lvo_launch_mapping(c->st, a, c->solve, c->cfg.outer_iters, c->lanes, want_registered, &c->launches, tm);
+  nvtxRangePop();
   c->map.gen ^= 1;
-  c->have_knn_events = time_knn;
 }
-void collect_knn_timing(lvo_ctx* c) {
-  c->tim.knn_ms = 0; c->tim.knn_launches = 0; c->tim.knn_bytes = 0;
-  if (!c->have_knn_events) return;
-  for (int o = 0; o < c->cfg.outer_iters; ++o) {
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, c->knn_ev[2 * o], c->knn_ev[2 * o + 1]) == cudaSuccess) c->tim.knn_ms += ms;
-    c->tim.knn_launches++;
-  }
+// plain-launch calls: begin / end of the sub-stage event list
+LvoStageTimer* stage_timer_begin(lvo_ctx* c, bool on) {
+  c->stage_tm.reset();
+  c->stage_tm.on = on;
+  return on ? &c->stage_tm : nullptr;
+}
+// after the stream has been synchronised: sub-stage sums into lvo_timings (stages that did not run keep 0)
+void collect_stage_timing(lvo_ctx* c, bool mapped) {
+  float ms[LVO_ST_COUNT]; int cnt[LVO_ST_COUNT];
+  c->stage_tm.collect(ms, cnt);
+  lvo_timings& t = c->tim;
+  t.reg_prepare_ms = ms[LVO_ST_REG_PREPARE]; t.reg_sort_ms = ms[LVO_ST_REG_SORT]; t.reg_separate_ms = ms[LVO_ST_REG_SEPARATE];
+  t.odo_association_ms = ms[LVO_ST_ODO_ASSOC]; t.odo_solver_ms = ms[LVO_ST_ODO_SOLVER]; t.odo_rest_ms = ms[LVO_ST_ODO_REST];
+  t.map_prepare_ms = ms[LVO_ST_MAP_PREPARE]; t.map_build_tree_ms = ms[LVO_ST_MAP_TREE];
+  t.map_association_ms = ms[LVO_ST_MAP_KNN] + ms[LVO_ST_MAP_FIT]; t.map_solver_ms = ms[LVO_ST_MAP_SOLVER];
+  t.map_optimization_ms = ms[LVO_ST_MAP_KNN] + ms[LVO_ST_MAP_FIT] + ms[LVO_ST_MAP_SOLVER];
+  t.map_add_points_ms = ms[LVO_ST_MAP_ADD]; t.map_filter_ms = ms[LVO_ST_MAP_FILTER]; t.map_pub_ms = ms[LVO_ST_MAP_PUB];
+  t.knn_ms = ms[LVO_ST_MAP_KNN]; t.knn_launches = cnt[LVO_ST_MAP_KNN]; t.knn_bytes = 0;
+  if (!mapped || !c->stage_tm.on) return;
   for (int l = 0; l < c->lanes; ++l) {
     const LaneState& s = c->h_ls[l];
     if (s.map_too_small) continue;
     const double M = (double)s.from_off[0][LVO_MAX_VALID] + (double)s.from_off[1][LVO_MAX_VALID];
     const double Q = (double)s.n_stack[0] + (double)s.n_stack[1];
-    c->tim.knn_bytes += s.stats.map_outer_executed * (16.0 * M + 56.0 * Q);   // iterations skipped at a fixed point search nothing
+    t.knn_bytes += s.stats.map_outer_executed * (16.0 * M + 56.0 * Q);   // iterations skipped at a fixed point search nothing
   }
+}
+// Host sweeps -> device staging buffer `buf` on stream `st`: lanes whose records are adjacent in host memory (one pinned slab per
+// sequence or per context, the usual producer layout) go up in ONE cudaMemcpyAsync per run instead of one per lane; a gap of up to
+// 64 KB between neighbours is copied along.  Sets h_in_ptr / h_in_n.  The staging buffer holds lanes * P * 32 bytes.
+int stage_sweeps(lvo_ctx* c, const lvo_cloud_view* sweeps, unsigned char* buf, cudaStream_t st) {
+  const int L = c->lanes;
+  c->span_order.resize(L);
+  for (int l = 0; l < L; ++l) c->span_order[l] = l;
+  std::sort(c->span_order.begin(), c->span_order.end(), [&](int a, int b) { return (uintptr_t)sweeps[a].data < (uintptr_t)sweeps[b].data; });
+  c->spans.clear();
+  const size_t cap = c->raw_lane_bytes * (size_t)L, max_gap = 64u << 10;
+  size_t dev_off = 0;
+  for (int k = 0; k < L; ++k) {
+    const int l = c->span_order[k];
+    const lvo_cloud_view& v = sweeps[l];
+    c->h_in_n[l] = (int)v.n;
+    if (v.n == 0) { c->h_in_ptr[l] = buf; continue; }
+    const unsigned char* h = (const unsigned char*)v.data;
+    const size_t bytes = v.n * v.stride;
+    bool merged = false;
+    if (!c->spans.empty()) {
+      lvo_ctx::Span& sp = c->spans.back();
+      const unsigned char* end = sp.host + sp.bytes;
+      if (h >= end && (size_t)(h - end) <= max_gap && sp.dev_off + (size_t)(h - sp.host) + bytes <= cap) {
+        sp.bytes = (size_t)(h - sp.host) + bytes;
+        c->h_in_ptr[l] = buf + sp.dev_off + (size_t)(h - sp.host);
+        dev_off = sp.dev_off + ((sp.bytes + 255) & ~(size_t)255);
+        merged = true;
+      }
+    }
+    if (!merged) {
+      if (dev_off + bytes > cap) { lvo_set_error(c, "sweeps exceed the staging buffer"); return LVO_E_CAPACITY; }
+      c->spans.push_back(lvo_ctx::Span{h, bytes, dev_off});
+      c->h_in_ptr[l] = buf + dev_off;
+      dev_off += (bytes + 255) & ~(size_t)255;
+    }
+  }
+  for (const lvo_ctx::Span& sp : c->spans) LVO_CUDA_OK(c, cudaMemcpyAsync(buf + sp.dev_off, sp.host, sp.bytes, cudaMemcpyHostToDevice, st));
+  return LVO_OK;
 }
 
 }  // namespace
@@ -282,6 +357,7 @@ void lvo_default_config(lvo_config* cfg) {
   cfg->skip_frame = 1; cfg->outer_iters = 10; cfg->lm_max_iters = 4; cfg->huber = 0.1; cfg->device = 0; cfg->lanes = 1;
   cfg->max_points = 0; cfg->max_map_corner = 0; cfg->max_map_surf = 0;
   cfg->distortion = 0;  // laserOdometry.cpp:67
+  cfg->debug_probes = 0;
 }
 
 int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
@@ -305,8 +381,6 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
   LVO_CUDA_OK(c, cudaStreamCreateWithFlags(&c->own_st, cudaStreamNonBlocking));
   c->st = c->own_st;
   for (int i = 0; i < 8; ++i) LVO_CUDA_OK(c, cudaEventCreate(&c->ev[i]));
-  c->knn_ev.resize(2 * LVO_MAX_OUTER);
-  for (auto& e : c->knn_ev) LVO_CUDA_OK(c, cudaEventCreate(&e));
   memset(&c->tim, 0, sizeof(c->tim));
 
   const int L = c->lanes;
@@ -359,13 +433,17 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
   od.ls = c->d_ls; od.lanes = L; od.distortion = cfg->distortion; od.full = ex.full;
   od.sharp = ex.sharp; od.less_sharp = ex.less_sharp; od.flat = ex.flat; od.less_flat = ex.less_flat;
   od.cap_sharp = c->cap_sharp; od.cap_lsharp = c->cap_lsharp; od.cap_flat = c->cap_flat; od.P = P;
+  // per-outer-iteration probe arrays: all LVO_MAX_OUTER iterations only when the parity probes are wanted, else the current and the previous one
+  const int slots = cfg->debug_probes ? LVO_MAX_OUTER : 2;
+  od.slots = slots;
   LVO_TRY(dalloc(c, &od.corner_last, (size_t)L * c->cap_lsharp)); LVO_TRY(dalloc(c, &od.surf_last, (size_t)L * P));
   od.factor_cap = std::max(c->cap_sharp + c->cap_flat, c->cap_lsharp + P);
   LVO_TRY(dalloc(c, &od.factors, (size_t)L * od.factor_cap));
   LVO_TRY(dalloc(c, &od.slow_list, (size_t)L * (c->cap_sharp + c->cap_flat))); LVO_TRY(dalloc(c, &od.slow_cnt, (size_t)L));
-  LVO_TRY(dalloc(c, &od.corner_corr, (size_t)L * LVO_MAX_OUTER * c->cap_sharp * 2));
-  LVO_TRY(dalloc(c, &od.plane_corr, (size_t)L * LVO_MAX_OUTER * c->cap_flat * 3));
-  LVO_TRY(alloc_grid(c, &od.grid, 8 * L, 1 << 22, (size_t)4 * L * (c->cap_lsharp + P), P));
+  LVO_TRY(dalloc(c, &od.corner_corr, (size_t)L * slots * c->cap_sharp * 2));
+  LVO_TRY(dalloc(c, &od.plane_corr, (size_t)L * slots * c->cap_flat * 3));
+  const size_t odo_cells = 2 * ((size_t)(1 << 22) + (size_t)LVO_AZ_BUCKETS * LVO_AZ_RINGS + (1 << 19) + (1 << 16));   // per lane, see k_setup_grid_problems
+  LVO_TRY(alloc_grid(c, &od.grid, 8 * L, 1 << 22, (size_t)4 * L * (c->cap_lsharp + P), P, odo_cells * L));
   k_setup_grid_problems<<<lvo_div_up(8 * L, 64), 64, 0, c->st>>>(od.grid.prob, 8 * L, od.corner_last, (size_t)c->cap_lsharp, od.surf_last, (size_t)P, c->d_ls, 0, 1.0f);
 
   // ---- mapping
@@ -373,7 +451,7 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
   memset(&mp, 0, sizeof(mp));
   mp.ls = c->d_ls; mp.lanes = L; mp.leaf[0] = (float)cfg->line_res; mp.leaf[1] = (float)cfg->plane_res;
   mp.in_pts[0] = ex.less_sharp; mp.in_pts[1] = ex.less_flat; mp.in_cap[0] = c->cap_lsharp; mp.in_cap[1] = P;
-  mp.full = ex.full; mp.P = P; mp.gen = 0;
+  mp.full = ex.full; mp.P = P; mp.gen = 0; mp.slots = slots;
   for (int t = 0; t < 2; ++t) {
     mp.map_cap[t] = mapc[t];
     for (int g = 0; g < 2; ++g) {
@@ -382,8 +460,8 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
     }
     LVO_TRY(dalloc(c, &mp.from_map[t], (size_t)L * mapc[t], false));
     LVO_TRY(dalloc(c, &mp.stack[t], (size_t)L * mp.in_cap[t]));
-    LVO_TRY(dalloc(c, &mp.knn_ind[t], (size_t)L * LVO_MAX_OUTER * mp.in_cap[t] * 5));
-    LVO_TRY(dalloc(c, &mp.fac_valid[t], (size_t)L * LVO_MAX_OUTER * mp.in_cap[t]));
+    LVO_TRY(dalloc(c, &mp.knn_ind[t], (size_t)L * slots * mp.in_cap[t] * 5));
+    LVO_TRY(dalloc(c, &mp.fac_valid[t], (size_t)L * slots * mp.in_cap[t]));
   }
   LVO_TRY(alloc_grid(c, &mp.grid, 2 * L, 1 << 22, (size_t)L * ((size_t)mapc[0] + mapc[1]), std::max(mapc[0], mapc[1])));
   k_setup_grid_problems<<<lvo_div_up(2 * L, 64), 64, 0, c->st>>>(mp.grid.prob, 2 * L, mp.from_map[0], (size_t)mapc[0], mp.from_map[1], (size_t)mapc[1], c->d_ls, 1, 1.0f);
@@ -428,7 +506,7 @@ int lvo_destroy(lvo_ctx* c) {
   for (void* p : c->pinned) cudaFreeHost(p);
   destroy_graphs(c);
   if (c->copy_st) { cudaStreamSynchronize(c->copy_st); cudaStreamDestroy(c->copy_st); cudaEventDestroy(c->copy_ev); cudaEventDestroy(c->compute_ev); }
-  if (c->own_st) { for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]); for (auto& e : c->knn_ev) cudaEventDestroy(e); cudaStreamDestroy(c->own_st); }
+  if (c->own_st) { for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]); c->stage_tm.destroy(); cudaStreamDestroy(c->own_st); }
   delete c;
   return LVO_OK;
 }
@@ -445,6 +523,7 @@ size_t lvo_state_bytes(void) { return sizeof(LaneState); }
 int lvo_set_option(lvo_ctx* c, int option, int value) {
   if (!c) return LVO_E_BADARG;
   if (option == LVO_OPT_GRAPHS) { c->opt_graphs = value; return LVO_OK; }
+  if (option == LVO_OPT_STAGE_TIMING) { c->opt_stage_timing = value ? 1 : 0; return LVO_OK; }
   if (option == LVO_OPT_FIXPOINT_SKIP) {   // a kernel argument: captured graphs hold the old value
     if (c->st) cudaStreamSynchronize(c->st);
     destroy_graphs(c);
@@ -466,16 +545,20 @@ int lvo_get_timings(const lvo_ctx* c, lvo_timings* out) { if (!c || !out) return
 int lvo_extract_features(lvo_ctx* c, lvo_cloud_view sweep, lvo_cloud_out* full, lvo_cloud_out* sharp, lvo_cloud_out* less_sharp, lvo_cloud_out* flat,
                          lvo_cloud_out* less_flat) {
   if (!c) return LVO_E_BADARG;
-  LVO_TRY(check_view(c, sweep, (size_t)c->P));
+  LVO_TRY(check_view(c, sweep, (size_t)c->P, true));
+  if (c->pending) { lvo_set_error(c, "lvo_wait has not been called for the last *_async step"); return LVO_E_STATE; }
   c->launches = 0;
   cudaEventRecord(c->ev[0], c->st);
   if (sweep.n) LVO_CUDA_OK(c, cudaMemcpyAsync(c->d_raw, sweep.data, sweep.n * sweep.stride, cudaMemcpyHostToDevice, c->st));
   for (int l = 0; l < c->lanes; ++l) { c->h_in_ptr[l] = c->d_raw + c->raw_lane_bytes * l; c->h_in_n[l] = l == 0 ? (int)sweep.n : 0; }
   LVO_TRY(set_inputs(c));
-  enqueue_extract(c, sweep.n ? (int)sweep.stride : 16, sweep.n ? (int)sweep.off_xyz : 0, (int)sweep.n);
+  LvoStageTimer* tm = stage_timer_begin(c, true);
+  enqueue_extract(c, sweep.n ? (int)sweep.stride : 16, sweep.n ? (int)sweep.off_xyz : 0, (int)sweep.n, tm);
+  c->stage_tm.stop(c->st);
   cudaEventRecord(c->ev[1], c->st);
   LVO_TRY(sync_state(c));
   cudaEventElapsedTime(&c->tim.extract_ms, c->ev[0], c->ev[1]);
+  collect_stage_timing(c, false);
   const LaneState& s = c->h_ls[0];
   int r = LVO_OK, q;
   if ((q = download_cloud(c, c->ex.full, (size_t)s.n_kept, full)) != LVO_OK) r = q;
@@ -491,6 +574,7 @@ int lvo_extract_features(lvo_ctx* c, lvo_cloud_view sweep, lvo_cloud_out* full, 
 int lvo_scan_to_scan(lvo_ctx* c, lvo_cloud_view sharp, lvo_cloud_view less_sharp, lvo_cloud_view flat, lvo_cloud_view less_flat, lvo_pose* T_last_curr,
                      lvo_pose* T_w_curr) {
   if (!c) return LVO_E_BADARG;
+  if (c->pending) { lvo_set_error(c, "lvo_wait has not been called for the last *_async step"); return LVO_E_STATE; }
   LVO_TRY(check_view(c, sharp, (size_t)c->cap_sharp)); LVO_TRY(check_view(c, less_sharp, (size_t)c->cap_lsharp));
   LVO_TRY(check_view(c, flat, (size_t)c->cap_flat)); LVO_TRY(check_view(c, less_flat, (size_t)c->P));
   c->launches = 0;
@@ -500,11 +584,14 @@ int lvo_scan_to_scan(lvo_ctx* c, lvo_cloud_view sharp, lvo_cloud_view less_sharp
   SetCounts sc; memset(&sc, 0, sizeof(sc));
   sc.what = 0; sc.v[0] = (int)sharp.n; sc.v[1] = (int)less_sharp.n; sc.v[2] = (int)flat.n; sc.v[3] = (int)less_flat.n;
   k_set_lane<<<1, 1, 0, c->st>>>(c->d_ls, 0, sc);
-  c->odo.corner_corr = c->odo.corner_corr; c->solve.trace = c->d_trace[0];
-  enqueue_odometry(c);
+  c->solve.trace = c->d_trace[0];
+  LvoStageTimer* tm = stage_timer_begin(c, true);
+  enqueue_odometry(c, tm);
+  c->stage_tm.stop(c->st);
   cudaEventRecord(c->ev[3], c->st);
   LVO_TRY(sync_state(c));
   cudaEventElapsedTime(&c->tim.odometry_ms, c->ev[2], c->ev[3]);
+  collect_stage_timing(c, false);
   const LaneState& s = c->h_ls[0];
   pose_out(T_last_curr, s.para_q, s.para_t);
   pose_out(T_w_curr, s.q_w, s.t_w);
@@ -515,6 +602,7 @@ int lvo_scan_to_scan(lvo_ctx* c, lvo_cloud_view sharp, lvo_cloud_view less_sharp
 int lvo_scan_to_map(lvo_ctx* c, lvo_cloud_view corner_last, lvo_cloud_view surf_last, lvo_cloud_view full_or_null, const lvo_pose* T_wodom_curr,
                     lvo_pose* T_wmap_curr, lvo_cloud_out* registered_or_null) {
   if (!c || !T_wodom_curr) return LVO_E_BADARG;
+  if (c->pending) { lvo_set_error(c, "lvo_wait has not been called for the last *_async step"); return LVO_E_STATE; }
   LVO_TRY(check_view(c, corner_last, (size_t)c->cap_lsharp)); LVO_TRY(check_view(c, surf_last, (size_t)c->P));
   LVO_TRY(check_view(c, full_or_null, (size_t)c->P));
   c->launches = 0;
@@ -528,11 +616,13 @@ int lvo_scan_to_map(lvo_ctx* c, lvo_cloud_view corner_last, lvo_cloud_view surf_
   for (int k = 0; k < 3; ++k) sc.pose[4 + k] = T_wodom_curr->t[k];
   k_set_lane<<<1, 1, 0, c->st>>>(c->d_ls, 0, sc);
   c->solve.trace = c->d_trace[1];
-  enqueue_mapping(c, 0, want_reg, true);
+  LvoStageTimer* tm = stage_timer_begin(c, true);
+  enqueue_mapping(c, 0, want_reg, tm);
+  c->stage_tm.stop(c->st);
   cudaEventRecord(c->ev[5], c->st);
   LVO_TRY(sync_state(c));
   cudaEventElapsedTime(&c->tim.mapping_ms, c->ev[4], c->ev[5]);
-  collect_knn_timing(c);
+  collect_stage_timing(c, true);
   const LaneState& s = c->h_ls[0];
   pose_out(T_wmap_curr, s.map_x, s.map_x + 4);
   int r = s.map_status;
@@ -548,74 +638,98 @@ int lvo_scan_to_map(lvo_ctx* c, lvo_cloud_view corner_last, lvo_cloud_view surf_
 
 // ---------------------------------------------------------------------------------------------------------------
 // Upload of the next frame into the staging buffer that is not in use, on the copy stream (lvo_step_batch_pipelined).  That buffer
-// was last read by the previous frame's kernels, which have completed (every call ends synchronised).
+// was last read by the previous frame's kernels, which have completed (every call ends synchronised).  Issued BEFORE this frame's
+// kernels are enqueued, so that the copy engine starts at once; the uploads are merged per run of adjacent lanes (stage_sweeps).
 static int enqueue_prefetch(lvo_ctx* c) {
   const lvo_cloud_view* next = c->pending_next;
   c->pending_next = nullptr;
   if (!next) return LVO_OK;
   unsigned char* bufs[2] = {c->d_raw, c->d_raw2};
-  unsigned char* nb = bufs[c->raw_cur ^ 1];
-  for (int l = 0; l < c->lanes; ++l)
-    if (next[l].n) LVO_CUDA_OK(c, cudaMemcpyAsync(nb + c->raw_lane_bytes * l, next[l].data, next[l].n * next[l].stride, cudaMemcpyHostToDevice, c->copy_st));
+  // stage_sweeps fills h_in_ptr / h_in_n for the NEXT frame: keep this frame's, which set_inputs has not uploaded yet
+  std::vector<const unsigned char*> keep_ptr(c->h_in_ptr, c->h_in_ptr + c->lanes);
+  std::vector<int> keep_n(c->h_in_n, c->h_in_n + c->lanes);
+  const int r = stage_sweeps(c, next, bufs[c->raw_cur ^ 1], c->copy_st);
+  c->next_in_ptr.assign(c->h_in_ptr, c->h_in_ptr + c->lanes);
+  std::copy(keep_ptr.begin(), keep_ptr.end(), c->h_in_ptr);
+  std::copy(keep_n.begin(), keep_n.end(), c->h_in_n);
+  if (r != LVO_OK) return r;
   LVO_CUDA_OK(c, cudaEventRecord(c->copy_ev, c->copy_st));
   c->prefetched.assign(next, next + c->lanes);
   return LVO_OK;
 }
 
-static int step_common(lvo_ctx* c, int stride, int off_xyz, int max_n, lvo_pose* T_wodom, lvo_pose* T_wmap) {
+// Enqueue one frame for every lane (no host synchronisation).
+static int step_enqueue(lvo_ctx* c, int stride, int off_xyz, int max_n) {
+  if (c->pending) { lvo_set_error(c, "lvo_wait has not been called for the last *_async step"); return LVO_E_STATE; }
   c->launches = 0;
+  LVO_TRY(enqueue_prefetch(c));
   LVO_TRY(set_inputs(c));
   const bool do_map = (c->frame % c->cfg.skip_frame) == 0;  // laserOdometry.cpp:643
   const bool want_graph = c->opt_graphs == 1 || (c->opt_graphs < 0 && c->lanes <= 8);
   const bool use_graph = want_graph && c->st != nullptr;    // the legacy default stream cannot be captured
+  nvtxRangePushA("lvo_step");
   if (use_graph) {
     if (c->graph_stride != stride || c->graph_off != off_xyz) { destroy_graphs(c); c->graph_stride = stride; c->graph_off = off_xyz; }
     const int gen = c->map.gen;
+    stage_timer_begin(c, false);
     cudaEventRecord(c->ev[0], c->st);
     if (!c->graph_exec[do_map][gen]) {
       // capture one frame: the launch sequence is static (grids from capacities, sizes read from device memory)
       cudaGraph_t graph = nullptr;
       LVO_CUDA_OK(c, cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
-      enqueue_extract(c, stride, off_xyz, c->P);
+      enqueue_extract(c, stride, off_xyz, c->P, nullptr);
       c->solve.trace = c->d_trace[0];
-      enqueue_odometry(c);
-      if (do_map) { c->solve.trace = c->d_trace[1]; enqueue_mapping(c, 1, true, false); }
+      enqueue_odometry(c, nullptr);
+      if (do_map) { c->solve.trace = c->d_trace[1]; enqueue_mapping(c, 1, true, nullptr); }
       cudaError_t e = cudaStreamEndCapture(c->st, &graph);
       if (do_map) c->map.gen = gen;   // enqueue_mapping flipped it; the flip belongs to the execution below
-      if (e != cudaSuccess || !graph) { lvo_set_error(c, std::string("graph capture: ") + cudaGetErrorString(e)); return LVO_E_CUDA; }
+      if (e != cudaSuccess || !graph) { nvtxRangePop(); lvo_set_error(c, std::string("graph capture: ") + cudaGetErrorString(e)); return LVO_E_CUDA; }
       e = cudaGraphInstantiate(&c->graph_exec[do_map][gen], graph, 0);
       cudaGraphDestroy(graph);
-      if (e != cudaSuccess) { lvo_set_error(c, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); return LVO_E_CUDA; }
+      if (e != cudaSuccess) { nvtxRangePop(); lvo_set_error(c, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); return LVO_E_CUDA; }
       c->graph_launches[do_map][gen] = c->launches;
     }
-    LVO_CUDA_OK(c, cudaGraphLaunch(c->graph_exec[do_map][gen], c->st));
+    cudaError_t ge = cudaGraphLaunch(c->graph_exec[do_map][gen], c->st);
+    if (ge != cudaSuccess) { nvtxRangePop(); lvo_set_error(c, std::string("cudaGraphLaunch: ") + cudaGetErrorString(ge)); return LVO_E_CUDA; }
     c->launches = c->graph_launches[do_map][gen];
     if (do_map) c->map.gen = gen ^ 1;
-    c->have_knn_events = false;
     cudaEventRecord(c->ev[3], c->st);
-    c->frame++;
-    LVO_TRY(enqueue_prefetch(c));
-    LVO_TRY(sync_state(c));
-    c->tim.extract_ms = c->tim.odometry_ms = 0.f;     // per-stage times are only available with plain launches
-    cudaEventElapsedTime(&c->tim.mapping_ms, c->ev[0], c->ev[3]);
-    collect_knn_timing(c);
   } else {
+    LvoStageTimer* tm = stage_timer_begin(c, c->opt_stage_timing != 0);
     cudaEventRecord(c->ev[0], c->st);
-    enqueue_extract(c, stride, off_xyz, max_n);
+    enqueue_extract(c, stride, off_xyz, max_n, tm);
     cudaEventRecord(c->ev[1], c->st);
     c->solve.trace = c->d_trace[0];
-    enqueue_odometry(c);
+    enqueue_odometry(c, tm);
     cudaEventRecord(c->ev[2], c->st);
-    if (do_map) { c->solve.trace = c->d_trace[1]; enqueue_mapping(c, 1, true, true); }
+    if (do_map) { c->solve.trace = c->d_trace[1]; enqueue_mapping(c, 1, true, tm); }
+    c->stage_tm.stop(c->st);
     cudaEventRecord(c->ev[3], c->st);
-    c->frame++;
-    LVO_TRY(enqueue_prefetch(c));
-    LVO_TRY(sync_state(c));
+  }
+  nvtxRangePop();
+  c->frame++;
+  // the lane states come back on the same stream; lvo_wait only has to synchronise
+  LVO_CUDA_OK(c, cudaMemcpyAsync(c->h_ls, c->d_ls, sizeof(LaneState) * c->lanes, cudaMemcpyDeviceToHost, c->st));
+  c->pending = true; c->pending_do_map = do_map; c->pending_graph = use_graph;
+  return LVO_OK;
+}
+
+// Wait for the frame enqueued by step_enqueue and deliver its results.
+static int step_finish(lvo_ctx* c, lvo_pose* T_wodom, lvo_pose* T_wmap) {
+  if (!c->pending) { lvo_set_error(c, "lvo_wait without a step in flight"); return LVO_E_STATE; }
+  c->pending = false;
+  const bool do_map = c->pending_do_map;
+  LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
+  LVO_CUDA_OK(c, cudaGetLastError());
+  if (c->pending_graph) {
+    c->tim.extract_ms = c->tim.odometry_ms = 0.f;     // per-stage times are only available with plain launches
+    cudaEventElapsedTime(&c->tim.mapping_ms, c->ev[0], c->ev[3]);
+  } else {
     cudaEventElapsedTime(&c->tim.extract_ms, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&c->tim.odometry_ms, c->ev[1], c->ev[2]);
     cudaEventElapsedTime(&c->tim.mapping_ms, c->ev[2], c->ev[3]);
-    if (do_map) collect_knn_timing(c);
   }
+  collect_stage_timing(c, do_map);
   int worst = LVO_OK;
   for (int l = 0; l < c->lanes; ++l) {
     const LaneState& s = c->h_ls[l];
@@ -642,67 +756,78 @@ static int step_common(lvo_ctx* c, int stride, int off_xyz, int max_n, lvo_pose*
   return worst;
 }
 
-int lvo_step_batch(lvo_ctx* c, const lvo_cloud_view* sweeps, lvo_pose* T_wodom, lvo_pose* T_wmap) {
-  if (!c || !sweeps) return LVO_E_BADARG;
-  int max_n = 0;
+static int check_sweeps(lvo_ctx* c, const lvo_cloud_view* sweeps, int* max_n) {
+  *max_n = 0;
   for (int l = 0; l < c->lanes; ++l) {
-    LVO_TRY(check_view(c, sweeps[l], (size_t)c->P));
+    LVO_TRY(check_view(c, sweeps[l], (size_t)c->P, true));
     if (sweeps[l].stride != sweeps[0].stride || sweeps[l].off_xyz != sweeps[0].off_xyz) { lvo_set_error(c, "all lanes must share one point layout"); return LVO_E_BADARG; }
     if (sweeps[l].stride > 32) { lvo_set_error(c, "stride > 32 unsupported in lvo_step_batch"); return LVO_E_BADARG; }
-    max_n = std::max(max_n, (int)sweeps[l].n);
+    *max_n = std::max(*max_n, (int)sweeps[l].n);
   }
-  for (int l = 0; l < c->lanes; ++l) {
-    unsigned char* dst = c->d_raw + c->raw_lane_bytes * l;
-    if (sweeps[l].n) LVO_CUDA_OK(c, cudaMemcpyAsync(dst, sweeps[l].data, sweeps[l].n * sweeps[l].stride, cudaMemcpyHostToDevice, c->st));
-    c->h_in_ptr[l] = dst; c->h_in_n[l] = (int)sweeps[l].n;
-  }
-  return step_common(c, (int)sweeps[0].stride, (int)sweeps[0].off_xyz, max_n, T_wodom, T_wmap);
+  return LVO_OK;
+}
+
+int lvo_step_batch_async(lvo_ctx* c, const lvo_cloud_view* sweeps) {
+  if (!c || !sweeps) return LVO_E_BADARG;
+  if (c->pending) { lvo_set_error(c, "lvo_wait has not been called for the last *_async step"); return LVO_E_STATE; }
+  int max_n = 0;
+  LVO_TRY(check_sweeps(c, sweeps, &max_n));
+  LVO_TRY(stage_sweeps(c, sweeps, c->d_raw, c->st));
+  return step_enqueue(c, (int)sweeps[0].stride, (int)sweeps[0].off_xyz, max_n);
+}
+int lvo_wait(lvo_ctx* c, lvo_pose* T_wodom, lvo_pose* T_wmap) {
+  if (!c) return LVO_E_BADARG;
+  return step_finish(c, T_wodom, T_wmap);
+}
+int lvo_step_batch(lvo_ctx* c, const lvo_cloud_view* sweeps, lvo_pose* T_wodom, lvo_pose* T_wmap) {
+  LVO_TRY(lvo_step_batch_async(c, sweeps));
+  return step_finish(c, T_wodom, T_wmap);
 }
 
 int lvo_step_batch_pipelined(lvo_ctx* c, const lvo_cloud_view* sweeps, const lvo_cloud_view* next, lvo_pose* T_wodom, lvo_pose* T_wmap) {
   if (!c || !sweeps) return LVO_E_BADARG;
+  if (c->pending) { lvo_set_error(c, "lvo_wait has not been called for the last *_async step"); return LVO_E_STATE; }
   if (!c->copy_st) {
     LVO_CUDA_OK(c, cudaStreamCreateWithFlags(&c->copy_st, cudaStreamNonBlocking));
     LVO_CUDA_OK(c, cudaEventCreateWithFlags(&c->copy_ev, cudaEventDisableTiming));
     LVO_CUDA_OK(c, cudaEventCreateWithFlags(&c->compute_ev, cudaEventDisableTiming));
     LVO_TRY(dalloc(c, &c->d_raw2, c->raw_lane_bytes * c->lanes, false));
   }
-  int max_n = 0;
-  for (int l = 0; l < c->lanes; ++l) {
-    LVO_TRY(check_view(c, sweeps[l], (size_t)c->P));
-    if (next) LVO_TRY(check_view(c, next[l], (size_t)c->P));
-    if (sweeps[l].stride != sweeps[0].stride || sweeps[l].off_xyz != sweeps[0].off_xyz || sweeps[l].stride > 32) { lvo_set_error(c, "all lanes must share one point layout (stride <= 32)"); return LVO_E_BADARG; }
-    max_n = std::max(max_n, (int)sweeps[l].n);
-  }
+  int max_n = 0, max_next = 0;
+  LVO_TRY(check_sweeps(c, sweeps, &max_n));
+  if (next) LVO_TRY(check_sweeps(c, next, &max_next));
   bool hit = (int)c->prefetched.size() == c->lanes;
   for (int l = 0; hit && l < c->lanes; ++l) hit = c->prefetched[l].data == sweeps[l].data && c->prefetched[l].n == sweeps[l].n && c->prefetched[l].stride == sweeps[l].stride;
   unsigned char* bufs[2] = {c->d_raw, c->d_raw2};
   if (hit) {
     c->raw_cur ^= 1;                                         // the prefetched buffer becomes current
     LVO_CUDA_OK(c, cudaStreamWaitEvent(c->st, c->copy_ev, 0));
+    for (int l = 0; l < c->lanes; ++l) { c->h_in_ptr[l] = c->next_in_ptr[l]; c->h_in_n[l] = (int)sweeps[l].n; }
   } else {
-    for (int l = 0; l < c->lanes; ++l)
-      if (sweeps[l].n) LVO_CUDA_OK(c, cudaMemcpyAsync(bufs[c->raw_cur] + c->raw_lane_bytes * l, sweeps[l].data, sweeps[l].n * sweeps[l].stride, cudaMemcpyHostToDevice, c->st));
+    LVO_TRY(stage_sweeps(c, sweeps, bufs[c->raw_cur], c->st));
   }
   c->prefetched.clear();
-  for (int l = 0; l < c->lanes; ++l) { c->h_in_ptr[l] = bufs[c->raw_cur] + c->raw_lane_bytes * l; c->h_in_n[l] = (int)sweeps[l].n; }
-  // the prefetch of `next` is enqueued by step_common AFTER this frame's kernels (enqueue_prefetch), so that the compute stream
-  // does not sit idle while the host issues one copy per lane
   c->pending_next = next;
-  const int r = step_common(c, (int)sweeps[0].stride, (int)sweeps[0].off_xyz, max_n, T_wodom, T_wmap);
+  int r = step_enqueue(c, (int)sweeps[0].stride, (int)sweeps[0].off_xyz, max_n);
   c->pending_next = nullptr;  // an early error return must not leave a pointer for a later call
-  return r;
+  if (r != LVO_OK) return r;
+  return step_finish(c, T_wodom, T_wmap);
 }
 
-int lvo_step_batch_dev(lvo_ctx* c, const lvo_point* const* d_sweeps, const size_t* n, lvo_pose* T_wodom, lvo_pose* T_wmap) {
+int lvo_step_batch_dev_async(lvo_ctx* c, const lvo_point* const* d_sweeps, const size_t* n) {
   if (!c || !d_sweeps || !n) return LVO_E_BADARG;
+  if (c->pending) { lvo_set_error(c, "lvo_wait has not been called for the last *_async step"); return LVO_E_STATE; }
   int max_n = 0;
   for (int l = 0; l < c->lanes; ++l) {
     if (n[l] > (size_t)c->P) { lvo_set_error(c, "input cloud exceeds context capacity"); return LVO_E_CAPACITY; }
     c->h_in_ptr[l] = (const unsigned char*)d_sweeps[l]; c->h_in_n[l] = (int)n[l];
     max_n = std::max(max_n, (int)n[l]);
   }
-  return step_common(c, 16, 0, max_n, T_wodom, T_wmap);
+  return step_enqueue(c, 16, 0, max_n);
+}
+int lvo_step_batch_dev(lvo_ctx* c, const lvo_point* const* d_sweeps, const size_t* n, lvo_pose* T_wodom, lvo_pose* T_wmap) {
+  LVO_TRY(lvo_step_batch_dev_async(c, d_sweeps, n));
+  return step_finish(c, T_wodom, T_wmap);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -818,6 +943,7 @@ int lvo_probe_fetch(lvo_ctx* c, int lane, int what, void* out, size_t cap_bytes,
   const void* src = nullptr; size_t bytes = 0;
   // 2-D probes (outer x rows) are gathered row block by row block below
   size_t row_bytes = 0, row_stride = 0; int rows = 1;
+  bool per_outer = false;   // probe arrays that keep every outer iteration only with lvo_config::debug_probes
   switch (what) {
     case LVO_P_FULL: src = ex.full + (size_t)lane * P; bytes = (size_t)s.n_kept * 16; break;
     case LVO_P_CURVATURE: src = ex.curv + (size_t)lane * P; bytes = (size_t)s.n_kept * 4; break;
@@ -830,8 +956,8 @@ int lvo_probe_fetch(lvo_ctx* c, int lane, int what, void* out, size_t cap_bytes,
     case LVO_P_LESS_SHARP: src = ex.less_sharp + (size_t)lane * c->cap_lsharp; bytes = (size_t)s.n_less_sharp * 16; break;
     case LVO_P_FLAT: src = ex.flat + (size_t)lane * c->cap_flat; bytes = (size_t)s.n_flat * 16; break;
     case LVO_P_LESS_FLAT: src = ex.less_flat + (size_t)lane * P; bytes = (size_t)s.n_less_flat * 16; break;
-    case LVO_P_ODO_CORNER_CORR: src = c->odo.corner_corr + (size_t)lane * LVO_MAX_OUTER * c->cap_sharp * 2; rows = O; row_bytes = (size_t)s.n_sharp * 8; row_stride = (size_t)c->cap_sharp * 8; break;
-    case LVO_P_ODO_PLANE_CORR: src = c->odo.plane_corr + (size_t)lane * LVO_MAX_OUTER * c->cap_flat * 3; rows = O; row_bytes = (size_t)s.n_flat * 12; row_stride = (size_t)c->cap_flat * 12; break;
+    case LVO_P_ODO_CORNER_CORR: src = c->odo.corner_corr + (size_t)lane * c->odo.slots * c->cap_sharp * 2; rows = O; per_outer = true; row_bytes = (size_t)s.n_sharp * 8; row_stride = (size_t)c->cap_sharp * 8; break;
+    case LVO_P_ODO_PLANE_CORR: src = c->odo.plane_corr + (size_t)lane * c->odo.slots * c->cap_flat * 3; rows = O; per_outer = true; row_bytes = (size_t)s.n_flat * 12; row_stride = (size_t)c->cap_flat * 12; break;
     case LVO_P_ODO_LM_TRACE: case LVO_P_MAP_LM_TRACE: {
       const double* base = c->d_trace[what == LVO_P_ODO_LM_TRACE ? 0 : 1] + (size_t)lane * LVO_MAX_OUTER * (LVO_MAX_LM + 1) * LVO_TRACE_W;
       src = base; rows = O; row_bytes = (size_t)(c->cfg.lm_max_iters + 1) * LVO_TRACE_W * 8; row_stride = (size_t)(LVO_MAX_LM + 1) * LVO_TRACE_W * 8; break;
@@ -842,15 +968,16 @@ int lvo_probe_fetch(lvo_ctx* c, int lane, int what, void* out, size_t cap_bytes,
     case LVO_P_MAP_SURF_FROM_MAP: src = c->map.from_map[1] + (size_t)lane * c->map.map_cap[1]; bytes = (size_t)s.from_off[1][LVO_MAX_VALID] * 16; break;
     case LVO_P_MAP_CORNER_KNN: case LVO_P_MAP_SURF_KNN: {
       const int t = what == LVO_P_MAP_CORNER_KNN ? 0 : 1;
-      src = c->map.knn_ind[t] + (size_t)lane * LVO_MAX_OUTER * c->map.in_cap[t] * 5; rows = O; row_bytes = (size_t)s.n_stack[t] * 20; row_stride = (size_t)c->map.in_cap[t] * 20; break;
+      src = c->map.knn_ind[t] + (size_t)lane * c->map.slots * c->map.in_cap[t] * 5; rows = O; per_outer = true; row_bytes = (size_t)s.n_stack[t] * 20; row_stride = (size_t)c->map.in_cap[t] * 20; break;
     }
     case LVO_P_MAP_CORNER_VALID: case LVO_P_MAP_SURF_VALID: {
       const int t = what == LVO_P_MAP_CORNER_VALID ? 0 : 1;
-      src = c->map.fac_valid[t] + (size_t)lane * LVO_MAX_OUTER * c->map.in_cap[t]; rows = O; row_bytes = (size_t)s.n_stack[t] * 4; row_stride = (size_t)c->map.in_cap[t] * 4; break;
+      src = c->map.fac_valid[t] + (size_t)lane * c->map.slots * c->map.in_cap[t]; rows = O; per_outer = true; row_bytes = (size_t)s.n_stack[t] * 4; row_stride = (size_t)c->map.in_cap[t] * 4; break;
     }
     case LVO_P_REGISTERED: src = c->map.registered + (size_t)lane * P; bytes = (size_t)s.n_kept * 16; break;
     default: return LVO_E_BADARG;
   }
+  if (per_outer && !c->cfg.debug_probes) { lvo_set_error(c, "per-outer-iteration probes need lvo_config::debug_probes = 1"); return LVO_E_STATE; }
   if (rows > 1 || row_bytes) bytes = row_bytes * rows;
   if (n_bytes) *n_bytes = bytes;
   if (!out) return LVO_OK;  // size query
@@ -946,7 +1073,7 @@ int lvo_knn(lvo_ctx* c, lvo_cloud_view cloud, lvo_cloud_view queries, int K, flo
 __global__ void k_setup_batch_problems(GridProblem* prob, int S, const float4* maps, const unsigned* m_off, const int* m_cnt, float cell) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= S) return;
-  prob[p].pts = maps + m_off[p]; prob[p].d_n = m_cnt + p; prob[p].want_cell = cell; prob[p].want_cell_z = 0.f; prob[p].mode = 0; prob[p].clamp_xy = 0.f; prob[p].bbox_from = -1;
+  prob[p].pts = maps + m_off[p]; prob[p].d_n = m_cnt + p; prob[p].want_cell = cell; prob[p].want_cell_z = 0.f; prob[p].mode = 0; prob[p].cells_cap = 0; prob[p].clamp_xy = 0.f; prob[p].bbox_from = -1;
 }
 
 int lvo_depth_associate(lvo_ctx* c, lvo_cloud_view sweep, const lvo_camera* cam, const float* keypoints_uv, size_t n_kp, float* depth_out, int* valid_out,

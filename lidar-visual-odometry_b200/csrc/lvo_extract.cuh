@@ -922,16 +922,19 @@ __global__ void __launch_bounds__(512) k_feature_compact(ExtractArgs a) {
   }
 }
 
-static inline void lvo_launch_extract(cudaStream_t st, const ExtractArgs& a, int lanes, int max_n_in, long long* launches) {
+static inline void lvo_launch_extract(cudaStream_t st, const ExtractArgs& a, int lanes, int max_n_in, long long* launches, LvoStageTimer* tm = nullptr) {
   if (max_n_in < 1) max_n_in = 1;
   dim3 gpts(lvo_div_up(max_n_in, LVO_EX_THREADS), lanes);
+  LVO_MARK(tm, LVO_ST_REG_PREPARE, st);
   k_extract_reset<<<lanes, 32, 0, st>>>(a);
   k_classify<<<gpts, LVO_EX_THREADS, 0, st>>>(a);
   k_ring_count<<<gpts, LVO_EX_THREADS, 0, st>>>(a);
   k_ring_offsets<<<lanes, LVO_MAX_RINGS, 0, st>>>(a);
   k_ring_scatter<<<gpts, LVO_EX_THREADS, 0, st>>>(a);
   k_curvature<<<gpts, LVO_EX_THREADS, 0, st>>>(a);
+  LVO_MARK(tm, LVO_ST_REG_SORT, st);
   k_sector_sort<<<dim3(a.n_scans, lanes), LVO_SECSORT_THREADS, 0, st>>>(a);
+  LVO_MARK(tm, LVO_ST_REG_SEPARATE, st);
   k_sector_pick_warp<<<dim3(lvo_div_up(a.n_scans, LVO_PICKW_THREADS / 32), lanes), LVO_PICKW_THREADS, 0, st>>>(a);
   k_lessflat_voxel<128><<<dim3(a.n_scans, lanes), 128, 128 * 17 * sizeof(unsigned long long), st>>>(a);
   k_lessflat_voxel<256><<<dim3(a.n_scans, lanes), 256, 256 * 17 * sizeof(unsigned long long), st>>>(a);

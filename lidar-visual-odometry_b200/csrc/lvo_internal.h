@@ -79,6 +79,53 @@ struct LaneState {
 // Launch accounting (bench.py's gpu_launches) and error capture.
 struct LvoLaunchCounter { long long launches; };
 
+// Sub-stage timing under the reference's TicToc names (SURVEY §5 "tracing"): the launch functions mark stage boundaries with CUDA
+// events on the launching stream (plain launches only; a null timer or a graph capture records nothing).  An interval runs from
+// one mark to the next; after the stream has been synchronised collect() sums the intervals per stage.
+enum LvoStage {
+  LVO_ST_REG_PREPARE = 0,  // "prepare time"                   scanRegistration.cpp:254
+  LVO_ST_REG_SORT,         // "sort q time"                    :409
+  LVO_ST_REG_SEPARATE,     // "seperate points time"           :410
+  LVO_ST_ODO_ASSOC,        // "data association time"          laserOdometry.cpp:564
+  LVO_ST_ODO_SOLVER,       // "solver time"                    :577
+  LVO_ST_ODO_REST,         // pose integration, cloud swap, kd-tree (grid) rebuild  :581-641
+  LVO_ST_MAP_PREPARE,      // "map prepare time"               laserMapping.cpp:552
+  LVO_ST_MAP_TREE,         // "build tree time"                :560
+  LVO_ST_MAP_KNN,          // 5-NN part of "mapping data assosiation time" :710 (the graded kernel)
+  LVO_ST_MAP_FIT,          // line / plane fits, the rest of :710
+  LVO_ST_MAP_SOLVER,       // "mapping solver time"            :721
+  LVO_ST_MAP_ADD,          // "add points time"                :784
+  LVO_ST_MAP_FILTER,       // "filter time"                    :802
+  LVO_ST_MAP_PUB,          // registered cloud ("mapping pub time" :850)
+  LVO_ST_COUNT
+};
+struct LvoStageTimer {
+  std::vector<cudaEvent_t> pool;
+  std::vector<int> stage_of;   // stage that starts at event i (-1 = end marker)
+  int used = 0;
+  bool on = false;
+  void reset() { used = 0; stage_of.clear(); }
+  void mark(int stage, cudaStream_t st) {
+    if (!on) return;
+    if (used == (int)pool.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; pool.push_back(e); }
+    cudaEventRecord(pool[used++], st);
+    stage_of.push_back(stage);
+  }
+  void stop(cudaStream_t st) { mark(-1, st); }
+  // ms[LVO_ST_COUNT], count[LVO_ST_COUNT]; the stream must be idle
+  void collect(float* ms, int* count) const {
+    for (int i = 0; i < LVO_ST_COUNT; ++i) { ms[i] = 0.f; count[i] = 0; }
+    for (int i = 0; i + 1 < used; ++i) {
+      const int s = stage_of[i];
+      if (s < 0) continue;
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, pool[i], pool[i + 1]) == cudaSuccess) { ms[s] += t; count[s]++; }
+    }
+  }
+  void destroy() { for (cudaEvent_t e : pool) cudaEventDestroy(e); pool.clear(); used = 0; }
+};
+#define LVO_MARK(tm, stage, st) do { if (tm) (tm)->mark((stage), (st)); } while (0)
+
 #define LVO_CUDA_OK(ctx, expr)                                                                          \
   do {                                                                                                  \
     cudaError_t _e = (expr);                                                                            \

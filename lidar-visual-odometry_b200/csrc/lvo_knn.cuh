@@ -33,6 +33,7 @@ struct GridProblem {   // device-resident descriptor
   int mode;            // 0: uniform xyz grid; 1: (ring, azimuth) grid — cell = ring * LVO_AZ_BUCKETS + azimuth bucket
   int bbox_from;       // >= 0: this problem searches the same cloud as problem `bbox_from` (offset back from its own index is
                        //       not used; absolute index) and copies its bounding box instead of recomputing it
+  int cells_cap;       // > 0: this problem's share of the cell table (the cell size doubles until the grid fits); 0 = the set's default
   float clamp_xy;      // > 0: the table only covers |x|, |y| <= clamp_xy; points outside go to the border cells (their true
                        //      distance is larger than the cell suggests, so every ring bound stays valid)
   // filled by k_grid_setup
@@ -49,6 +50,7 @@ struct GridSet {
   GridProblem* prob;        // [nprob]
   int nprob;
   int cells_cap_per_problem;
+  long long table_cap_total; // cells allocated for the whole set (sum of the per-problem shares)
   unsigned* table;          // [nprob * cells_cap + 1] counts -> starts
   int* d_table_len;         // total cells + 1
   int* rank;                // [pts_cap_total] rank of a point inside its cell, laid out per problem at pt_off
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(256) k_grid_setup(GridSet g) {
             org[c] = lo; dim[c] = hi - lo + 1;
             nc *= (long long)dim[c];
           }
-          if (nc <= (long long)g.cells_cap_per_problem) break;
+          if (nc <= (long long)(q.cells_cap > 0 ? q.cells_cap : g.cells_cap_per_problem)) break;
           cell *= 2.0f;
           if (cellz < cell) cellz = cell;
         }
@@ -197,7 +199,7 @@ static inline void lvo_grid_build(cudaStream_t st, const GridSet& g, long long* 
   k_grid_setup<<<1, 256, 0, st>>>(g);
   k_grid_zero<<<1184, 256, 0, st>>>(g);
   k_grid_count<<<gp, 256, 0, st>>>(g);
-  const long long table_cap = (long long)g.nprob * g.cells_cap_per_problem + 1;
+  const long long table_cap = (g.table_cap_total > 0 ? g.table_cap_total : (long long)g.nprob * g.cells_cap_per_problem) + 1;
   lvo_scan_exclusive(st, g.table, g.d_table_len, (int)(table_cap < 0x7fffffffLL ? table_cap : 0x7fffffffLL), nullptr, g.scan, launches);
   k_grid_fill<<<gp, 256, 0, st>>>(g);
   if (launches) *launches += 6;

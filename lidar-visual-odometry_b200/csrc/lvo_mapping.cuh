@@ -52,8 +52,9 @@ struct MapArgs {
   unsigned* app_first;               // [2*lanes][LVO_NCUBES] first engine output position of those
   unsigned* new_cnt;                 // [2*lanes][LVO_NCUBES + 1]
   // probes
-  int* knn_ind[2];                   // [type] -> [lanes][LVO_MAX_OUTER][in_cap[type]][5]
-  int* fac_valid[2];                 // [type] -> [lanes][LVO_MAX_OUTER][in_cap[type]]
+  int* knn_ind[2];                   // [type] -> [lanes][slots][in_cap[type]][5]
+  int* fac_valid[2];                 // [type] -> [lanes][slots][in_cap[type]]
+  int slots;                         // outer-iteration slots kept (LVO_MAX_OUTER with lvo_config::debug_probes, else 2)
   float4* registered;                // [lanes][P] or null
 };
 
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(128) k_map_knn(MapArgs a) {
     const float4 sel = transform_point(s.map_x, s.map_x + 4, ori);
     TopK<5> tk;
     const bool ok = thread_knn<5>(t ? g1 : g0, sel.x, sel.y, sel.z, 1.0f, tk);
-    int* ki = a.knn_ind[t] + (((size_t)lane * LVO_MAX_OUTER + a.outer) * a.in_cap[t] + i) * 5;
+    int* ki = a.knn_ind[t] + (((size_t)lane * a.slots + a.outer % a.slots) * a.in_cap[t] + i) * 5;
 #pragma unroll
     for (int k = 0; k < 5; ++k) ki[k] = ok ? tk.id[k] : -1;
   }
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(128) k_map_fit(MapArgs a) {
     if (f < ntot) {
       const int t = f >= n0 ? 1 : 0;
       const int i = t ? f - n0 : f;
-      const int* ki = a.knn_ind[t] + (((size_t)lane * LVO_MAX_OUTER + a.outer) * a.in_cap[t] + i) * 5;
+      const int* ki = a.knn_ind[t] + (((size_t)lane * a.slots + a.outer % a.slots) * a.in_cap[t] + i) * 5;
       int id[5];
 #pragma unroll
       for (int k = 0; k < 5; ++k) id[k] = ki[k];
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(128) k_map_fit(MapArgs a) {
       fac.type = -1; fac.pad = 0; fac.d = 0;
       if (id[0] >= 0) fit_factor(t, a.stack[t][(size_t)lane * a.in_cap[t] + i], t ? M1 : M0, id, fac);
       a.factors[(size_t)lane * a.factor_cap + f] = fac;
-      a.fac_valid[t][((size_t)lane * LVO_MAX_OUTER + a.outer) * a.in_cap[t] + i] = fac.type >= 0 ? 1 : 0;
+      a.fac_valid[t][((size_t)lane * a.slots + a.outer % a.slots) * a.in_cap[t] + i] = fac.type >= 0 ? 1 : 0;
       if (fac.type >= 0) { if (t == 0) nc++; else nsf++; }
     }
   }
@@ -430,8 +431,9 @@ __global__ void k_register(MapArgs a) {
 }
 
 static inline void lvo_launch_mapping(cudaStream_t st, MapArgs a, const SolveArgs& solve_proto, int outer_iters, int lanes, bool want_registered,
-                                      long long* launches, cudaEvent_t* knn_ev /* [2*outer] or null */) {
+                                      long long* launches, LvoStageTimer* tm = nullptr) {
   const int L2 = 2 * lanes;
+  LVO_MARK(tm, LVO_ST_MAP_PREPARE, st);
   k_map_begin<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a);
   k_map_gather<<<dim3(LVO_MAX_VALID, L2), 128, 0, st>>>(a);
   k_stack_offsets<<<1, 256, 0, st>>>(a);
@@ -441,25 +443,29 @@ static inline void lvo_launch_mapping(cudaStream_t st, MapArgs a, const SolveArg
   lvo_voxel_run(st, a.vx, lanes * (a.in_cap[0] + a.in_cap[1]), L2, seg_bits, launches);
   k_stack_scatter<<<dim3(8, L2), 256, 0, st>>>(a);
   if (launches) *launches += 1;
+  LVO_MARK(tm, LVO_ST_MAP_TREE, st);
   lvo_grid_build(st, a.grid, launches);
   const int nstack_cap = a.in_cap[0] + a.in_cap[1];
   dim3 ga(max(1, min(lvo_div_up(nstack_cap, 128), 128)), lanes);
   for (int o = 0; o < outer_iters; ++o) {
     a.outer = o;
-    if (knn_ev) cudaEventRecord(knn_ev[2 * o], st);
+    LVO_MARK(tm, LVO_ST_MAP_KNN, st);
     k_map_knn<<<ga, 128, 0, st>>>(a);
-    if (knn_ev) cudaEventRecord(knn_ev[2 * o + 1], st);
+    LVO_MARK(tm, LVO_ST_MAP_FIT, st);
     k_map_fit<<<ga, 128, 0, st>>>(a);
     if (launches) *launches += 1;
     SolveArgs sa = solve_proto;
     sa.which = 1; sa.outer = o; sa.n_outer = outer_iters; sa.factors = a.factors; sa.factor_cap = a.factor_cap; sa.distort = 0; sa.lane0 = 0;  // LidarEdgeFactor(..., 1.0), :610
+    LVO_MARK(tm, LVO_ST_MAP_SOLVER, st);
     lvo_launch_lm(st, sa, lanes, 16384);
     if (launches) *launches += 2;
   }
+  LVO_MARK(tm, LVO_ST_MAP_ADD, st);
   k_map_finish<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a);
   k_refilter_offsets<<<1, 256, 0, st>>>(a);
   k_refilter_gather<<<dim3(64, L2), 256, 0, st>>>(a);
   if (launches) *launches += 3;
+  LVO_MARK(tm, LVO_ST_MAP_FILTER, st);
   int seg_bits2 = 1; while ((1 << seg_bits2) < L2 * LVO_MSEGS) seg_bits2++;
   lvo_voxel_run(st, a.vx, a.vx.cap_items, L2 * LVO_MSEGS, seg_bits2, launches);
   k_rebuild_reset<<<148, 256, 0, st>>>(a);
@@ -468,5 +474,6 @@ static inline void lvo_launch_mapping(cudaStream_t st, MapArgs a, const SolveArg
   k_rebuild_copy<<<dim3(64, L2), 256, 0, st>>>(a);
   k_map_end<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a);
   if (launches) *launches += 5;
+  LVO_MARK(tm, LVO_ST_MAP_PUB, st);
   if (want_registered && a.registered) { k_register<<<dim3(64, lanes), 256, 0, st>>>(a); if (launches) *launches += 1; }
 }

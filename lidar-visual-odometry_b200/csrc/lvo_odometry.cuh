@@ -34,8 +34,9 @@ struct OdoArgs {
   LvoFactor* factors; int factor_cap;
   int* slow_list;    // [lanes][cap_sharp + cap_flat] features the fast kernel hands to the tile kernel
   int* slow_cnt;     // [lanes]
-  int* corner_corr;  // [lanes][LVO_MAX_OUTER][cap_sharp][2]   probes
-  int* plane_corr;   // [lanes][LVO_MAX_OUTER][cap_flat][3]
+  int* corner_corr;  // [lanes][slots][cap_sharp][2]   probes; the association of outer iteration o reads those of o - 1
+  int* plane_corr;   // [lanes][slots][cap_flat][3]
+  int slots;         // outer-iteration slots kept: LVO_MAX_OUTER with lvo_config::debug_probes, else 2 (slot = outer % slots)
 };
 
 __global__ void k_odo_begin(OdoArgs a) {
@@ -197,10 +198,10 @@ __device__ __forceinline__ int odo_emit(const OdoArgs& a, int lane, int f, int n
   }
   a.factors[(size_t)lane * a.factor_cap + f] = fac;
   if (corner) {
-    int* c = a.corner_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer) * a.cap_sharp + f) * 2;
+    int* c = a.corner_corr + (((size_t)lane * a.slots + a.outer % a.slots) * a.cap_sharp + f) * 2;
     c[0] = i1; c[1] = i2;
   } else {
-    int* c = a.plane_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer) * a.cap_flat + (f - ns)) * 3;
+    int* c = a.plane_corr + (((size_t)lane * a.slots + a.outer % a.slots) * a.cap_flat + (f - ns)) * 3;
     c[0] = i1; c[1] = i2; c[2] = i3;
   }
   return fac.type;
@@ -243,8 +244,8 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
     const float4 sel = transform_to_start(s.para_q, s.para_t, pt, a.distortion);
     int pc = -1, pA = -1, pB = -1;
     if (a.outer > 0) {
-      if (corner) { const int* c = a.corner_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer - 1) * a.cap_sharp + f) * 2; pc = c[0]; pB = c[1]; }
-      else { const int* c = a.plane_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer - 1) * a.cap_flat + (f - ns)) * 3; pc = c[0]; pA = c[1]; pB = c[2]; }
+      if (corner) { const int* c = a.corner_corr + (((size_t)lane * a.slots + (a.outer - 1) % a.slots) * a.cap_sharp + f) * 2; pc = c[0]; pB = c[1]; }
+      else { const int* c = a.plane_corr + (((size_t)lane * a.slots + (a.outer - 1) % a.slots) * a.cap_flat + (f - ns)) * 3; pc = c[0]; pA = c[1]; pB = c[2]; }
     }
     float d = FLT_MAX; int id = INT_MAX;
     auto near = [&](float4 p) {
@@ -408,8 +409,8 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
   // azimuth window.  Results are identical to the unbounded search.
   int pc = -1, pA = -1, pB = -1;
   if (have && a.outer > 0) {
-    if (corner) { const int* c = a.corner_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer - 1) * a.cap_sharp + f) * 2; pc = c[0]; pB = c[1]; }
-    else { const int* c = a.plane_corr + (((size_t)lane * LVO_MAX_OUTER + a.outer - 1) * a.cap_flat + (f - ns)) * 3; pc = c[0]; pA = c[1]; pB = c[2]; }
+    if (corner) { const int* c = a.corner_corr + (((size_t)lane * a.slots + (a.outer - 1) % a.slots) * a.cap_sharp + f) * 2; pc = c[0]; pB = c[1]; }
+    else { const int* c = a.plane_corr + (((size_t)lane * a.slots + (a.outer - 1) % a.slots) * a.cap_flat + (f - ns)) * 3; pc = c[0]; pA = c[1]; pB = c[2]; }
   }
   bool boxed = false;
   if (pc >= 0) {
@@ -578,7 +579,8 @@ static inline int lvo_odo_chunk(int lanes) {
   if (env > 0) return env;
   return lanes;
 }
-static inline void lvo_launch_odometry(cudaStream_t st, OdoArgs a, const SolveArgs& solve_proto, int outer_iters, int lanes, long long* launches) {
+static inline void lvo_launch_odometry(cudaStream_t st, OdoArgs a, const SolveArgs& solve_proto, int outer_iters, int lanes, long long* launches, LvoStageTimer* tm = nullptr) {
+  LVO_MARK(tm, LVO_ST_ODO_REST, st);
   k_odo_begin<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a);
   if (launches) *launches += 1;
   const int nfeat_cap = a.cap_sharp + a.cap_flat;
@@ -594,6 +596,7 @@ static inline void lvo_launch_odometry(cudaStream_t st, OdoArgs a, const SolveAr
     dim3 gf(max(1, lvo_div_up(nfeat_cap, 128)), nl);
     for (int o = 0; o < outer_iters; ++o) {
       a.outer = o;
+      LVO_MARK(tm, LVO_ST_ODO_ASSOC, st);
       cudaMemsetAsync(a.slow_cnt + l0, 0, sizeof(int) * nl, st);
       k_odo_assoc_fast<<<gf, 128, 0, st>>>(a);
       if (launches) *launches += 1;
@@ -601,11 +604,13 @@ static inline void lvo_launch_odometry(cudaStream_t st, OdoArgs a, const SolveAr
       else k_odo_assoc<32><<<gs, 256, 0, st>>>(a);
       SolveArgs sa = solve_proto;
       sa.which = 0; sa.outer = o; sa.n_outer = outer_iters; sa.factors = a.factors; sa.factor_cap = a.factor_cap; sa.distort = a.distortion != 0; sa.lane0 = l0;
+      LVO_MARK(tm, LVO_ST_ODO_SOLVER, st);
       lvo_launch_lm(st, sa, nl, nfeat_cap);
       if (launches) *launches += 2;
     }
   }
   a.lane0 = 0;
+  LVO_MARK(tm, LVO_ST_ODO_REST, st);
   k_odo_integrate<<<lvo_div_up(lanes, 64), 64, 0, st>>>(a, outer_iters);
   if (a.distortion == 2) { k_odo_to_end<<<dim3(64, lanes), 256, 0, st>>>(a); if (launches) *launches += 1; }
   k_odo_swap<<<dim3(32, lanes), 256, 0, st>>>(a);
