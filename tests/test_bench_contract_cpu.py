@@ -18,17 +18,28 @@ def _run(args, env=None):
 
 
 def test_reference_arm_prints_one_contract_line():
-    r = _run(["--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "1", "--ref-threads", "2"])
+    r = _run(["--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "1", "--ref-threads", "2", "--ref-impl", "port", "--frames-per-step", "2"])
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, r.stdout
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"].startswith("scan-to-map scans/sec") and d["unit"] == "scans/s"
     assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["higher_is_better"] is True and d["vs_baseline"] is None
-    assert d["value"] > 0 and abs(d["value"] - 2 * 2 / (d["ms_per_step"] * 2e-3)) < 1e-6 * d["value"]   # threads x steps / time
+    assert d["value"] > 0 and abs(d["value"] - 2 * 2 * 2 / (d["ms_per_step"] * 2e-3)) < 1e-6 * d["value"]   # threads x steps x frames per step / time
+    assert d["config"]["frames_per_step"] == 2
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 2 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_runs_the_reference_node_sources_when_built():
+    """With oracle/_ref/libref_*.so present the arm times the reference's OWN scanRegistration / laserOdometry / laserMapping sources
+    (kind "reference"); without them it falls back to the restated port and says so."""
+    import refnode_py
+    r = _run(["--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "1", "--ref-threads", "2", "--frames-per-step", "2"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
+    assert d["cpu_baseline"]["kind"] == ("reference" if refnode_py.available() else "port") and d["value"] > 0
 
 
 def test_reference_arm_other_ranks_stay_silent():

@@ -269,7 +269,7 @@ def test_map_capacity_overflow_keeps_lanes_safe(lvo_mod, synth):
     overflowed = 0
     for k in range(8):
         big = synth.sweep(64, 0, k)[0]
-        small = np.ascontiguousarray(synth.sweep(64, 1, k)[0][::24])     # sparse sweep: its map stays far below the caps
+        small = np.ascontiguousarray(synth.sweep(64, 1, 0)[0][::24])     # sparse sweep of a sensor at rest: its map stays far below the caps
         views = [L.view_of(big), L.view_of(small)]
         arr = (L.CloudView * 2)(*[v[0] for v in views])
         po, pm = (L.Pose * 2)(), (L.Pose * 2)()

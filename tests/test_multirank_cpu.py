@@ -47,7 +47,7 @@ def test_two_rank_plumbing():
         p.join(timeout=60)
         assert p.exitcode == 0
     (r0, plan0, seq0, ms0, g0), (r1, plan1, seq1, ms1, g1) = res
-    assert plan0 == plan1 == [(0, 0), (1, 0), (2, 0), (3, 0), (0, 5), (1, 5)]
+    assert plan0 == plan1 == [(0, 0), (0, 1), (1, 0), (1, 1), (2, 0), (2, 1)]   # lanes of one sequence are adjacent, one frame apart
     assert seq0 != seq1                                   # ranks work on different sequences
     assert ms0 == ms1 == [11.0, 20.0]                     # max over ranks, identical on every rank
     assert np.array_equal(g0[0], g0[1]) and np.array_equal(g0[0], g1[1])  # same sequence -> bitwise identical poses on any rank
