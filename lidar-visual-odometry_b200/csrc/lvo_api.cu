@@ -462,6 +462,7 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
     LVO_TRY(dalloc(c, &mp.stack[t], (size_t)L * mp.in_cap[t]));
     LVO_TRY(dalloc(c, &mp.knn_ind[t], (size_t)L * slots * mp.in_cap[t] * 5));
     LVO_TRY(dalloc(c, &mp.fac_valid[t], (size_t)L * slots * mp.in_cap[t]));
+    LVO_TRY(dalloc(c, &mp.qorder[t], (size_t)L * mp.in_cap[t]));
   }
   LVO_TRY(alloc_grid(c, &mp.grid, 2 * L, 1 << 22, (size_t)L * ((size_t)mapc[0] + mapc[1]), std::max(mapc[0], mapc[1])));
   k_setup_grid_problems<<<lvo_div_up(2 * L, 64), 64, 0, c->st>>>(mp.grid.prob, 2 * L, mp.from_map[0], (size_t)mapc[0], mp.from_map[1], (size_t)mapc[1], c->d_ls, 1, 1.0f);
