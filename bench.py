@@ -363,6 +363,7 @@ def main():
     ap.add_argument("--knn-frames", type=int, default=128, help="throughput-mode 5-NN: number of config-3 frames in one launch (0 = skip)")
     ap.add_argument("--no-extras", action="store_true", help="skip the config-2 / 3 / 5 side measurements")
     ap.add_argument("--no-single", action="store_true", help="skip the single-trajectory measurement")
+    ap.add_argument("--map-caps", type=int, nargs=2, default=[1 << 18, 1 << 19], help="max_map_corner / max_map_surf of the timed contexts (points per lane)")
     ap.add_argument("--e2e-order", default=os.environ.get("LVO_BENCH_E2E_ORDER", "first"), choices=["first", "last"],
                     help="run the host-buffer arm before or after the device-resident arm")
     ap.add_argument("--graphs", type=int, default=int(os.environ.get("LVO_BENCH_GRAPHS", "-1")),
@@ -426,8 +427,8 @@ def main():
     stream = torch.cuda.current_stream()
     G = args.groups
     per = lanes // G
-    mk = dict(n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, lanes=per, device=local_rank, max_points=131072, max_map_corner=1 << 18,
-              max_map_surf=1 << 19, debug_probes=0)
+    mk = dict(n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, lanes=per, device=local_rank, max_points=131072, max_map_corner=args.map_caps[0],
+              max_map_surf=args.map_caps[1], debug_probes=0)
     # One context per group of `per` lanes, each on its own CUDA stream and driven by its own host thread (include/lvo.h: a context
     # is single-threaded, distinct contexts run concurrently — the reference's multi-sequence mechanism, SURVEY 8b "Threading").
     # The stages of different groups overlap on the GPU (sort-bound extraction next to latency-bound association / LM).

@@ -464,7 +464,7 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
     LVO_TRY(dalloc(c, &mp.fac_valid[t], (size_t)L * slots * mp.in_cap[t]));
     LVO_TRY(dalloc(c, &mp.qorder[t], (size_t)L * mp.in_cap[t]));
   }
-  LVO_TRY(alloc_grid(c, &mp.grid, 2 * L, 1 << 22, (size_t)L * ((size_t)mapc[0] + mapc[1]), std::max(mapc[0], mapc[1])));
+  LVO_TRY(alloc_grid(c, &mp.grid, 2 * L, 1 << 21, (size_t)L * ((size_t)mapc[0] + mapc[1]), std::max(mapc[0], mapc[1])));   // 2 M cells of 1 m: a 250 x 250 x 32 m neighbourhood; larger boxes double the cell edge
   k_setup_grid_problems<<<lvo_div_up(2 * L, 64), 64, 0, c->st>>>(mp.grid.prob, 2 * L, mp.from_map[0], (size_t)mapc[0], mp.from_map[1], (size_t)mapc[1], c->d_ls, 1, 1.0f);
   LVO_TRY(dalloc(c, &mp.item_off, (size_t)2 * L + 1));
   mp.factors = od.factors; mp.factor_cap = od.factor_cap;

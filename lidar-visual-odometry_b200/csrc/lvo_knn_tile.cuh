@@ -25,6 +25,9 @@
 #define LVO_KT_RUN 60           // cells of an x-run; the staged range is the run plus one cell on either side
 #define LVO_KT_CS (LVO_KT_RUN + 4)
 #define LVO_QSORT_MAX 8192      // queries per (lane, type) that k_map_qsort orders
+#define LVO_KT_BULK_MIN 64      // rows of at least this many points (1 KB) go through cp.async.bulk; shorter ones are loaded by the lanes
+                                // (a bulk copy costs ~0.2 us of the SM's copy unit whatever its size: measured, profiles/r2_knn_tile_notes.md)
+#define LVO_KT_MAX_GROUPS 5     // a chunk whose 32 queries fall into more cell rows than this is searched thread-per-query instead
 
 // ---- mbarrier / bulk-copy PTX (sm_90+; SASS: SYNCS.* and UBLKCP) ---------------------------------------------------------------
 __device__ __forceinline__ unsigned kt_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -76,6 +79,16 @@ __device__ __forceinline__ void kt_warp_search(const GridView& g, KtWarpSmem& sm
   }
   const int rowkey = have ? (cz + 1) * (g.dim[1] + 2) + (cy + 1) : -1;
   unsigned todo = __ballot_sync(0xffffffffu, have);
+  {
+    // Scattered queries (far-field arcs of the sweep: a few queries per cell row) would be staged one or two at a time, each group paying
+    // two dependent L2 round trips; there the 32 lanes walking their own cells concurrently are faster.
+    const unsigned same = __match_any_sync(0xffffffffu, rowkey);
+    const unsigned heads = __ballot_sync(0xffffffffu, have && (int)ln == __ffs(same) - 1);
+    if (__popc(heads) > LVO_KT_MAX_GROUPS) {
+      if (have) valid = thread_knn<5>(g, qx, qy, qz, max_sq, tk);
+      return;
+    }
+  }
   while (todo) {
     // ---- the group: lanes whose query lies in the cell row of the first lane still to do, x-run capped at LVO_KT_RUN cells
     const int leader = __ffs(todo) - 1;
@@ -136,16 +149,18 @@ __device__ __forceinline__ void kt_warp_search(const GridView& g, KtWarpSmem& sm
 #pragma unroll
     for (int r = 0; r < 9; ++r) { off[r] = total; total += sm.cs[r][jmax] - sm.cs[r][0]; }
     if (total > 0) {
-      if (ln == 0) {
-        kt_mbar_expect_tx(&sm.bar, total * 16u);
+      unsigned bulk_bytes = 0;
 #pragma unroll
-        for (int r = 0; r < 9; ++r) {
-          const unsigned b = sm.cs[r][0], cnt = sm.cs[r][jmax] - b;
-          if (cnt) kt_bulk_g2s(&sm.pts[off[r]], g.pts + b, cnt * 16u, &sm.bar);
-        }
+      for (int r = 0; r < 9; ++r) { const unsigned cnt = sm.cs[r][jmax] - sm.cs[r][0]; if (cnt >= LVO_KT_BULK_MIN) bulk_bytes += cnt * 16u; }
+      if (bulk_bytes && ln == 0) kt_mbar_expect_tx(&sm.bar, bulk_bytes);
+#pragma unroll
+      for (int r = 0; r < 9; ++r) {
+        const unsigned b = sm.cs[r][0], cnt = sm.cs[r][jmax] - b;
+        if (cnt >= LVO_KT_BULK_MIN) { if (ln == 0) kt_bulk_g2s(&sm.pts[off[r]], g.pts + b, cnt * 16u, &sm.bar); }
+        else for (unsigned t = ln; t < cnt; t += 32) sm.pts[off[r] + t] = __ldg(g.pts + b + t);
       }
-      while (!kt_mbar_try_wait(&sm.bar, phase)) {}
-      phase ^= 1u;
+      if (bulk_bytes) { while (!kt_mbar_try_wait(&sm.bar, phase)) {} phase ^= 1u; }
+      __syncwarp();
     }
     // ---- every lane of the group scans the 27 cells of its own query out of shared memory
     if (fits) {
