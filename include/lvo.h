@@ -281,6 +281,11 @@ int lvo_set_stream(lvo_ctx* ctx, void* cuda_stream);
 /* LVO_OPT_STAGE_TIMING (default 1): record the sub-stage CUDA events of lvo_timings in plain-launch lvo_step_batch* calls (~100
  * cudaEventRecord per frame); 0 = only the three whole-stage times.  The three per-stage entry points always record them. */
 #define LVO_OPT_STAGE_TIMING 3
+/* LVO_OPT_KNN_TILE (default 0; environment LVO_KNN_TILE at lvo_create): 1 = the 5-NN map search stages its candidate cells in shared
+ * memory (cell-sorted queries, warp tiles, cp.async.bulk for long rows: csrc/lvo_knn_tile.cuh) instead of one thread walking the 27 cells
+ * of its query.  Same index sets bit for bit.  Pays off for dense query sets; the stack of one sweep is mostly scattered arcs, where the
+ * thread-per-query form keeps four times as many searches in flight and wins (measurements: profiles/r2_summary.md). */
+#define LVO_OPT_KNN_TILE 4
 int lvo_set_option(lvo_ctx* ctx, int option, int value);
 /* Bytes copied device->host per lane at the end of every synchronous call (poses, counters, status). */
 size_t lvo_state_bytes(void);

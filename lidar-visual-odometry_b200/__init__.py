@@ -19,6 +19,7 @@ LVO_W_FIRST_FRAME, LVO_W_FEW_CORR, LVO_W_MAP_TOO_SMALL = 1, 2, 3
 LVO_OPT_GRAPHS = 1
 LVO_OPT_FIXPOINT_SKIP = 2
 LVO_OPT_STAGE_TIMING = 3
+LVO_OPT_KNN_TILE = 4
 
 # enum lvo_probe
 (P_FULL, P_CURVATURE, P_SORT_IND, P_LABEL, P_PICKED, P_SCAN_START, P_SCAN_END, P_SHARP, P_LESS_SHARP, P_FLAT, P_LESS_FLAT,

@@ -452,6 +452,8 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
   mp.ls = c->d_ls; mp.lanes = L; mp.leaf[0] = (float)cfg->line_res; mp.leaf[1] = (float)cfg->plane_res;
   mp.in_pts[0] = ex.less_sharp; mp.in_pts[1] = ex.less_flat; mp.in_cap[0] = c->cap_lsharp; mp.in_cap[1] = P;
   mp.full = ex.full; mp.P = P; mp.gen = 0; mp.slots = slots;
+  { const char* e = getenv("LVO_KNN_TILE"); mp.knn_tile = e ? atoi(e) : 0; }   // default: thread-per-query search (faster on sweep-shaped query sets, profiles/r2_summary.md)
+  lvo_mapping_kernel_attributes();
   for (int t = 0; t < 2; ++t) {
     mp.map_cap[t] = mapc[t];
     for (int g = 0; g < 2; ++g) {
@@ -525,6 +527,12 @@ int lvo_set_option(lvo_ctx* c, int option, int value) {
   if (!c) return LVO_E_BADARG;
   if (option == LVO_OPT_GRAPHS) { c->opt_graphs = value; return LVO_OK; }
   if (option == LVO_OPT_STAGE_TIMING) { c->opt_stage_timing = value ? 1 : 0; return LVO_OK; }
+  if (option == LVO_OPT_KNN_TILE) {   // a kernel choice baked into captured graphs
+    if (c->st) cudaStreamSynchronize(c->st);
+    destroy_graphs(c);
+    c->map.knn_tile = value ? 1 : 0;
+    return LVO_OK;
+  }
   if (option == LVO_OPT_FIXPOINT_SKIP) {   // a kernel argument: captured graphs hold the old value
     if (c->st) cudaStreamSynchronize(c->st);
     destroy_graphs(c);

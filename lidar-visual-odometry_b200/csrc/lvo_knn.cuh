@@ -332,12 +332,28 @@ __device__ __forceinline__ bool thread_knn(const GridView& g, float qx, float qy
       rb[k] = __ldg(g.cell_start + rowbase + x0); re[k] = __ldg(g.cell_start + rowbase + x1 + 1);
     }
   }
+  // candidates in batches of four: four independent 16-byte loads in flight per thread instead of one (the loop is bound by load
+  // latency, not by bandwidth or issue slots: ncu long-scoreboard stalls); insertion order is unchanged, hence the same result
 #pragma unroll
-  for (int k = 0; k < 9; ++k)
-    for (unsigned t = rb[k]; t < re[k]; ++t) {
-      const float4 p = __ldg(g.pts + t);
-      tk.insert(sqdist3(p, qx, qy, qz), __float_as_int(p.w));
+  for (int k = 0; k < 9; ++k) {
+    unsigned t = rb[k];
+    const unsigned e = re[k];
+    for (; t + 4 <= e; t += 4) {
+      const float4 p0 = __ldg(g.pts + t), p1 = __ldg(g.pts + t + 1), p2 = __ldg(g.pts + t + 2), p3 = __ldg(g.pts + t + 3);
+      tk.insert(sqdist3(p0, qx, qy, qz), __float_as_int(p0.w));
+      tk.insert(sqdist3(p1, qx, qy, qz), __float_as_int(p1.w));
+      tk.insert(sqdist3(p2, qx, qy, qz), __float_as_int(p2.w));
+      tk.insert(sqdist3(p3, qx, qy, qz), __float_as_int(p3.w));
     }
+    if (t < e) {   // 1..3 left: load them together as well
+      const float4 p0 = __ldg(g.pts + t);
+      const float4 p1 = t + 1 < e ? __ldg(g.pts + t + 1) : p0;
+      const float4 p2 = t + 2 < e ? __ldg(g.pts + t + 2) : p0;
+      tk.insert(sqdist3(p0, qx, qy, qz), __float_as_int(p0.w));
+      if (t + 1 < e) tk.insert(sqdist3(p1, qx, qy, qz), __float_as_int(p1.w));
+      if (t + 2 < e) tk.insert(sqdist3(p2, qx, qy, qz), __float_as_int(p2.w));
+    }
+  }
   for (int r = 2; r <= R; ++r) {
     const float bound = (float)(r - 1) * g.cell;
     if (tk.d[K - 1] < bound * bound) break;

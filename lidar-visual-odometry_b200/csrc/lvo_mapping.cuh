@@ -57,6 +57,7 @@ struct MapArgs {
   int* fac_valid[2];                 // [type] -> [lanes][slots][in_cap[type]]
   int slots;                         // outer-iteration slots kept (LVO_MAX_OUTER with lvo_config::debug_probes, else 2)
   int* qorder[2];                    // [type] -> [lanes][in_cap[type]] stack indices in map-cell order (k_map_qsort)
+  int knn_tile;                      // LVO_OPT_KNN_TILE
   float4* registered;                // [lanes][P] or null
 };
 
@@ -496,6 +497,12 @@ __global__ void k_register(MapArgs a) {
     a.registered[(size_t)lane * a.P + i] = transform_point(s.map_x, s.map_x + 4, a.full[(size_t)lane * a.P + i]);
 }
 
+// once per process and device, before the first launch (dynamic shared memory above 48 KB needs the opt-in)
+static inline void lvo_mapping_kernel_attributes() {
+  cudaFuncSetAttribute(k_map_qsort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((LVO_QSORT_MAX + LVO_QSORT_MAX / 16) * sizeof(unsigned long long)));
+  cudaFuncSetAttribute(k_map_knn_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LVO_KT_SMEM_BYTES);
+}
+
 static inline void lvo_launch_mapping(cudaStream_t st, MapArgs a, const SolveArgs& solve_proto, int outer_iters, int lanes, bool want_registered,
                                       long long* launches, LvoStageTimer* tm = nullptr) {
   const int L2 = 2 * lanes;
@@ -511,13 +518,8 @@ static inline void lvo_launch_mapping(cudaStream_t st, MapArgs a, const SolveArg
   if (launches) *launches += 1;
   LVO_MARK(tm, LVO_ST_MAP_TREE, st);
   lvo_grid_build(st, a.grid, launches);
-  // LVO_KNN_TILE = 0 selects the thread-per-query search (k_map_knn) instead of the shared-memory tiled one (A/B aid, same results)
-  static int knn_tile = -1;
-  if (knn_tile < 0) {
-    const char* e = getenv("LVO_KNN_TILE"); knn_tile = e ? atoi(e) : 1;
-    cudaFuncSetAttribute(k_map_qsort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((LVO_QSORT_MAX + LVO_QSORT_MAX / 16) * sizeof(unsigned long long)));
-    cudaFuncSetAttribute(k_map_knn_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LVO_KT_SMEM_BYTES);
-  }
+  // a.knn_tile (LVO_OPT_KNN_TILE): the shared-memory tiled search instead of the thread-per-query one (same results bit for bit)
+  const int knn_tile = a.knn_tile;
   if (knn_tile) {
     k_map_qsort<<<dim3(2, lanes), 512, (LVO_QSORT_MAX + LVO_QSORT_MAX / 16) * sizeof(unsigned long long), st>>>(a);
     if (launches) *launches += 1;

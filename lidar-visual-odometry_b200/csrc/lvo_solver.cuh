@@ -22,11 +22,8 @@
 #pragma once
 #include "lvo_internal.h"
 #include <float.h>
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
 
-#define LVO_LM_THREADS 256
-#define LVO_LM_CLUSTER_MAX 8   // CTAs per lane (1, 2, 4 or 8): one thread-block cluster, partial sums exchanged through DSMEM
+#define LVO_LM_THREADS 384     // one CTA per lane: 12 warps x <= 170 registers, no spills; block barriers instead of cluster barriers
 #define LVO_NACC 28  // 21 + 6 + 1
 
 // ---- small dense routines (double) ---------------------------------------------------------------------------
@@ -295,22 +292,24 @@ struct SolveArgs {
 
 struct LmShared {
   double red[LVO_LM_THREADS / 32][LVO_NACC];
-  double partial[LVO_NACC];  // this CTA's partial sums
-  double sum[LVO_NACC];      // (CTA 0) reduced accumulators of the last evaluation
+  double sum[LVO_NACC];      // reduced accumulators of the last evaluation
   double xeval[7];           // point to evaluate next
   int ctrl;                  // 0 = evaluate xeval, 1 = finished
 };
 
-// All CTAs of the cluster call this; afterwards CTA 0's sh.sum holds the cluster-wide sums (fixed summation tree).
+// All threads of the CTA call this; afterwards sh.sum holds the sums over all factors of the lane (fixed summation tree:
+// per-thread strided partial sums, warp shuffle tree, warps in rank order => bitwise deterministic).
 template <bool DISTORT>
-__device__ __forceinline__ void lm_evaluate(const SolveArgs& a, const LvoFactor* F, int nslots, const double* x, LmShared& sh, cg::cluster_group& cluster) {
-  const unsigned crank = cluster.block_rank(), csize = cluster.num_blocks();
+__device__ __forceinline__ void lm_evaluate(const SolveArgs& a, const LvoFactor* __restrict__ F, int nslots, const double* x, LmShared& sh) {
   double acc[LVO_NACC];
 #pragma unroll
   for (int i = 0; i < LVO_NACC; ++i) acc[i] = 0.0;
-  for (int s = crank * LVO_LM_THREADS + threadIdx.x; s < nslots; s += LVO_LM_THREADS * csize) {
+  double xl[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) xl[i] = x[i];
+  for (int s = threadIdx.x; s < nslots; s += LVO_LM_THREADS) {
     const LvoFactor f = F[s];
-    if (f.type >= 0) accumulate_factor<DISTORT>(f, x, a.huber, acc);
+    if (f.type >= 0) accumulate_factor<DISTORT>(f, xl, a.huber, acc);
   }
   const unsigned ln = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
@@ -325,27 +324,14 @@ __device__ __forceinline__ void lm_evaluate(const SolveArgs& a, const LvoFactor*
     double v = 0;
 #pragma unroll
     for (int ww = 0; ww < LVO_LM_THREADS / 32; ++ww) v += sh.red[ww][threadIdx.x];
-    sh.partial[threadIdx.x] = v;
+    sh.sum[threadIdx.x] = v;
   }
-  cluster.sync();
-  if (crank == 0) {
-    if (threadIdx.x < LVO_NACC) {
-      double v = 0;
-#pragma unroll
-      for (unsigned r = 0; r < csize; ++r) v += cluster.map_shared_rank(&sh, r)->partial[threadIdx.x];
-      sh.sum[threadIdx.x] = v;
-    }
-    __syncthreads();
-  }
+  __syncthreads();
 }
-// CTA 0 thread 0: publish the next evaluation point / the stop flag to every CTA of the cluster
-__device__ __forceinline__ void lm_broadcast(LmShared& sh, cg::cluster_group& cluster, const double* xc, bool go) {
-  const unsigned csize = cluster.num_blocks();
-  for (unsigned r = 0; r < csize; ++r) {
-    LmShared* o = cluster.map_shared_rank(&sh, r);
-    if (go) for (int i = 0; i < 7; ++i) o->xeval[i] = xc[i];
-    o->ctrl = go ? 0 : 1;
-  }
+// thread 0: publish the next evaluation point / the stop flag
+__device__ __forceinline__ void lm_broadcast(LmShared& sh, const double* xc, bool go) {
+  if (go) for (int i = 0; i < 7; ++i) sh.xeval[i] = xc[i];
+  sh.ctrl = go ? 0 : 1;
 }
 
 // State of the trust-region loop, owned by thread 0.
@@ -357,7 +343,7 @@ struct LmCtl {
   int iter, invalid_run, nfactors;
 };
 
-__device__ inline double gradient_max_norm_dev(const double* x, const double* g) {
+__device__ __noinline__ double gradient_max_norm_dev(const double* x, const double* g) {
   // || x - Plus(x, -g) ||_inf.  The translation block of Plus is a plain addition, so its entries of the difference are
   // |g_t| exactly: if one of them already exceeds the tolerance the test "<= 1e-10" is decided without the quaternion
   // exponential (sin / cos in double on the one thread everybody waits for).
@@ -377,7 +363,7 @@ __device__ inline void lm_trace(const SolveArgs& a, int lane, int row, const dou
   t[7] = cost; t[8] = radius; t[9] = (double)flags;
 }
 // Computes the next candidate (looping over invalid steps).  Returns true if a candidate must be evaluated.
-__device__ inline bool lm_next_step(const SolveArgs& a, int lane, LmCtl& c) {
+__device__ __noinline__ bool lm_next_step(const SolveArgs& a, int lane, LmCtl& c) {
   const int idx[6][6] = {{0, 1, 2, 3, 4, 5}, {1, 6, 7, 8, 9, 10}, {2, 7, 11, 12, 13, 14}, {3, 8, 12, 15, 16, 17}, {4, 9, 13, 16, 18, 19}, {5, 10, 14, 17, 19, 20}};
   while (true) {
     if (c.iter >= a.max_iters) return false;  // NO_CONVERGENCE
@@ -421,12 +407,11 @@ __device__ inline bool lm_next_step(const SolveArgs& a, int lane, LmCtl& c) {
 }
 
 template <bool DISTORT>
-__global__ void __launch_bounds__(LVO_LM_THREADS, 2) k_lm_solve(SolveArgs a) {
+__global__ void __launch_bounds__(LVO_LM_THREADS, 1) k_lm_solve(SolveArgs a) {
   __shared__ LmShared sh;
-  __shared__ LmCtl ctl;  // only thread 0 of CTA 0 touches it; shared to keep it out of its registers
-  cg::cluster_group cluster = cg::this_cluster();
-  const bool lead = cluster.block_rank() == 0 && threadIdx.x == 0;
-  const int lane = a.lane0 + blockIdx.x / cluster.num_blocks();
+  __shared__ LmCtl ctl;  // only thread 0 touches it; shared to keep it out of its registers
+  const bool lead = threadIdx.x == 0;
+  const int lane = a.lane0 + blockIdx.x;
   LaneState& s = a.ls[lane];
   if (a.which == 0 ? (s.odo_inited == 0 || s.odo_done != 0) : (s.map_too_small != 0 || s.map_done != 0)) return;
   const int nslots = a.which == 0 ? (s.n_sharp + s.n_flat) : (s.n_stack[0] + s.n_stack[1]);
@@ -434,7 +419,7 @@ __global__ void __launch_bounds__(LVO_LM_THREADS, 2) k_lm_solve(SolveArgs a) {
   double* xg = a.which == 0 ? s.para_q : s.map_x;  // para_q[4], para_t[3] are contiguous
   if (threadIdx.x < 7) sh.xeval[threadIdx.x] = xg[threadIdx.x];
   __syncthreads();
-  lm_evaluate<DISTORT>(a, F, nslots, sh.xeval, sh, cluster);
+  lm_evaluate<DISTORT>(a, F, nslots, sh.xeval, sh);
   if (lead) {
     LmCtl& c = ctl;
     for (int i = 0; i < 7; ++i) c.x[i] = c.x0[i] = sh.xeval[i];
@@ -456,11 +441,11 @@ __global__ void __launch_bounds__(LVO_LM_THREADS, 2) k_lm_solve(SolveArgs a) {
       lm_trace(a, lane, 0, c.x, c.cost, c.radius, 32 | (gconv ? 16 : 0));
       if (!gconv) go = lm_next_step(a, lane, c);
     }
-    lm_broadcast(sh, cluster, c.xc, go);
+    lm_broadcast(sh, c.xc, go);
   }
-  cluster.sync();
+  __syncthreads();
   while (sh.ctrl == 0) {
-    lm_evaluate<DISTORT>(a, F, nslots, sh.xeval, sh, cluster);
+    lm_evaluate<DISTORT>(a, F, nslots, sh.xeval, sh);
     if (lead) {
       LmCtl& c = ctl;
       const double new_cost = sh.sum[27];
@@ -495,9 +480,9 @@ __global__ void __launch_bounds__(LVO_LM_THREADS, 2) k_lm_solve(SolveArgs a) {
         if (c.radius < 1e-32) go = false;
         if (go) go = lm_next_step(a, lane, c);
       }
-      lm_broadcast(sh, cluster, c.xc, go);
+      lm_broadcast(sh, c.xc, go);
     }
-    cluster.sync();
+    __syncthreads();
   }
   if (lead) {
     LmCtl& c = ctl;
@@ -532,27 +517,9 @@ __global__ void __launch_bounds__(LVO_LM_THREADS, 2) k_lm_solve(SolveArgs a) {
   }
 }
 
-// one cluster per lane; the cluster size is the largest of 8, 4, 2, 1 that keeps all lanes resident in one wave
-// (2 CTAs per SM x 148 SMs), so that few lanes get short latency and many lanes get full throughput
+// one CTA per lane (max_slots is kept for the call sites; the factor loop is strided over the CTA whatever the count)
 static inline void lvo_launch_lm(cudaStream_t st, const SolveArgs& sa, int lanes, int max_slots) {
-  int csize = LVO_LM_CLUSTER_MAX;
-  while (csize > 1 && lanes * csize > 296) csize >>= 1;
-  // small problems (scan-to-scan: < 2.4 k slots) do not amortise the cluster barriers: at most 4 slots per thread is enough
-  while (csize > 1 && max_slots <= csize * LVO_LM_THREADS * 2) csize >>= 1;
-  { // LVO_LM_CLUSTER = 1 | 2 | 4 | 8 overrides the choice (tuning aid, like LVO_ODO_CHUNK / LVO_FAST_H)
-    static int env = -1;
-    if (env < 0) { const char* e = getenv("LVO_LM_CLUSTER"); env = e ? atoi(e) : 0; }
-    if (env == 1 || env == 2 || env == 4 || env == 8) csize = env;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(lanes * csize, 1, 1);
-  cfg.blockDim = dim3(LVO_LM_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  if (sa.distort) cudaLaunchKernelEx(&cfg, k_lm_solve<true>, sa);
-  else cudaLaunchKernelEx(&cfg, k_lm_solve<false>, sa);
+  (void)max_slots;
+  if (sa.distort) k_lm_solve<true><<<lanes, LVO_LM_THREADS, 0, st>>>(sa);
+  else k_lm_solve<false><<<lanes, LVO_LM_THREADS, 0, st>>>(sa);
 }
