@@ -569,6 +569,11 @@ def main():
     ex = [(c.stats(l).odo_outer_executed, c.stats(l).map_outer_executed) for c in ctx_d for l in range(per)]
     outer_ran = [float(np.mean([e[0] for e in ex])), float(np.mean([e[1] for e in ex]))]
     map_sizes = np.array([[c.stats(l).map_corner_from_map, c.stats(l).map_surf_from_map] for c in ctx_d for l in range(per)])
+    # LVO_OPT_KNN_REUSE: share of the scan-to-map queries that were searched in full, per outer iteration (iteration 0: all), last timed frame
+    st_all = [c.stats(l) for c in ctx_d for l in range(per)]
+    q_tot = float(sum(x.map_corner_stack + x.map_surf_stack for x in st_all if x.map_outer_executed > 0)) or 1.0
+    knn_full_frac = [float(sum(x.map_knn_full[o] for x in st_all if x.map_outer_executed > o)) /
+                     (float(sum(x.map_corner_stack + x.map_surf_stack for x in st_all if x.map_outer_executed > o)) or 1.0) for o in range(10)]
     # Roofline of the graded kernel: inside the timed region the contexts overlap, so a per-launch event time of k_map_knn includes
     # whatever the other streams were running.  It is therefore taken from context 0 advancing ALONE for a few more frames right
     # after the timed region (same maps, same library path, per-launch CUDA events inside the library); the in-situ average is
@@ -697,6 +702,10 @@ def main():
                                              "what": "LVO_OPT_FIXPOINT_SKIP (include/lvo.h): an outer iteration that returns the pose bit for bit unchanged makes "
                                                      "the remaining ones exact repeats; they are not run. Poses / maps / counters are bitwise those of the full "
                                                      "schedule (tests/test_gpu_mapping.py::test_fixpoint_skip_is_bitwise_identical)"},
+                           "knn_reuse": {"full_search_fraction_per_outer_iteration": knn_full_frac,
+                                         "what": "LVO_OPT_KNN_REUSE (include/lvo.h): share of a lane's 5-NN queries searched in full in each outer iteration of the "
+                                                 "last timed frame; the others re-rank their five known neighbours under a guard-radius certificate (bitwise the "
+                                                 "same rows: tests/test_gpu_mapping.py::test_knn_reuse_is_bitwise_identical)"},
                            "l2": f"inputs larger than L2: every frame reads {lanes} new sweeps ({lanes * 1.92:.0f} MB) and rebuilds every grid; no flush",
                            "timing": "one CUDA event pair on the main stream around all K steps of all contexts (context streams wait for the start event, "
                                      "the end event waits for every context's last kernel)"},

@@ -103,6 +103,9 @@ typedef struct lvo_stats {
   /* outer iterations that actually ran (== outer_iters unless LVO_OPT_FIXPOINT_SKIP cut the loop short; the per-iteration
    * entries above are then filled with the values of the last iteration that ran, which every later one would reproduce) */
   int odo_outer_executed, map_outer_executed;
+  /* LVO_OPT_KNN_REUSE: queries of lvo_scan_to_map that were searched in full per outer iteration (iteration 0: all of them; later
+   * ones: those whose neighbour set could not be carried over with a certificate).  Diagnostic only. */
+  int map_knn_full[16];
 } lvo_stats;
 
 typedef struct lvo_ctx lvo_ctx; /* one per (GPU, group of lanes); owns streams, device arenas, cross-frame state */
@@ -286,6 +289,13 @@ int lvo_set_stream(lvo_ctx* ctx, void* cuda_stream);
  * of its query.  Same index sets bit for bit.  Pays off for dense query sets; the stack of one sweep is mostly scattered arcs, where the
  * thread-per-query form keeps four times as many searches in flight and wins (measurements: profiles/r2_summary.md). */
 #define LVO_OPT_KNN_TILE 4
+/* LVO_OPT_KNN_REUSE (default 1; environment LVO_KNN_REUSE at lvo_create).  The outer iterations of lvo_scan_to_map
+ * (laserMapping.cpp:562) search the same map from a pose that barely moves.  With 1, a full 5-NN search also records a guard radius
+ * (a lower bound on the distance to every point outside the neighbour set); a later iteration whose query moved by less than the
+ * slack re-ranks the five known neighbours instead of searching, and a query whose row is unchanged keeps its line / plane fit.
+ * The certificate is conservative, so index sets, factors and poses are bitwise those of searching every time
+ * (tests/test_gpu_mapping.py::test_knn_reuse_is_bitwise_identical); 0 = search and fit every query in every iteration. */
+#define LVO_OPT_KNN_REUSE 5
 int lvo_set_option(lvo_ctx* ctx, int option, int value);
 /* Bytes copied device->host per lane at the end of every synchronous call (poses, counters, status). */
 size_t lvo_state_bytes(void);

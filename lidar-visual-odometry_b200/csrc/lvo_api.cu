@@ -453,6 +453,7 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
   mp.in_pts[0] = ex.less_sharp; mp.in_pts[1] = ex.less_flat; mp.in_cap[0] = c->cap_lsharp; mp.in_cap[1] = P;
   mp.full = ex.full; mp.P = P; mp.gen = 0; mp.slots = slots;
   { const char* e = getenv("LVO_KNN_TILE"); mp.knn_tile = e ? atoi(e) : 0; }   // default: thread-per-query search (faster on sweep-shaped query sets, profiles/r2_summary.md)
+  { const char* e = getenv("LVO_KNN_REUSE"); mp.knn_reuse = e ? atoi(e) : 1; }   // default: neighbour sets carried across the outer iterations with a certificate
   lvo_mapping_kernel_attributes();
   for (int t = 0; t < 2; ++t) {
     mp.map_cap[t] = mapc[t];
@@ -465,10 +466,15 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
     LVO_TRY(dalloc(c, &mp.knn_ind[t], (size_t)L * slots * mp.in_cap[t] * 5));
     LVO_TRY(dalloc(c, &mp.fac_valid[t], (size_t)L * slots * mp.in_cap[t]));
     LVO_TRY(dalloc(c, &mp.qorder[t], (size_t)L * mp.in_cap[t]));
+    LVO_TRY(dalloc(c, &mp.knn_ref[t], (size_t)L * mp.in_cap[t], false));
+    LVO_TRY(dalloc(c, &mp.knn_sel[t], (size_t)L * mp.in_cap[t] * 5, false));
+    LVO_TRY(dalloc(c, &mp.knn_flag[t], (size_t)L * mp.in_cap[t], false));
   }
   LVO_TRY(alloc_grid(c, &mp.grid, 2 * L, 1 << 21, (size_t)L * ((size_t)mapc[0] + mapc[1]), std::max(mapc[0], mapc[1])));   // 2 M cells of 1 m: a 250 x 250 x 32 m neighbourhood; larger boxes double the cell edge
   k_setup_grid_problems<<<lvo_div_up(2 * L, 64), 64, 0, c->st>>>(mp.grid.prob, 2 * L, mp.from_map[0], (size_t)mapc[0], mp.from_map[1], (size_t)mapc[1], c->d_ls, 1, 1.0f);
   LVO_TRY(dalloc(c, &mp.item_off, (size_t)2 * L + 1));
+  LVO_TRY(dalloc(c, &mp.fit_list, (size_t)L * (mp.in_cap[0] + mp.in_cap[1]), false));
+  LVO_TRY(dalloc(c, &mp.fit_cnt, (size_t)L * LVO_MAX_OUTER));
   mp.factors = od.factors; mp.factor_cap = od.factor_cap;
   LVO_TRY(dalloc(c, &mp.app_cnt, (size_t)2 * L * LVO_NCUBES)); LVO_TRY(dalloc(c, &mp.app_first, (size_t)2 * L * LVO_NCUBES));
   LVO_TRY(dalloc(c, &mp.new_cnt, (size_t)2 * L * (LVO_NCUBES + 1)));
@@ -531,6 +537,12 @@ int lvo_set_option(lvo_ctx* c, int option, int value) {
     if (c->st) cudaStreamSynchronize(c->st);
     destroy_graphs(c);
     c->map.knn_tile = value ? 1 : 0;
+    return LVO_OK;
+  }
+  if (option == LVO_OPT_KNN_REUSE) {
+    if (c->st) cudaStreamSynchronize(c->st);
+    destroy_graphs(c);
+    c->map.knn_reuse = value ? 1 : 0;
     return LVO_OK;
   }
   if (option == LVO_OPT_FIXPOINT_SKIP) {   // a kernel argument: captured graphs hold the old value

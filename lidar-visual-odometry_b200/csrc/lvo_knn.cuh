@@ -332,9 +332,10 @@ __device__ __forceinline__ bool thread_knn(const GridView& g, float qx, float qy
       rb[k] = __ldg(g.cell_start + rowbase + x0); re[k] = __ldg(g.cell_start + rowbase + x1 + 1);
     }
   }
-  // candidates in batches of four: four independent 16-byte loads in flight per thread instead of one (the loop is bound by load
-  // latency, not by bandwidth or issue slots: ncu long-scoreboard stalls); insertion order is unchanged, hence the same result
-#pragma unroll
+  // candidates in batches of four: four independent 16-byte loads in flight per thread instead of one; insertion order is unchanged,
+  // hence the same result.  ONE copy of the row body (unroll 1): nine inlined copies made the kernel 7200 SASS instructions (115 KB) and
+  // instruction-fetch bound (ncu: stalled_no_instruction 20 of 27 warp-cycles per issue, profiles/r2a_map_knn_fit_stalls.txt).
+#pragma unroll 1
   for (int k = 0; k < 9; ++k) {
     unsigned t = rb[k];
     const unsigned e = re[k];

@@ -58,6 +58,13 @@ struct MapArgs {
   int slots;                         // outer-iteration slots kept (LVO_MAX_OUTER with lvo_config::debug_probes, else 2)
   int* qorder[2];                    // [type] -> [lanes][in_cap[type]] stack indices in map-cell order (k_map_qsort)
   int knn_tile;                      // LVO_OPT_KNN_TILE
+  // LVO_OPT_KNN_REUSE: certified reuse of a query's neighbour set across the outer iterations of a frame (k_map_knn_reuse)
+  int knn_reuse;
+  float4* knn_ref[2];                // [type] -> [lanes][in_cap[type]] query position of the last full search (x, y, z) and its guard radius (w)
+  int* knn_sel[2];                   // [type] -> [lanes][in_cap[type]][5] the up-to-5 nearest points of the last search, ranked at the latest pose (INT_MAX = none)
+  int* knn_flag[2];                  // [type] -> [lanes][in_cap[type]] LVO_KF_* bits
+  int* fit_list;                     // [lanes][in_cap[0] + in_cap[1]] factor slots whose row changed in this outer iteration (k_map_fit_reuse refits them)
+  int* fit_cnt;                      // [lanes][LVO_MAX_OUTER] their number per outer iteration (zeroed by k_map_begin)
   float4* registered;                // [lanes][P] or null
 };
 
@@ -105,7 +112,7 @@ __global__ void k_map_begin(MapArgs a) {
   s.map_too_small = !(s.from_off[0][LVO_MAX_VALID] > 10 && s.from_off[1][LVO_MAX_VALID] > 50);  // :554
   s.map_status = s.map_too_small ? LVO_W_MAP_TOO_SMALL : LVO_OK;
   s.map_done = 0; s.stats.map_outer_executed = 0;
-  for (int o = 0; o < LVO_MAX_OUTER; ++o) { s.stats.map_corner_corr[o] = 0; s.stats.map_surf_corr[o] = 0; s.stats.map_lm_iters[o] = 0; s.stats.map_final_cost[o] = 0; }
+  for (int o = 0; o < LVO_MAX_OUTER; ++o) { s.stats.map_corner_corr[o] = 0; s.stats.map_surf_corr[o] = 0; s.stats.map_lm_iters[o] = 0; s.stats.map_final_cost[o] = 0; s.stats.map_knn_full[o] = 0; if (a.fit_cnt) a.fit_cnt[lane * LVO_MAX_OUTER + o] = 0; }
   for (int c = 0; c < 3; ++c) { s.stats.center_cube[c] = s.center[c]; s.stats.cen[c] = s.cen[c]; }
 }
 
@@ -238,6 +245,263 @@ __global__ void __launch_bounds__(128) k_map_knn(MapArgs a) {
     for (int k = 0; k < 5; ++k) ki[k] = ok ? tk.id[k] : -1;
   }
 }
+// ---- certified reuse of the neighbour sets across outer iterations (LVO_OPT_KNN_REUSE) -----------------------------------------
+// The ten outer iterations of a frame (:562) search the SAME map with a pose that moves less and less, so almost every query keeps
+// its five neighbours from one iteration to the next.  A full search at position q_ref leaves, besides the set S of the (up to)
+// five nearest points, a GUARD radius: a lower bound on the distance from q_ref to every map point outside S — the smaller of
+// the sixth-best candidate distance and the distance from q_ref to the boundary of the 3 x 3 x 3 cell block that was scanned.
+// At a later position q_new (moved by delta = |q_new - q_ref|) every point outside S is at least guard - delta away, so
+//   (a) |S| = 5 and the largest new distance inside S is below guard - delta: S is exactly the 5-NN set at q_new, and ranking its
+//       members by the reference's (distance, index) key with distances computed by the same float expression gives the very row a
+//       full search returns (no outside point can even tie);
+//   (b) guard - delta > 1: every point outside S fails the d5^2 < 1.0 gate (:584 / :652), so the row is S (if |S| = 5 and its
+//       fifth distance passes the gate) or "no correspondence", again exactly what a full search returns;
+//   otherwise the query is searched in full again.  All comparisons carry margins (1e-4 relative + 1e-5 m) that dwarf float rounding
+//   (~1e-7 relative), and they only decide WHETHER the shortcut is taken, never a result.  A query whose row did not change keeps its
+//   factor record (the fit depends only on the query point and on the ordered neighbour points), so k_map_fit_reuse skips it.
+#define LVO_KF_ROW 1       // the row of the latest iteration is valid (5 neighbours inside the gate)
+#define LVO_KF_FACTOR 2    // the factor record of the latest fit is valid (type >= 0)
+#define LVO_KF_CHANGED 4   // the row changed in this iteration: k_map_fit_reuse must refit
+
+// (distance, index)-ranked merge of the per-lane lists of a TW-lane tile; afterwards every lane of the tile holds the tile-wide best K
+template <int K, int TW>
+__device__ __forceinline__ void tile_merge(TopK<K>& tk) {
+  float rd[K]; int ri[K];
+  int ptr = 0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float cd = FLT_MAX; int ci = INT_MAX;
+#pragma unroll
+    for (int j = 0; j < K; ++j) if (j == ptr) { cd = tk.d[j]; ci = tk.id[j]; }
+    float bd = cd; int bi = ci;
+#pragma unroll
+    for (int o = TW / 2; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, bd, o, TW);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o, TW);
+      if (TopK<K>::less(od, oi, bd, bi)) { bd = od; bi = oi; }
+    }
+    rd[k] = bd; ri[k] = bi;
+    if (bi == ci && bd == cd && ci != INT_MAX) ptr++;  // ids are unique, so exactly one lane advances
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) { tk.d[k] = rd[k]; tk.id[k] = ri[k]; }
+}
+
+// Full search of one query by an 8-lane tile (four queries per warp; every call is made by all 32 lanes): the 9 rows of the
+// 3 x 3 x 3 cell block around the query (cell >= 1 m covers the 1 m gate), lanes strided over the concatenated candidate ranges
+// (two loads in flight per lane), six best candidates by (distance, index), and the guard radius of the certificate above.
+// One thread walking the block on its own has a dependent chain of ~8-30 load round trips (corner queries see 50-170 candidates)
+// and a warp waits for its slowest lane (ncu: 10 of 32 threads active); the tile shares a query's candidates between 8 lanes.
+__device__ __forceinline__ void tile8_knn6_block(const GridView& g, bool active, float qx, float qy, float qz, TopK<6>& tk, float& guard) {
+  const int tl = (int)tile_lane<8>();
+  tk.init();
+  guard = 0.f;
+  const int cx = cell_coord(qx, g.inv_cell) - g.org[0], cy = cell_coord(qy, g.inv_cell) - g.org[1], cz = cell_coord(qz, g.inv_cell_z) - g.org[2];
+  auto consider = [&](float4 p, int) { tk.insert(sqdist3(p, qx, qy, qz), __float_as_int(p.w)); };
+#pragma unroll 1
+  for (int base = 0; base < 9; base += 8) {   // rows 0..7, then row 8
+    const int row = base + tl;
+    unsigned b = 0, e = 0;
+    if (active && g.dim[0] > 0 && row < 9) row_bounds(g, cz + row / 3 - 1, cy + row % 3 - 1, cx - 1, cx + 1, b, e);
+    tile_scan_ranges<8, 8>(g.pts, b, e, consider);
+  }
+  tile_merge<6, 8>(tk);
+  // guard radius: min(sixth-best distance, distance to the boundary of the scanned block), shrunk by the safety margin.
+  // The block reaches one whole cell beyond the query's own cell on every side.
+  const float fx = floorf(qx * g.inv_cell), fy = floorf(qy * g.inv_cell), fz = floorf(qz * g.inv_cell_z);
+  if (g.dim[0] > 0 && fabsf(fx) < 8.0e6f && fabsf(fy) < 8.0e6f && fabsf(fz) < 8.0e6f) {   // cell coordinates exact in float (and not clamped by cell_coord)
+    const float cz_size = 1.0f / g.inv_cell_z;
+    const float lx = qx - fx * g.cell, ly = qy - fy * g.cell, lz = qz - fz * cz_size;   // offsets inside the cell, in [0, cell]
+    const float bx = fminf(lx, g.cell - lx) + g.cell, by = fminf(ly, g.cell - ly) + g.cell, bz = fminf(lz, cz_size - lz) + cz_size;
+    float gd = fminf(fminf(bx, by), bz);
+    if (tk.id[5] != INT_MAX) gd = fminf(gd, sqrtf(tk.d[5]));
+    guard = fmaxf(gd * 0.9999f - 1e-5f, 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_map_knn_reuse(MapArgs a) {
+  __shared__ float4 s_sel[128];
+  __shared__ int s_list[128], s_fit[128];
+  __shared__ int s_n, s_nfit, s_off;
+  const int lane = blockIdx.y;
+  const LaneState& s = a.ls[lane];
+  if (s.map_too_small || s.map_done) return;   // :554 / fixed point reached (LVO_OPT_FIXPOINT_SKIP)
+  const int n0 = s.n_stack[0], ntot = n0 + s.n_stack[1];
+  int nc = 0, nsf = 0;   // factors kept from the previous iteration (unchanged rows)
+  __shared__ GridView gv[2];   // shared, not registers: the certificate phase wants occupancy
+  if (threadIdx.x < 2) gv[threadIdx.x] = grid_view(a.grid, 2 * lane + threadIdx.x);
+  const float4* M0 = a.from_map[0] + (size_t)lane * a.map_cap[0];
+  const float4* M1 = a.from_map[1] + (size_t)lane * a.map_cap[1];
+  const int slot = a.outer % a.slots;
+  for (int base = blockIdx.x * blockDim.x; base < ntot; base += gridDim.x * blockDim.x) {
+    if (threadIdx.x == 0) { s_n = 0; s_nfit = 0; }
+    __syncthreads();
+    // ---- phase A, one thread per query: the query in the map frame; from the second outer iteration on, the certificate
+    const int f = base + threadIdx.x;
+    bool need_full = false, refit = false;
+    if (f < ntot) {
+      need_full = true;
+      const int t = f >= n0 ? 1 : 0;
+      const int i = t ? f - n0 : f;
+      const size_t qi = (size_t)lane * a.in_cap[t] + i;
+      const float4 ori = a.stack[t][qi];
+      const float4 sel = transform_point(s.map_x, s.map_x + 4, ori);   // pointAssociateToMap :154-163
+      s_sel[threadIdx.x] = sel;
+      if (a.outer > 0) {
+        const float4 ref = a.knn_ref[t][qi];
+        const int flag = a.knn_flag[t][qi];
+        int id[5], old[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) old[k] = id[k] = a.knn_sel[t][qi * 5 + k];
+        const float4* M = t ? M1 : M0;
+        float d[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) d[k] = id[k] != INT_MAX ? sqdist3(M[id[k]], sel.x, sel.y, sel.z) : FLT_MAX;
+        // rank by (distance, index): insertion sort of five (INT_MAX entries carry FLT_MAX and stay last)
+#pragma unroll
+        for (int k = 1; k < 5; ++k)
+#pragma unroll
+          for (int j = k; j > 0; --j)
+            if (TopK<5>::less(d[j], id[j], d[j - 1], id[j - 1])) {
+              const float td = d[j]; d[j] = d[j - 1]; d[j - 1] = td;
+              const int ti = id[j]; id[j] = id[j - 1]; id[j - 1] = ti;
+            }
+        const float dx = sel.x - ref.x, dy = sel.y - ref.y, dz = sel.z - ref.z;
+        const float delta = sqrtf(dx * dx + dy * dy + dz * dz) * 1.0001f + 1e-5f;
+        const float B = ref.w - delta;           // every point outside the set is farther than this from the new position
+        const bool full_set = id[4] != INT_MAX;
+        bool decided = false, row_ok = false;
+        if (full_set && sqrtf(d[4]) * 1.0001f + 1e-5f < B) { decided = true; row_ok = (double)d[4] < 1.0; }
+        else if (B > 1.0002f) { decided = true; row_ok = full_set && (double)d[4] < 1.0; }
+        if (decided) {
+          need_full = false;
+          bool reordered = false;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) if (old[k] != id[k]) { reordered = true; a.knn_sel[t][qi * 5 + k] = id[k]; }
+          if (a.slots > 2) {   // per-iteration probe rows (lvo_config::debug_probes); the path itself reads knn_sel / knn_flag
+            int* ki = a.knn_ind[t] + (((size_t)lane * a.slots + slot) * a.in_cap[t] + i) * 5;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) ki[k] = row_ok ? id[k] : -1;
+          }
+          const bool changed = row_ok != ((flag & LVO_KF_ROW) != 0) || (row_ok && reordered);
+          a.knn_flag[t][qi] = (flag & LVO_KF_FACTOR) | (row_ok ? LVO_KF_ROW : 0) | (changed ? LVO_KF_CHANGED : 0);
+          refit = changed;
+          if (!changed) {   // the factor record of the previous iteration stands
+            const int v = (flag & LVO_KF_FACTOR) ? 1 : 0;
+            if (a.slots > 2) a.fac_valid[t][((size_t)lane * a.slots + slot) * a.in_cap[t] + i] = v;   // probe (lvo_config::debug_probes)
+            if (v) { if (t == 0) nc++; else nsf++; }
+          }
+        }
+      }
+    }
+    // ---- the queries that need a full search, compacted so that the 8-lane tiles below are all busy
+    {
+      const unsigned m = __ballot_sync(0xffffffffu, need_full);
+      int off = 0;
+      if ((threadIdx.x & 31) == 0 && m) off = atomicAdd(&s_n, __popc(m));
+      off = __shfl_sync(0xffffffffu, off, 0);
+      if (need_full) s_list[off + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = (int)threadIdx.x;
+      const unsigned m2 = __ballot_sync(0xffffffffu, refit);
+      int off2 = 0;
+      if ((threadIdx.x & 31) == 0 && m2) off2 = atomicAdd(&s_nfit, __popc(m2));
+      off2 = __shfl_sync(0xffffffffu, off2, 0);
+      if (refit) s_fit[off2 + __popc(m2 & ((1u << (threadIdx.x & 31)) - 1u))] = (int)threadIdx.x;
+    }
+    __syncthreads();
+    const int nfull = s_n;
+    // the factor slots k_map_fit_reuse has to refit: the rows that changed under the certificate and every query searched in full
+    // (iteration 0 refits everything and needs no list)
+    const int nfit = s_nfit + nfull;
+    if (a.outer > 0 && nfit > 0) {
+      if (threadIdx.x == 0) s_off = atomicAdd(&a.fit_cnt[lane * LVO_MAX_OUTER + a.outer], nfit);
+      __syncthreads();
+      int* fl = a.fit_list + (size_t)lane * (a.in_cap[0] + a.in_cap[1]) + s_off;
+      if ((int)threadIdx.x < nfit) fl[threadIdx.x] = base + ((int)threadIdx.x < s_nfit ? s_fit[threadIdx.x] : s_list[threadIdx.x - s_nfit]);
+    }
+    if (threadIdx.x == 0 && nfull) atomicAdd(&a.ls[lane].stats.map_knn_full[a.outer], nfull);
+    // ---- phase B: 16 tiles of 8 lanes per block; a warp's four tiles take entries 4 w .. 4 w + 3 of every group of 16
+    const int w = threadIdx.x >> 5, tile = (threadIdx.x & 31) >> 3;
+    for (int e0 = 4 * w; e0 < nfull; e0 += 16) {   // uniform per warp
+      const int e = e0 + tile;
+      const bool active = e < nfull;
+      const int src = active ? s_list[e] : 0;
+      const int f2 = base + src;
+      const int t = (active && f2 >= n0) ? 1 : 0;
+      const float4 sel = s_sel[src];
+      TopK<6> tk;
+      float guard;
+      // both types in one warp: the grid is selected per tile (all members are per-tile values)
+      tile8_knn6_block(gv[t], active, sel.x, sel.y, sel.z, tk, guard);
+      if (active && tile_lane<8>() == 0) {
+        const int i = t ? f2 - n0 : f2;
+        const size_t qi = (size_t)lane * a.in_cap[t] + i;
+        const bool row_ok = tk.id[4] != INT_MAX && (double)tk.d[4] < 1.0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) a.knn_sel[t][qi * 5 + k] = tk.id[k];
+        if (a.slots > 2) {
+          int* ki = a.knn_ind[t] + (((size_t)lane * a.slots + slot) * a.in_cap[t] + i) * 5;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) ki[k] = row_ok ? tk.id[k] : -1;
+        }
+        a.knn_ref[t][qi] = make_float4(sel.x, sel.y, sel.z, guard);
+        // a full search always asks for a refit (it is the rare path after the first iteration)
+        const int oldf = a.outer > 0 ? a.knn_flag[t][qi] : 0;
+        a.knn_flag[t][qi] = (oldf & LVO_KF_FACTOR) | (row_ok ? LVO_KF_ROW : 0) | LVO_KF_CHANGED;
+      }
+    }
+    __syncthreads();
+  }
+  nc = __reduce_add_sync(0xffffffffu, nc);
+  nsf = __reduce_add_sync(0xffffffffu, nsf);
+  if ((threadIdx.x & 31) == 0) {
+    if (nc) atomicAdd(&a.ls[lane].stats.map_corner_corr[a.outer], nc);
+    if (nsf) atomicAdd(&a.ls[lane].stats.map_surf_corr[a.outer], nsf);
+  }
+}
+
+// fits for the rows that changed (the list k_map_knn_reuse wrote; iteration 0: every query); the others keep their factor record
+__global__ void __launch_bounds__(128) k_map_fit_reuse(MapArgs a) {
+  const int lane = blockIdx.y;
+  LaneState& s = a.ls[lane];
+  if (s.map_too_small || s.map_done) return;
+  const int n0 = s.n_stack[0], ntot = n0 + s.n_stack[1];
+  const int n = a.outer > 0 ? a.fit_cnt[lane * LVO_MAX_OUTER + a.outer] : ntot;
+  const int* fl = a.fit_list + (size_t)lane * (a.in_cap[0] + a.in_cap[1]);
+  const float4* M0 = a.from_map[0] + (size_t)lane * a.map_cap[0];
+  const float4* M1 = a.from_map[1] + (size_t)lane * a.map_cap[1];
+  const int slot = a.outer % a.slots;
+  int nc = 0, nsf = 0;
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const int e = base + threadIdx.x;
+    if (e < n) {
+      const int f2 = a.outer > 0 ? fl[e] : e;
+      const int t = f2 >= n0 ? 1 : 0;
+      const int i = t ? f2 - n0 : f2;
+      const size_t qi = (size_t)lane * a.in_cap[t] + i;
+      const int flag = a.knn_flag[t][qi];
+      LvoFactor fac;
+      fac.type = -1; fac.pad = 0; fac.d = 0;
+      if (flag & LVO_KF_ROW) {
+        int id[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) id[k] = a.knn_sel[t][qi * 5 + k];
+        fit_factor(t, a.stack[t][qi], t ? M1 : M0, id, fac);
+      }
+      a.factors[(size_t)lane * a.factor_cap + f2] = fac;
+      const int v = fac.type >= 0 ? 1 : 0;
+      if (a.slots > 2) a.fac_valid[t][((size_t)lane * a.slots + slot) * a.in_cap[t] + i] = v;   // probe
+      a.knn_flag[t][qi] = (flag & LVO_KF_ROW) | (v ? LVO_KF_FACTOR : 0);
+      if (v) { if (t == 0) nc++; else nsf++; }
+    }
+  }
+  nc = __reduce_add_sync(0xffffffffu, nc);
+  nsf = __reduce_add_sync(0xffffffffu, nsf);
+  if ((threadIdx.x & 31) == 0) {
+    if (nc) atomicAdd(&s.stats.map_corner_corr[a.outer], nc);
+    if (nsf) atomicAdd(&s.stats.map_surf_corr[a.outer], nsf);
+  }
+}
+
 // Order of the queries for the tiled search: stack indices sorted by the map-grid cell (z, y, x) of the point under the frame's INITIAL
 // pose.  One CTA per (lane, type), register bitonic sort of (cell key, index); stacks beyond LVO_QSORT_MAX keep their order.
 __global__ void __launch_bounds__(512) k_map_qsort(MapArgs a) {
@@ -531,9 +795,11 @@ static inline void lvo_launch_mapping(cudaStream_t st, MapArgs a, const SolveArg
     a.outer = o;
     LVO_MARK(tm, LVO_ST_MAP_KNN, st);
     if (knn_tile) k_map_knn_tile<<<gt, LVO_KT_WARPS * 32, LVO_KT_SMEM_BYTES, st>>>(a);
+    else if (a.knn_reuse) k_map_knn_reuse<<<ga, 128, 0, st>>>(a);
     else k_map_knn<<<ga, 128, 0, st>>>(a);
     LVO_MARK(tm, LVO_ST_MAP_FIT, st);
-    k_map_fit<<<ga, 128, 0, st>>>(a);
+    if (!knn_tile && a.knn_reuse) k_map_fit_reuse<<<ga, 128, 0, st>>>(a);
+    else k_map_fit<<<ga, 128, 0, st>>>(a);
     if (launches) *launches += 1;
     SolveArgs sa = solve_proto;
     sa.which = 1; sa.outer = o; sa.n_outer = outer_iters; sa.factors = a.factors; sa.factor_cap = a.factor_cap; sa.distort = 0; sa.lane0 = 0;  // LidarEdgeFactor(..., 1.0), :610

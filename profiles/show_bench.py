@@ -15,3 +15,4 @@ for k, v in (d.get("other_configs") or {}).items():
     print(k, {a: b for a, b in v.items() if a != "what"} if isinstance(v, dict) else v)
 print("cpu:", d.get("cpu_baseline"))
 print(d["config"]["map_points_in_neighbourhood_last_frame"], d["config"]["fixpoint_skip"]["outer_iterations_run_mean"], d["host"], d["clocks"])
+print("knn full-search fraction per outer:", [round(x, 3) for x in (d["config"].get("knn_reuse") or {}).get("full_search_fraction_per_outer_iteration", [])])

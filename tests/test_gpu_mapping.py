@@ -289,3 +289,42 @@ def test_map_capacity_overflow_keeps_lanes_safe(lvo_mod, synth):
         assert (s1.map_corner_total, s1.map_surf_total) == (b.stats(0).map_corner_total, b.stats(0).map_surf_total)
     assert overflowed >= 1
     a.close(); b.close()
+
+
+def test_knn_reuse_is_bitwise_identical(lvo_mod, synth):
+    """LVO_OPT_KNN_REUSE (default on): a query of lvo_scan_to_map keeps its neighbour set across the outer iterations
+    (laserMapping.cpp:562, :582 / :648) when a guard radius recorded by its last full search certifies that no other map point
+    can enter it, and keeps its fit when the row is unchanged.  Every 5-NN row and factor flag of ALL ten iterations, the counters,
+    poses and maps must equal those of searching and fitting every query every time."""
+    L = lvo_mod
+    mk = dict(lanes=2, max_map_corner=1 << 18, max_map_surf=1 << 19)
+    a, b = L.Lvo(**mk), L.Lvo(**mk)
+    for c, v in ((a, 1), (b, 0)):
+        c.set_option(L.LVO_OPT_GRAPHS, 0)
+        c.set_option(L.LVO_OPT_KNN_REUSE, v)
+        c.set_option(L.LVO_OPT_FIXPOINT_SKIP, 0)   # every one of the ten iterations runs, so the certificate is exercised ten times
+    arrays = ("map_corner_corr", "map_surf_corr", "map_lm_iters", "map_final_cost")
+    probes = (L.P_MAP_CORNER_KNN, L.P_MAP_SURF_KNN, L.P_MAP_CORNER_VALID, L.P_MAP_SURF_VALID, L.P_MAP_LM_TRACE)
+    full = reused = 0
+    for k in range(12):
+        sws = [synth.sweep(64, 0, k)[0], synth.sweep(64, 5, k)[0]]
+        sa, oa, ma = a.step_batch(sws)
+        sb, ob, mb = b.step_batch(sws)
+        assert sa == sb and np.array_equal(oa, ob) and np.array_equal(ma, mb), k
+        for lane in range(2):
+            x, y = a.stats(lane), b.stats(lane)
+            for name in arrays:
+                assert list(getattr(x, name)) == list(getattr(y, name)), (k, lane, name)
+            for what in probes:
+                assert np.array_equal(a.probe(what, lane), b.probe(what, lane)), (k, lane, what)
+            if x.map_outer_executed:
+                q = x.map_corner_stack + x.map_surf_stack
+                assert x.map_knn_full[0] == q and list(y.map_knn_full) == [0] * 16
+                full += sum(x.map_knn_full[1:10]); reused += 9 * q - sum(x.map_knn_full[1:10])
+    assert reused > 4 * full, (reused, full)   # the certificate carries most rows (typically > 90 %)
+    for lane in range(2):
+        for which in (0, 1):
+            pa, ca = a.map_export(lane, which)
+            pb, cb = b.map_export(lane, which)
+            assert np.array_equal(ca, cb) and np.array_equal(_bits(pa), _bits(pb))
+    a.close(); b.close()
