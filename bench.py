@@ -373,6 +373,8 @@ def main():
                          "are exact repeats and are not run; 0 = always run all ten")
     ap.add_argument("--no-full-schedule", action="store_true", help="skip the extra device-resident arm with LVO_OPT_FIXPOINT_SKIP = 0")
     ap.add_argument("--only-knn", action="store_true", help="profiling aid: only the throughput-mode 5-NN measurement")
+    ap.add_argument("--profile-iso", type=int, default=0, help="profiling aid: bracket this many of the isolated frames after the timed region with "
+                    "cudaProfilerStart / cudaProfilerStop (use with `ncu --profile-from-start off`: nothing before them is profiled or serialised)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     F = max(1, args.frames_per_step)
@@ -586,11 +588,15 @@ def main():
     ctx_d[0].set_option(L.LVO_OPT_FIXPOINT_SKIP, 0)   # ... and every one of the ten launches should search all lanes (kernel property)
     stage_batch = None
     for k in range(total, total + iso_extra):
+        if args.profile_iso and k == total + iso_extra - args.profile_iso:
+            torch.cuda.synchronize(); torch.cuda.profiler.start()
         step_dev(0, k)
         t = ctx_d[0].timings()
         knn_ms += t.knn_ms; knn_launches += t.knn_launches; knn_bytes += t.knn_bytes
         iso_frames += 1
         stage_batch = ctx_d[0].stage_timings()
+    if args.profile_iso:
+        torch.cuda.synchronize(); torch.cuda.profiler.stop()
     for c in ctx_d:
         c.close()
     # the same device-resident arm with the reference's full schedule (every lane runs all ten outer iterations), for comparison

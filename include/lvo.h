@@ -106,6 +106,11 @@ typedef struct lvo_stats {
   /* LVO_OPT_KNN_REUSE: queries of lvo_scan_to_map that were searched in full per outer iteration (iteration 0: all of them; later
    * ones: those whose neighbour set could not be carried over with a certificate).  Diagnostic only. */
   int map_knn_full[16];
+  /* scan-to-scan features per outer iteration that the thread-per-feature association handed to the warp-per-feature kernel, and why
+   * (summed over the iterations of the frame): 0 no bound on the closest point, 1 bound wider than a fine cell, 2 closest point beyond the
+   * 5 m gate, 3 an adjacent-ring target exists but its azimuth window is wider than the fast limit, 4 an adjacent-ring target has no
+   * candidate nearby.  Diagnostic only. */
+  int odo_slow[16], odo_slow_why[5];
 } lvo_stats;
 
 typedef struct lvo_ctx lvo_ctx; /* one per (GPU, group of lanes); owns streams, device arenas, cross-frame state */

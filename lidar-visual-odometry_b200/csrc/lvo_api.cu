@@ -685,7 +685,11 @@ static int step_enqueue(lvo_ctx* c, int stride, int off_xyz, int max_n) {
   c->launches = 0;
   LVO_TRY(enqueue_prefetch(c));
   LVO_TRY(set_inputs(c));
-  const bool do_map = (c->frame % c->cfg.skip_frame) == 0;  // laserOdometry.cpp:643
+  // LVO_STAGE_MASK (profiling aid, environment only): bit 0 extract, bit 1 scan-to-scan, bit 2 scan-to-map; stages left out are not
+  // enqueued, so the saturated throughput of a prefix of the chain can be measured (results are only meaningful with the default 7)
+  static int stage_mask = -1;
+  if (stage_mask < 0) { const char* e = getenv("LVO_STAGE_MASK"); stage_mask = e ? atoi(e) : 7; }
+  const bool do_map = (c->frame % c->cfg.skip_frame) == 0 && (stage_mask & 4);  // laserOdometry.cpp:643
   const bool want_graph = c->opt_graphs == 1 || (c->opt_graphs < 0 && c->lanes <= 8);
   const bool use_graph = want_graph && c->st != nullptr;    // the legacy default stream cannot be captured
   nvtxRangePushA("lvo_step");
@@ -718,10 +722,10 @@ static int step_enqueue(lvo_ctx* c, int stride, int off_xyz, int max_n) {
   } else {
     LvoStageTimer* tm = stage_timer_begin(c, c->opt_stage_timing != 0);
     cudaEventRecord(c->ev[0], c->st);
-    enqueue_extract(c, stride, off_xyz, max_n, tm);
+    if (stage_mask & 1) enqueue_extract(c, stride, off_xyz, max_n, tm);
     cudaEventRecord(c->ev[1], c->st);
     c->solve.trace = c->d_trace[0];
-    enqueue_odometry(c, tm);
+    if (stage_mask & 2) enqueue_odometry(c, tm);
     cudaEventRecord(c->ev[2], c->st);
     if (do_map) { c->solve.trace = c->d_trace[1]; enqueue_mapping(c, 1, true, tm); }
     c->stage_tm.stop(c->st);

@@ -45,7 +45,8 @@ __global__ void k_odo_begin(OdoArgs a) {
   LaneState& s = a.ls[lane];
   s.odo_status = s.odo_inited ? LVO_OK : LVO_W_FIRST_FRAME;
   s.odo_done = 0; s.stats.odo_outer_executed = 0;
-  for (int o = 0; o < LVO_MAX_OUTER; ++o) { s.stats.odo_corner_corr[o] = 0; s.stats.odo_plane_corr[o] = 0; s.stats.odo_lm_iters[o] = 0; s.stats.odo_final_cost[o] = 0; }
+  for (int o = 0; o < LVO_MAX_OUTER; ++o) { s.stats.odo_corner_corr[o] = 0; s.stats.odo_plane_corr[o] = 0; s.stats.odo_lm_iters[o] = 0; s.stats.odo_final_cost[o] = 0; s.stats.odo_slow[o] = 0; }
+  for (int k = 0; k < 5; ++k) s.stats.odo_slow_why[k] = 0;
 }
 
 struct Best { float d; int pos; int j; };
@@ -258,7 +259,10 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
     if (pc >= 0) { d = sqdist3(C[pc], sel.x, sel.y, sel.z); id = pc; }
     else if (g.dim[0] > 0) { unsigned b, e; row_bounds(g, cz, cy, cx, cx, b, e); scan_range4(g.pts, b, e, near); }
     float rad = sqrtf(d) * 1.0001f + 1e-5f;
+    // (a box query on the 2 m middle grid for bounds between 0.5 and 2 m was tried here: it halves the list handed to the warp-per-feature
+    // kernel but one thread then walks a (4 m)^3 box while its warp waits — association time went from 4.1 to 5.1 ms per 128-lane frame)
     bool fast = id != INT_MAX && rad < g.cell && (double)d < 25.0;
+    int why = id == INT_MAX ? 0 : (!(rad < g.cell) ? 1 : 2);
     int closest = -1, same = -1, other = -1;
     float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
     if (fast) {
@@ -330,7 +334,9 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
         } else {
           hA = corner ? 0 : (bA.j >= 0 ? az_halfwidth(bA.d, rho) : LVO_AZ_BUCKETS);
           hB = bB.j >= 0 ? az_halfwidth(bB.d, rho) : LVO_AZ_BUCKETS;
-          if (hA > a.fast_h || hB > a.fast_h) { fast = false; break; }   // a target has no candidate nearby or its window is wide: leave it to the cooperative kernel
+          if (hA > a.fast_h || hB > a.fast_h) {   // a target has no candidate nearby or its window is wide: leave it to the cooperative kernel
+            fast = false; why = ((!corner && bA.j < 0) || bB.j < 0) ? 4 : 3; break;
+          }
           skipA = corner ? hA : sA; skipB = sB;
         }
         unsigned wb[10], we[10];   // part 0 of every bucket range; fetched together before any candidate
@@ -363,6 +369,7 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
       made_c = corner && type >= 0; made_p = !corner && type >= 0;
     } else {
       a.slow_list[(size_t)lane * (a.cap_sharp + a.cap_flat) + atomicAdd(&a.slow_cnt[lane], 1)] = f;
+      atomicAdd(&s.stats.odo_slow[a.outer], 1); atomicAdd(&s.stats.odo_slow_why[why], 1);
     }
   }
   const int nc = __popc(__ballot_sync(0xffffffffu, made_c)), np = __popc(__ballot_sync(0xffffffffu, made_p));
@@ -412,17 +419,22 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
     if (corner) { const int* c = a.corner_corr + (((size_t)lane * a.slots + (a.outer - 1) % a.slots) * a.cap_sharp + f) * 2; pc = c[0]; pB = c[1]; }
     else { const int* c = a.plane_corr + (((size_t)lane * a.slots + (a.outer - 1) % a.slots) * a.cap_flat + (f - ns)) * 3; pc = c[0]; pA = c[1]; pB = c[2]; }
   }
-  bool boxed = false;
+  bool boxed = false, boxed_mid = false;
   if (pc >= 0) {
     const float dp = sqdist3(C[pc], sel.x, sel.y, sel.z);
     const float rad = sqrtf(dp) * 1.0001f + 1e-5f;
     if (rad < gfine.cell) { boxed = true; d = dp; id = pc; }
+    else if (rad < gmid.cell && gmid.dim[0] > 0) { boxed_mid = true; d = dp; id = pc; }   // bound between a fine and a middle cell: box on the 2 m grid
   }
   if (__any_sync(0xffffffffu, boxed)) {
     tile_box_nn1<TW>(gfine, boxed, sel, sqrtf(d) * 1.0001f + 1e-5f, d, id);
     key = id; tile_min3<TW>(d, key, id);
   }
-  const bool unboxed = have && !boxed;
+  if (__any_sync(0xffffffffu, boxed_mid)) {
+    tile_box_nn1<TW>(gmid, boxed_mid, sel, sqrtf(d) * 1.0001f + 1e-5f, d, id);
+    key = id; tile_min3<TW>(d, key, id);
+  }
+  const bool unboxed = have && !boxed && !boxed_mid;
   if (__any_sync(0xffffffffu, unboxed)) {
     tile_block_nn1<TW>(gfine, unboxed, sel, d, id);
     key = id; tile_min3<TW>(d, key, id);

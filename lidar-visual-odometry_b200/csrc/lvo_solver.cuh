@@ -23,7 +23,12 @@
 #include "lvo_internal.h"
 #include <float.h>
 
+#ifndef LVO_LM_THREADS
 #define LVO_LM_THREADS 384     // one CTA per lane: 12 warps x <= 170 registers, no spills; block barriers instead of cluster barriers
+#endif
+#ifndef LVO_LM_MINB
+#define LVO_LM_MINB 1
+#endif
 #define LVO_NACC 28  // 21 + 6 + 1
 
 // ---- small dense routines (double) ---------------------------------------------------------------------------
@@ -407,7 +412,7 @@ __device__ __noinline__ bool lm_next_step(const SolveArgs& a, int lane, LmCtl& c
 }
 
 template <bool DISTORT>
-__global__ void __launch_bounds__(LVO_LM_THREADS, 1) k_lm_solve(SolveArgs a) {
+__global__ void __launch_bounds__(LVO_LM_THREADS, LVO_LM_MINB) k_lm_solve(SolveArgs a) {
   __shared__ LmShared sh;
   __shared__ LmCtl ctl;  // only thread 0 touches it; shared to keep it out of its registers
   const bool lead = threadIdx.x == 0;
