@@ -134,8 +134,8 @@ def knn_throughput(L, frames, reps, device, peak):
     map data, cold L2.  Two workloads:
       config3  : `frames` x (corner, surf) problems of config-3 size (~100 k corner + ~390 k surf map points, ~8 k queries of one
                  sweep per frame, all within ~60 m of the sensor) — the queries touch a quarter of the map;
-      covering : the same maps with the queries spread over the WHOLE map (one query per ~5 map points), so that the algorithmic
-                 bytes 16 M + 56 Q are bytes the search really needs."""
+      covering : the same maps with the queries spread over the WHOLE map (one query per ~5 map points, in the voxel-index order a
+                 pcl::VoxelGrid output has), so that the algorithmic bytes 16 M + 56 Q are bytes the search really needs."""
     import torch
     g = torch.Generator(device="cuda").manual_seed(1234)
     ax = torch.arange(-125.0, 125.0, 0.4, device="cuda")
@@ -159,6 +159,14 @@ def knn_throughput(L, frames, reps, device, peak):
     qc_s[:, :3] += torch.randn(len(qc_s), 3, device="cuda", generator=g) * 0.2
     qc_c = corner[torch.randperm(len(corner), device="cuda", generator=g)[:len(corner) // 5]].clone()
     qc_c[:, :3] += torch.randn(len(qc_c), 3, device="cuda", generator=g) * 0.1
+
+    def voxel_order(q, leaf):
+        # the order pcl::VoxelGrid leaves a cloud in (z, y, x voxel index ascending): what the stack of laserMapping.cpp:543-549 looks like
+        v = torch.floor(q[:, :3] / leaf).to(torch.int64)
+        v -= v.min(0).values
+        key = (v[:, 2] * (int(v[:, 1].max()) + 1) + v[:, 1]) * (int(v[:, 0].max()) + 1) + v[:, 0]
+        return q[torch.argsort(key, stable=True)].contiguous()
+    qc_s, qc_c = voxel_order(qc_s, 0.8), voxel_order(qc_c, 0.4)
     out = {}
     for name, (qa, qb), nfr in (("config3", (q_c, q_s), frames), ("covering", (qc_c, qc_s), max(1, frames // 2))):
         maps, queries, mc, qc = [], [], [], []
@@ -722,7 +730,7 @@ def main():
                 "full_schedule": None if ms_f != ms_f else {"value": scans / (ms_f * 1e-3), "unit": "scans/s", "ms_per_step": ms_f / args.steps,
                                                             "what": "device-resident arm with LVO_OPT_FIXPOINT_SKIP = 0: all ten outer iterations run for every lane"},
                 "single_trajectory": single,
-                "roofline": {"bound": "hbm", "kernel": "k_map_knn (5-NN grid search)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "roofline": {"bound": "hbm", "kernel": "k_map_knn_reuse (5-NN grid search of lvo_scan_to_map; LVO_OPT_KNN_REUSE carries certified neighbour sets across outer iterations)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak if peak else None,
                              # dram__bytes_read.sum + dram__bytes_write.sum per launch of an `ncu --set full` capture taken in the SAME launch state
                              # (lanes per launch, frame index, commit recorded in profiles/r2_traffic.json); null when no such capture exists
