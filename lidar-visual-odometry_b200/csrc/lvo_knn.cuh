@@ -215,6 +215,12 @@ struct TopK {
 #pragma unroll
     for (int k = 0; k < K; ++k) { d[k] = FLT_MAX; id[k] = INT_MAX; }
   }
+  // empty list that only accepts candidates with d < bound, or d == bound (they rank before the INT_MAX placeholders): for searches whose
+  // result is void anyway unless K candidates lie inside `bound`, most candidates of a cell block are then rejected by ONE comparison
+  __device__ __forceinline__ void init(float bound) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) { d[k] = bound; id[k] = INT_MAX; }
+  }
   __device__ __forceinline__ static bool less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
   __device__ __forceinline__ void insert(float dd, int ii) {
     if (!less(dd, ii, d[K - 1], id[K - 1])) return;
@@ -315,7 +321,7 @@ __device__ __forceinline__ void thread_scan_row(const GridView& g, int cz, int c
 }
 template <int K>
 __device__ __forceinline__ bool thread_knn(const GridView& g, float qx, float qy, float qz, float max_sq, TopK<K>& tk) {
-  tk.init();
+  tk.init(max_sq);   // a candidate at or beyond the gate can only end in a void result (the test at the end), so it need not be ranked
   if (g.dim[0] <= 0) return false;
   const int cx = cell_coord(qx, g.inv_cell) - g.org[0], cy = cell_coord(qy, g.inv_cell) - g.org[1], cz = cell_coord(qz, g.inv_cell_z) - g.org[2];
   int R = (int)ceilf(sqrtf(max_sq) * g.inv_cell);

@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(128) k_map_knn(MapArgs a) {
 //   otherwise the query is searched in full again.  All comparisons carry margins (1e-4 relative + 1e-5 m) that dwarf float rounding
 //   (~1e-7 relative), and they only decide WHETHER the shortcut is taken, never a result.  A query whose row did not change keeps its
 //   factor record (the fit depends only on the query point and on the ordered neighbour points), so k_map_fit_reuse skips it.
+#define LVO_KNN_PRUNE_SQ 1.21f   // full searches rank candidates inside 1.1 m only: the gate is 1 m, the rest only feeds the guard radius
 #define LVO_KF_ROW 1       // the row of the latest iteration is valid (5 neighbours inside the gate)
 #define LVO_KF_FACTOR 2    // the factor record of the latest fit is valid (type >= 0)
 #define LVO_KF_CHANGED 4   // the row changed in this iteration: k_map_fit_reuse must refit
@@ -272,14 +273,15 @@ __device__ __forceinline__ float knn_guard(const GridView& g, float qx, float qy
   const float lx = qx - fx * g.cell, ly = qy - fy * g.cell, lz = qz - fz * cz_size;   // offsets inside the cell, in [0, cell]
   const float bx = fminf(lx, g.cell - lx) + g.cell, by = fminf(ly, g.cell - ly) + g.cell, bz = fminf(lz, cz_size - lz) + cz_size;
   float gd = fminf(fminf(bx, by), bz);
-  if (tk.id[5] != INT_MAX) gd = fminf(gd, sqrtf(tk.d[5]));
+  // candidates are only ranked inside LVO_KNN_PRUNE_SQ (TopK::init(bound)): an empty sixth slot means "nothing else inside that radius"
+  gd = fminf(gd, sqrtf(tk.d[5]));
   return fmaxf(gd * 0.9999f - 1e-5f, 0.f);
 }
 
 // Full search of one query by ONE thread (the form of thread_knn, six best): used in outer iteration 0, where every query of the lane is
 // searched and the thread-per-query form keeps the most searches in flight (measured: 135 us against 220 us for the tile form at 128 lanes).
 __device__ __forceinline__ void thread_knn6_block(const GridView& g, float qx, float qy, float qz, TopK<6>& tk) {
-  tk.init();
+  tk.init(LVO_KNN_PRUNE_SQ);
   if (g.dim[0] <= 0) return;
   const int cx = cell_coord(qx, g.inv_cell) - g.org[0], cy = cell_coord(qy, g.inv_cell) - g.org[1], cz = cell_coord(qz, g.inv_cell_z) - g.org[2];
   unsigned rb[9], re[9];
@@ -346,7 +348,7 @@ __device__ __forceinline__ void tile_merge(TopK<K>& tk) {
 // and a warp waits for its slowest lane (ncu: 10 of 32 threads active); the tile shares a query's candidates between 8 lanes.
 __device__ __forceinline__ void tile8_knn6_block(const GridView& g, bool active, float qx, float qy, float qz, TopK<6>& tk, float& guard) {
   const int tl = (int)tile_lane<8>();
-  tk.init();
+  tk.init(LVO_KNN_PRUNE_SQ);
   guard = 0.f;
   const int cx = cell_coord(qx, g.inv_cell) - g.org[0], cy = cell_coord(qy, g.inv_cell) - g.org[1], cz = cell_coord(qz, g.inv_cell_z) - g.org[2];
   auto consider = [&](float4 p, int) { tk.insert(sqdist3(p, qx, qy, qz), __float_as_int(p.w)); };
