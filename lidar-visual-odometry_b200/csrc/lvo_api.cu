@@ -490,8 +490,8 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
   LVO_TRY(dalloc(c, &vx.seg_div, 2 * NS)); LVO_TRY(dalloc(c, &vx.seg_mode, NS)); LVO_TRY(dalloc(c, &vx.d_vbits, 1)); LVO_TRY(dalloc(c, &vx.d_bits, 1));
   for (int k = 0; k < 2; ++k) { LVO_TRY(dalloc(c, &vx.sort.keys[k], NI, false)); LVO_TRY(dalloc(c, &vx.sort.vals[k], NI, false)); }
   const size_t tiles = (size_t)lvo_div_up((long long)NI, LVO_SORT_TILE) + 1;
-  LVO_TRY(dalloc(c, &vx.sort.hist, 256 * tiles)); LVO_TRY(dalloc(c, &vx.sort.d_hist_len, 1));
-  LVO_TRY(alloc_scan(c, &vx.sort.scan, 256 * tiles));
+  LVO_TRY(dalloc(c, &vx.sort.ghist, (size_t)LVO_SORT_GHIST_WORDS)); LVO_TRY(dalloc(c, &vx.sort.d_epoch, 1));
+  LVO_TRY(dalloc(c, &vx.sort.status, 256 * tiles));   // zero-filled once: epoch 0 never matches (k_sort_ghist bumps the epoch before the first pass)
   vx.sort.cap = vx.cap_items;
   LVO_TRY(dalloc(c, &vx.outpos, NI)); LVO_TRY(dalloc(c, &vx.out_pts, NI, false)); LVO_TRY(dalloc(c, &vx.out_aux, NI));
   LVO_TRY(dalloc(c, &vx.seg_out_cnt, NS)); LVO_TRY(dalloc(c, &vx.seg_out_start, NS + 1)); LVO_TRY(dalloc(c, &vx.d_n_out, 1));

@@ -123,53 +123,54 @@ static inline void lvo_scan_exclusive(cudaStream_t st, unsigned* data, const int
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// stable LSD radix sort of (u64 key, u32 value), 8 bits per pass
+// stable LSD radix sort of (u64 key, u32 value), 8 bits per pass, ONE kernel per pass ("onesweep" structure):
+//   k_sort_ghist     one sweep over the keys builds the digit histograms of ALL passes (shared-memory atomics, one global atomic per
+//                    bin and block); it also opens a new epoch for the tile status words;
+//   k_sort_onesweep  per pass: a block takes the next tile (atomic ticket, so a tile's predecessors are always running or done),
+//                    ranks its 4096 keys by digit (warp match + per-warp counters, stable), publishes the tile's digit counts in a
+//                    status word per (tile, digit) and obtains its global offsets by DECOUPLED LOOK-BACK over the preceding tiles
+//                    (thread d walks digit d: add aggregates until a tile with an inclusive prefix is met), then scatters.
+// Against the former histogram / 3-kernel scan / scatter sequence this is 1 launch per pass instead of 5, no per-tile histogram
+// array in HBM and one read of the keys less per pass.  A status word is (tag << 32 | count) with tag = 2 * (8 * epoch + pass) + flag:
+// the epoch is a DEVICE counter bumped by k_sort_ghist, so stale words of earlier sorts (or earlier replays of a captured graph)
+// never match and the array needs no clearing.
 // ---------------------------------------------------------------------------------------------------------------
 struct LvoSortBufs {
   unsigned long long* keys[2];
   unsigned* vals[2];
-  unsigned* hist;   // 256 * cap_tiles
-  int* d_hist_len;  // device scalar
-  LvoScanScratch scan;
-  int cap;          // capacity in pairs
+  unsigned* ghist;               // [8][256] digit histograms of all passes, then [8] tile tickets
+  unsigned long long* status;    // [cap_tiles][256]
+  unsigned* d_epoch;             // device scalar
+  int cap;                       // capacity in pairs
 };
+#define LVO_SORT_GHIST_WORDS (8 * 256 + 8)
 
 __device__ __forceinline__ int lvo_sort_passes(int bits) { return (bits + 7) >> 3; }
 
-__global__ void k_sort_hist(const unsigned long long* __restrict__ keys0, const unsigned long long* __restrict__ keys1, const int* __restrict__ d_n,
-                            const int* __restrict__ d_bits, int pass, unsigned* __restrict__ hist, int* __restrict__ d_hist_len) {
-  __shared__ unsigned h[256];
-  const int bits = *d_bits;
-  if (pass * 8 >= bits) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *d_hist_len = 0;
-    return;
-  }
+__global__ void __launch_bounds__(256) k_sort_ghist(const unsigned long long* __restrict__ keys, const int* __restrict__ d_n, const int* __restrict__ d_bits,
+                                                    unsigned* __restrict__ ghist, unsigned* __restrict__ d_epoch) {
+  __shared__ unsigned h[8][256];
+  const int passes = min(lvo_sort_passes(*d_bits), 8);
   const int n = *d_n;
-  const int ntiles = (n + LVO_SORT_TILE - 1) / LVO_SORT_TILE;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *d_hist_len = 256 * ntiles;
-  const unsigned long long* keys = (pass & 1) ? keys1 : keys0;
-  const int shift = pass * 8;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    h[threadIdx.x] = 0;
-    __syncthreads();
-    const int base = tile * LVO_SORT_TILE;
-#pragma unroll
-    for (int k = 0; k < LVO_SORT_ITEMS; ++k) {
-      int i = base + k * LVO_SORT_THREADS + threadIdx.x;
-      if (i < n) atomicAdd(&h[(unsigned)(keys[i] >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    hist[threadIdx.x * ntiles + tile] = h[threadIdx.x];
-    __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *d_epoch = *d_epoch + 1u;   // read by the pass kernels, which start after this kernel has finished
+  for (int k = threadIdx.x; k < 8 * 256; k += blockDim.x) (&h[0][0])[k] = 0;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long key = keys[i];
+    for (int p = 0; p < passes; ++p) atomicAdd(&h[p][(unsigned)(key >> (8 * p)) & 255u], 1u);
   }
+  __syncthreads();
+  for (int k = threadIdx.x; k < passes * 256; k += blockDim.x) { const unsigned v = (&h[0][0])[k]; if (v) atomicAdd(&ghist[k], v); }
 }
 
-__global__ void __launch_bounds__(LVO_SORT_THREADS)
-k_sort_scatter(unsigned long long* __restrict__ keys0, unsigned long long* __restrict__ keys1, unsigned* __restrict__ vals0,
-               unsigned* __restrict__ vals1, const int* __restrict__ d_n, const int* __restrict__ d_bits, int pass,
-               const unsigned* __restrict__ hist) {
+__global__ void __launch_bounds__(LVO_SORT_THREADS, 2)
+k_sort_onesweep(unsigned long long* __restrict__ keys0, unsigned long long* __restrict__ keys1, unsigned* __restrict__ vals0,
+                unsigned* __restrict__ vals1, const int* __restrict__ d_n, const int* __restrict__ d_bits, int pass,
+                unsigned* __restrict__ ghist, unsigned long long* status, const unsigned* __restrict__ d_epoch) {
   __shared__ unsigned wcnt[LVO_SORT_WARPS][256];
   __shared__ unsigned gbase[256];
+  __shared__ unsigned sm_scan[33];
+  __shared__ int s_tile;
   const int bits = *d_bits;
   if (pass * 8 >= bits) return;
   const int n = *d_n;
@@ -181,9 +182,17 @@ k_sort_scatter(unsigned long long* __restrict__ keys0, unsigned long long* __res
   const int shift = pass * 8;
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const unsigned tag = 2u * (8u * (*d_epoch) + (unsigned)pass);   // + 1: inclusive prefix
+  unsigned* ticket = ghist + 8 * 256 + pass;
+  // first output position of every digit: exclusive scan of this pass's histogram (thread d <-> digit d)
+  unsigned tot_unused;
+  const unsigned digit_base = block_excl_scan(ghist[pass * 256 + threadIdx.x], sm_scan, &tot_unused);
+  while (true) {
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
     for (int k = threadIdx.x; k < LVO_SORT_WARPS * 256; k += LVO_SORT_THREADS) (&wcnt[0][0])[k] = 0;
     __syncthreads();
+    const int tile = s_tile;
+    if (tile >= ntiles) break;
     unsigned long long key[LVO_SORT_ITEMS];
     unsigned val[LVO_SORT_ITEMS];
     unsigned short lpos[LVO_SORT_ITEMS];
@@ -214,7 +223,20 @@ k_sort_scatter(unsigned long long* __restrict__ keys0, unsigned long long* __res
         wcnt[ww][d] = run;
         run += t;
       }
-      gbase[d] = hist[d * ntiles + tile];
+      // decoupled look-back over the preceding tiles of this pass
+      volatile unsigned long long* st = status;
+      unsigned excl = 0;
+      if (tile > 0) {
+        st[(size_t)tile * 256 + d] = ((unsigned long long)tag << 32) | run;   // aggregate of this tile
+        for (int t = tile - 1; t >= 0; --t) {
+          unsigned long long v;
+          do { v = st[(size_t)t * 256 + d]; } while (((unsigned)(v >> 32) | 1u) != (tag | 1u));
+          excl += (unsigned)v;
+          if ((unsigned)(v >> 32) & 1u) break;   // inclusive prefix: everything before tile t is in it
+        }
+      }
+      st[(size_t)tile * 256 + d] = ((unsigned long long)(tag | 1u) << 32) | (excl + run);
+      gbase[d] = digit_base + excl;
     }
     __syncthreads();
 #pragma unroll
@@ -236,12 +258,12 @@ k_sort_scatter(unsigned long long* __restrict__ keys0, unsigned long long* __res
 static inline void lvo_sort_pairs(cudaStream_t st, const LvoSortBufs& b, const int* d_n, int n_cap, const int* d_bits, int max_bits,
                                   long long* launches) {
   int tiles = lvo_div_up(n_cap, LVO_SORT_TILE);
-  int grid = tiles < 1184 ? (tiles < 1 ? 1 : tiles) : 1184;
+  int grid = tiles < 592 ? (tiles < 1 ? 1 : tiles) : 592;
   int passes = (max_bits + 7) / 8;
-  for (int p = 0; p < passes; ++p) {
-    k_sort_hist<<<grid, LVO_SORT_THREADS, 0, st>>>(b.keys[0], b.keys[1], d_n, d_bits, p, b.hist, b.d_hist_len);
-    lvo_scan_exclusive(st, b.hist, b.d_hist_len, 256 * tiles, nullptr, b.scan, launches);
-    k_sort_scatter<<<grid, LVO_SORT_THREADS, 0, st>>>(b.keys[0], b.keys[1], b.vals[0], b.vals[1], d_n, d_bits, p, b.hist);
-    if (launches) *launches += 2;
-  }
+  if (passes > 8) passes = 8;
+  cudaMemsetAsync(b.ghist, 0, sizeof(unsigned) * LVO_SORT_GHIST_WORDS, st);
+  k_sort_ghist<<<max(1, min(lvo_div_up(n_cap, 256 * 16), 592)), 256, 0, st>>>(b.keys[0], d_n, d_bits, b.ghist, b.d_epoch);
+  for (int p = 0; p < passes; ++p)
+    k_sort_onesweep<<<grid, LVO_SORT_THREADS, 0, st>>>(b.keys[0], b.keys[1], b.vals[0], b.vals[1], d_n, d_bits, p, b.ghist, b.status, b.d_epoch);
+  if (launches) *launches += 1 + passes;
 }
