@@ -145,20 +145,20 @@ __global__ void k_setup_grid_problems(GridProblem* prob, int nprob, const float4
                                       LaneState* ls, int which, float cell) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nprob) return;
-  const int per = which == 0 ? 8 : 2;
+  const int per = which == 0 ? LVO_ODO_GRIDS : 2;
   const int lane = p / per, t = p & 1;
   prob[p].pts = (t ? base1 + (size_t)lane * stride1 : base0 + (size_t)lane * stride0);
   if (which == 0) prob[p].d_n = t ? &ls[lane].n_surf_last : &ls[lane].n_corner_last;
   else prob[p].d_n = &ls[lane].from_off[t][LVO_MAX_VALID];
   const int k = p % per;
   // odometry: fine grid 0.5 x 0.5 x 2 m for the surf cloud (dense in x-y, sparse in z), 1 x 1 x 2 m for the corner cloud,
-  // middle grids 2 m, coarse grids 8 m
-  prob[p].want_cell = which == 0 ? (k >= 6 ? 8.0f : (k >= 4 ? 2.0f : (k == 1 ? 0.5f : 1.0f))) : cell;
-  prob[p].want_cell_z = which == 0 ? (k >= 6 ? 8.0f : 2.0f) : 0.f;
+  // middle grids 2 m (their shells cover the 5 m gate; the former 8 m coarse grids were built every frame and never searched)
+  prob[p].want_cell = which == 0 ? (k >= 4 ? 2.0f : (k == 1 ? 0.5f : 1.0f)) : cell;
+  prob[p].want_cell_z = which == 0 ? 2.0f : 0.f;
   prob[p].mode = (which == 0 && (k == 2 || k == 3)) ? 1 : 0;
   // share of the cell table (lvo_odo_cells_cap): the fine grids get 4 M cells, the (ring, azimuth) grids their fixed size, the 2 m
   // and 8 m grids 1/8 and 1/64 of the fine share; a grid that does not fit doubles its cell edge (k_grid_setup)
-  prob[p].cells_cap = which == 0 ? (k < 2 ? (1 << 22) : (k < 4 ? LVO_AZ_BUCKETS * LVO_AZ_RINGS : (k < 6 ? (1 << 19) : (1 << 16)))) : 0;
+  prob[p].cells_cap = which == 0 ? (k < 2 ? (1 << 22) : (k < 4 ? LVO_AZ_BUCKETS * LVO_AZ_RINGS : (1 << 19))) : 0;
   prob[p].clamp_xy = 0.f;
   prob[p].bbox_from = (which == 0 && k >= 4) ? p - k + (k & 1) : -1;   // middle / coarse grids reuse the fine grid's box
 }
@@ -442,9 +442,9 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
   LVO_TRY(dalloc(c, &od.slow_list, (size_t)L * (c->cap_sharp + c->cap_flat))); LVO_TRY(dalloc(c, &od.slow_cnt, (size_t)L));
   LVO_TRY(dalloc(c, &od.corner_corr, (size_t)L * slots * c->cap_sharp * 2));
   LVO_TRY(dalloc(c, &od.plane_corr, (size_t)L * slots * c->cap_flat * 3));
-  const size_t odo_cells = 2 * ((size_t)(1 << 22) + (size_t)LVO_AZ_BUCKETS * LVO_AZ_RINGS + (1 << 19) + (1 << 16));   // per lane, see k_setup_grid_problems
-  LVO_TRY(alloc_grid(c, &od.grid, 8 * L, 1 << 22, (size_t)4 * L * (c->cap_lsharp + P), P, odo_cells * L));
-  k_setup_grid_problems<<<lvo_div_up(8 * L, 64), 64, 0, c->st>>>(od.grid.prob, 8 * L, od.corner_last, (size_t)c->cap_lsharp, od.surf_last, (size_t)P, c->d_ls, 0, 1.0f);
+  const size_t odo_cells = 2 * ((size_t)(1 << 22) + (size_t)LVO_AZ_BUCKETS * LVO_AZ_RINGS + (1 << 19));   // per lane, see k_setup_grid_problems
+  LVO_TRY(alloc_grid(c, &od.grid, LVO_ODO_GRIDS * L, 1 << 22, (size_t)3 * L * (c->cap_lsharp + P), P, odo_cells * L));
+  k_setup_grid_problems<<<lvo_div_up(LVO_ODO_GRIDS * L, 64), 64, 0, c->st>>>(od.grid.prob, LVO_ODO_GRIDS * L, od.corner_last, (size_t)c->cap_lsharp, od.surf_last, (size_t)P, c->d_ls, 0, 1.0f);
 
   // ---- mapping
   MapArgs& mp = c->map;

@@ -28,7 +28,10 @@
 #define LVO_VSEGS (LVO_MAX_VALID + 1)                        // + one pseudo segment for inserts into non-valid cubes
 
 // One residual block, the parameters of the reference functors (lidarFactor.hpp):
-//   type 0 LidarEdgeFactor      : c = curr_point, a = last_point_a, b = last_point_b, d = s (interpolation ratio; 1 unless DISTORTION)
+//   type 0 LidarEdgeFactor      : c = curr_point, a = last_point_a, b = (last_point_a - last_point_b) / |last_point_a - last_point_b| (the unit
+//                                 direction of the edge, taken once when the record is written: the functor's residual
+//                                 (lp - a) x (lp - b) / |a - b| equals (lp - a) x b' exactly, and its Jacobian with respect to lp is -[b']x,
+//                                 so an evaluation needs no square root and no division), d = s (interpolation ratio; 1 unless DISTORTION)
 //   type 1 LidarPlaneFactor     : c = curr_point, a = last_point_j, b = ljm_norm (unit normal, built at construction), d = s
 //   type 2 LidarPlaneNormFactor : c = curr_point, a = plane_unit_norm, d = negative_OA_dot_norm
 //   type -1 : no factor for this feature
@@ -36,6 +39,14 @@ struct __align__(16) LvoFactor {
   double c[3], a[3], b[3], d;
   int type, pad;
 };
+#ifdef __CUDACC__
+// b slot of a type-0 record from the two line points (lidarFactor.hpp:36-37: de = lpa - lpb, de.norm())
+__device__ __forceinline__ void lvo_edge_direction(const double* a, const double* b, double* e) {
+  const double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+  const double den = sqrt(dx * dx + dy * dy + dz * dz);
+  e[0] = dx / den; e[1] = dy / den; e[2] = dz / den;
+}
+#endif
 
 // Scalars of one lane that live on the device.
 struct LaneState {

@@ -199,7 +199,8 @@ __device__ __forceinline__ void fit_factor(int t, const float4 ori, const float4
       fac.type = 0; fac.d = 1.0;
       fac.c[0] = ori.x; fac.c[1] = ori.y; fac.c[2] = ori.z;
       fac.a[0] = 0.1 * ux + center.x; fac.a[1] = 0.1 * uy + center.y; fac.a[2] = 0.1 * uz + center.z;
-      fac.b[0] = -0.1 * ux + center.x; fac.b[1] = -0.1 * uy + center.y; fac.b[2] = -0.1 * uz + center.z;
+      const double lb[3] = {-0.1 * ux + center.x, -0.1 * uy + center.y, -0.1 * uz + center.z};   // point_b :606-608
+      lvo_edge_direction(fac.a, lb, fac.b);
     }
   } else {
     double A[15], b[5] = {-1, -1, -1, -1, -1}, n[3];

@@ -18,6 +18,8 @@
 #include "lvo_knn.cuh"
 #include "lvo_solver.cuh"
 
+#define LVO_ODO_GRIDS 6   // search structures per lane over the previous sweep's two clouds
+
 struct OdoArgs {
   LaneState* ls;
   int lanes, outer;
@@ -30,7 +32,7 @@ struct OdoArgs {
   int cap_sharp, cap_lsharp, cap_flat, P;
   // previous sweep
   float4* corner_last; float4* surf_last;  // [lanes][cap_lsharp], [lanes][P]
-  GridSet grid;                            // problems 8*lane + {0/1 corner/surf fine xyz, 2/3 corner/surf (ring,azimuth), 4/5 corner/surf middle xyz, 6/7 corner/surf coarse xyz}
+  GridSet grid;                            // problems LVO_ODO_GRIDS*lane + {0/1 corner/surf fine xyz, 2/3 corner/surf (ring,azimuth), 4/5 corner/surf middle xyz}
   LvoFactor* factors; int factor_cap;
   int* slow_list;    // [lanes][cap_sharp + cap_flat] features the fast kernel hands to the tile kernel
   int* slow_cnt;     // [lanes]
@@ -181,7 +183,8 @@ __device__ __forceinline__ int odo_emit(const OdoArgs& a, int lane, int f, int n
         fac.type = 0;
         fac.c[0] = pt.x; fac.c[1] = pt.y; fac.c[2] = pt.z;
         fac.a[0] = pj.x; fac.a[1] = pj.y; fac.a[2] = pj.z;
-        fac.b[0] = pb.x; fac.b[1] = pb.y; fac.b[2] = pb.z;
+        const double lb[3] = {pb.x, pb.y, pb.z};
+        lvo_edge_direction(fac.a, lb, fac.b);
       }
     } else if (same >= 0 && other >= 0) {
       i1 = closest; i2 = same; i3 = other;
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
   const int lane = a.lane0 + blockIdx.y;
   LaneState& s = a.ls[lane];
   if (!s.odo_inited || s.odo_done) return;   // first frame / fixed point reached (LVO_OPT_FIXPOINT_SKIP)
-  if (threadIdx.x < 4) gv[threadIdx.x] = grid_view(a.grid, 8 * lane + threadIdx.x);
+  if (threadIdx.x < 4) gv[threadIdx.x] = grid_view(a.grid, LVO_ODO_GRIDS * lane + threadIdx.x);
   __syncthreads();
   const int ns = s.n_sharp, nf = s.n_flat;
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -381,11 +384,11 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
 
 template <int TW>
 __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
-  __shared__ GridView gv[8];
+  __shared__ GridView gv[LVO_ODO_GRIDS];
   const int lane = a.lane0 + blockIdx.y;
   LaneState& s = a.ls[lane];
   if (!s.odo_inited || s.odo_done) return;   // first frame / fixed point reached (LVO_OPT_FIXPOINT_SKIP)
-  if (threadIdx.x < 8) gv[threadIdx.x] = grid_view(a.grid, 8 * lane + threadIdx.x);
+  if (threadIdx.x < LVO_ODO_GRIDS) gv[threadIdx.x] = grid_view(a.grid, LVO_ODO_GRIDS * lane + threadIdx.x);
   __syncthreads();
   const int ns = s.n_sharp, nf = s.n_flat;
   const int tl = (int)tile_lane<TW>();

@@ -219,13 +219,12 @@ __device__ __forceinline__ void accumulate_factor(const LvoFactor& f, const doub
     double Jl[3][6];
     const d3 lp = interp_point_jacobian(x, f.d, d3{f.c[0], f.c[1], f.c[2]}, Jl);
     if (f.type == 0) {
-      const d3 u{lp.x - f.a[0], lp.y - f.a[1], lp.z - f.a[2]}, v{lp.x - f.b[0], lp.y - f.b[1], lp.z - f.b[2]};
-      const d3 nu = d3cross(u, v);
-      const d3 de{f.a[0] - f.b[0], f.a[1] - f.b[1], f.a[2] - f.b[2]};
-      const double den = sqrt(de.x * de.x + de.y * de.y + de.z * de.z);
-      const double r[3] = {nu.x / den, nu.y / den, nu.z / den};
+      // (lp - a) x (lp - b) / |a - b| = (lp - a) x e with e = (a - b) / |a - b| = f.b (lvo_internal.h); d r / d lp = -[e]x
+      const d3 u{lp.x - f.a[0], lp.y - f.a[1], lp.z - f.a[2]}, e{f.b[0], f.b[1], f.b[2]};
+      const d3 nu = d3cross(u, e);
+      const double r[3] = {nu.x, nu.y, nu.z};
       const double rho1 = loss(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-      const double D[3][3] = {{0, de.z / den, -de.y / den}, {-de.z / den, 0, de.x / den}, {de.y / den, -de.x / den, 0}};
+      const double D[3][3] = {{0, e.z, -e.y}, {-e.z, 0, e.x}, {e.y, -e.x, 0}};
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         double Jr[6];
@@ -246,13 +245,11 @@ __device__ __forceinline__ void accumulate_factor(const LvoFactor& f, const doub
   const d3 rc = quat_rotate(x, d3{f.c[0], f.c[1], f.c[2]});
   const d3 lp{rc.x + x[4], rc.y + x[5], rc.z + x[6]};
   if (f.type == 0) {
-    const d3 u{lp.x - f.a[0], lp.y - f.a[1], lp.z - f.a[2]}, v{lp.x - f.b[0], lp.y - f.b[1], lp.z - f.b[2]};
-    const d3 nu = d3cross(u, v);
-    const d3 de{f.a[0] - f.b[0], f.a[1] - f.b[1], f.a[2] - f.b[2]};
-    const double den = sqrt(de.x * de.x + de.y * de.y + de.z * de.z);
-    const double r[3] = {nu.x / den, nu.y / den, nu.z / den};
+    const d3 u{lp.x - f.a[0], lp.y - f.a[1], lp.z - f.a[2]}, e{f.b[0], f.b[1], f.b[2]};
+    const d3 nu = d3cross(u, e);
+    const double r[3] = {nu.x, nu.y, nu.z};
     const double rho1 = loss(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-    const double D[3][3] = {{0, de.z / den, -de.y / den}, {-de.z / den, 0, de.x / den}, {de.y / den, -de.x / den, 0}};
+    const double D[3][3] = {{0, e.z, -e.y}, {-e.z, 0, e.x}, {e.y, -e.x, 0}};
     const double Jp[3][3] = {{0, 2 * rc.z, -2 * rc.y}, {-2 * rc.z, 0, 2 * rc.x}, {2 * rc.y, -2 * rc.x, 0}};
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
