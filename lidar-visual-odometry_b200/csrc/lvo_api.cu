@@ -455,6 +455,7 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
   { const char* e = getenv("LVO_KNN_TILE"); mp.knn_tile = e ? atoi(e) : 0; }   // default: thread-per-query search (faster on sweep-shaped query sets, profiles/r2_summary.md)
   { const char* e = getenv("LVO_KNN_REUSE"); mp.knn_reuse = e ? atoi(e) : 1; }   // default: neighbour sets carried across the outer iterations with a certificate
   lvo_mapping_kernel_attributes();
+  lvo_extract_kernel_attributes();
   for (int t = 0; t < 2; ++t) {
     mp.map_cap[t] = mapc[t];
     for (int g = 0; g < 2; ++g) {
