@@ -111,6 +111,8 @@ typedef struct lvo_stats {
    * 5 m gate, 3 an adjacent-ring target exists but its azimuth window is wider than the fast limit, 4 an adjacent-ring target has no
    * candidate nearby.  Diagnostic only. */
   int odo_slow[16], odo_slow_why[5];
+  /* LVO_OPT_ODO_REUSE: scan-to-scan features per outer iteration whose correspondence was carried over under the certificate */
+  int odo_certified[16];
 } lvo_stats;
 
 typedef struct lvo_ctx lvo_ctx; /* one per (GPU, group of lanes); owns streams, device arenas, cross-frame state */
@@ -301,6 +303,13 @@ int lvo_set_stream(lvo_ctx* ctx, void* cuda_stream);
  * The certificate is conservative, so index sets, factors and poses are bitwise those of searching every time
  * (tests/test_gpu_mapping.py::test_knn_reuse_is_bitwise_identical); 0 = search and fit every query in every iteration. */
 #define LVO_OPT_KNN_REUSE 5
+/* LVO_OPT_ODO_REUSE (default 1; environment LVO_ODO_REUSE at lvo_create).  The same idea for lvo_scan_to_scan (laserOdometry.cpp:364):
+ * a feature's factor depends only on WHICH points of the previous sweep were chosen (closest point, same-ring and adjacent-ring
+ * partners, :386-440 / :470-532).  A full association also records guard radii for its three searches; in a later outer iteration
+ * a feature whose three points are certified still to be the strict minima keeps its factor record and is not searched again.
+ * Correspondences, factors and poses are bitwise those of searching every time
+ * (tests/test_gpu_odometry.py::test_odo_reuse_is_bitwise_identical); 0 = associate every feature in every iteration. */
+#define LVO_OPT_ODO_REUSE 6
 int lvo_set_option(lvo_ctx* ctx, int option, int value);
 /* Bytes copied device->host per lane at the end of every synchronous call (poses, counters, status). */
 size_t lvo_state_bytes(void);

@@ -39,7 +39,53 @@ struct OdoArgs {
   int* corner_corr;  // [lanes][slots][cap_sharp][2]   probes; the association of outer iteration o reads those of o - 1
   int* plane_corr;   // [lanes][slots][cap_flat][3]
   int slots;         // outer-iteration slots kept: LVO_MAX_OUTER with lvo_config::debug_probes, else 2 (slot = outer % slots)
+  // LVO_OPT_ODO_REUSE: certified reuse of a feature's correspondence across the outer iterations of a frame (see odo_certified)
+  int reuse;
+  float4* ref;       // [lanes][cap_sharp + cap_flat] feature position (TransformToStart) at its last full association
+  float4* guard;     // [lanes][cap_sharp + cap_flat] guard radii of that association: x closest point, y same-ring point, z adjacent-ring point
 };
+
+// ---- certified reuse of a correspondence across outer iterations (LVO_OPT_ODO_REUSE) ---------------------------------------------
+// The outer iterations of a frame (:364) associate the SAME two clouds from a pose that moves less and less, and a factor record
+// depends only on WHICH points were chosen (closest j; l / m in the same / adjacent rings), never on the pose.  A full association
+// at position q_ref therefore also records, for each of its (up to) three searches, a GUARD radius: a lower bound on the distance
+// from q_ref to every OTHER eligible point of that search — the smaller of the second-best candidate distance and the radius of the
+// region that was scanned completely (box half-width, azimuth window, the 5 m gate).  At a later position q_new, moved by delta, every
+// other eligible point is at least guard - delta away; if the chosen point's new distance is below that, and inside the 5 m gate
+// (:389 / :473), it is still the strict minimum.  The eligibility of l / m depends only on j and on fixed ring ids and indices, so
+// with j unchanged the filters are unchanged.  All three certified: the factor record stands and the feature is skipped.  Margins of
+// 1e-4 relative + 1e-5 m dwarf float rounding and only decide WHETHER the shortcut is taken.
+#define LVO_ODO_SLACK 0.05f   // extra radius (m) scanned around a full association so that the next iterations can be certified
+__device__ __forceinline__ float odo_guard_of(float d2_second, float region) {
+  const float g = fminf(fminf(sqrtf(d2_second), region), 5.0f);   // candidates at or beyond the gate are never ranked: they are >= 5 m away
+  return fmaxf(g * 0.9999f - 1e-5f, 0.f);
+}
+// radius around the query (horizontal range rho) inside which every point lies in the azimuth window of half-width h buckets
+// (inverse of az_halfwidth: two buckets of the half-width are quantisation / rounding margin)
+__device__ __forceinline__ float az_region(int h, float rho) {
+  if (2 * h + 1 >= LVO_AZ_BUCKETS) return FLT_MAX;
+  const float ang = (float)(h - 2) * (6.28318548f / (float)LVO_AZ_BUCKETS);
+  if (ang <= 0.f) return 0.f;
+  if (ang >= 1.5f) return rho * 0.99f;   // beyond ~86 degrees: a point outside the window is farther than rho sin(1.5)
+  return rho * sinf(ang) * 0.999f;
+}
+__device__ __forceinline__ int az_halfwidth(float d2, float rho);
+__device__ __forceinline__ int az_halfwidth_slack(float d2, float rho) {
+  const float d = sqrtf(d2) + LVO_ODO_SLACK;
+  return az_halfwidth(d * d, rho);
+}
+// true iff the previous iteration's correspondence (pc, pA, pB) of this feature is certified at `sel`
+__device__ __forceinline__ bool odo_certified(const OdoArgs& a, size_t fi, bool corner, float4 sel, const float4* C, int pc, int pA, int pB) {
+  if (pc < 0 || pB < 0 || (!corner && pA < 0)) return false;
+  const float4 g = a.guard[fi], r = a.ref[fi];
+  const float dx = sel.x - r.x, dy = sel.y - r.y, dz = sel.z - r.z;
+  const float delta = sqrtf(dx * dx + dy * dy + dz * dz) * 1.0001f + 1e-5f;
+  auto still = [&](int idx, float guard) {
+    const float dd = sqdist3(C[idx], sel.x, sel.y, sel.z);
+    return dd < 25.0f && sqrtf(dd) * 1.0001f + 1e-5f + delta < guard;
+  };
+  return still(pc, g.x) && still(pB, g.z) && (corner || still(pA, g.y));
+}
 
 __global__ void k_odo_begin(OdoArgs a) {
   const int lane = blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,7 +93,7 @@ __global__ void k_odo_begin(OdoArgs a) {
   LaneState& s = a.ls[lane];
   s.odo_status = s.odo_inited ? LVO_OK : LVO_W_FIRST_FRAME;
   s.odo_done = 0; s.stats.odo_outer_executed = 0;
-  for (int o = 0; o < LVO_MAX_OUTER; ++o) { s.stats.odo_corner_corr[o] = 0; s.stats.odo_plane_corr[o] = 0; s.stats.odo_lm_iters[o] = 0; s.stats.odo_final_cost[o] = 0; s.stats.odo_slow[o] = 0; }
+  for (int o = 0; o < LVO_MAX_OUTER; ++o) { s.stats.odo_corner_corr[o] = 0; s.stats.odo_plane_corr[o] = 0; s.stats.odo_lm_iters[o] = 0; s.stats.odo_final_cost[o] = 0; s.stats.odo_slow[o] = 0; s.stats.odo_certified[o] = 0; }
   for (int k = 0; k < 5; ++k) s.stats.odo_slow_why[k] = 0;
 }
 
@@ -96,13 +142,14 @@ __device__ __forceinline__ int az_halfwidth(float d2, float rho) {
 // ---- one 8-lane tile per feature (four features per warp); every call below is made by all 32 lanes --------------------
 // rows 3k .. 3k+2 (k = part) of the 3x3 row block around (cx, cy, cz): lanes 0..2 of the tile fetch the bounds
 template <int TW>
-__device__ __forceinline__ void tile_block_nn1(const GridView& g, bool active, float4 sel, float& d, int& id) {
+__device__ __forceinline__ void tile_block_nn1(const GridView& g, bool active, float4 sel, float& d, int& id, float& d2) {
   const int tl = (int)tile_lane<TW>();
   const int cx = cell_coord(sel.x, g.inv_cell) - g.org[0], cy = cell_coord(sel.y, g.inv_cell) - g.org[1], cz = cell_coord(sel.z, g.inv_cell_z) - g.org[2];
   auto consider = [&](float4 p, int) {
     const int i = __float_as_int(p.w);
     const float dd = sqdist3(p, sel.x, sel.y, sel.z);
-    if (dd < d || (dd == d && i < id)) { d = dd; id = i; }
+    if (dd < d || (dd == d && i < id)) { if (id != INT_MAX) d2 = fminf(d2, d); d = dd; id = i; }
+    else if (i != id) d2 = fminf(d2, dd);   // d2: best distance among the other candidates (guard radius of LVO_OPT_ODO_REUSE)
   };
   for (int base = 0; base < 9; base += TW) {   // 9 rows: two steps for 8-lane tiles, one for full warps
     const int row = base + tl;
@@ -115,12 +162,13 @@ __device__ __forceinline__ void tile_block_nn1(const GridView& g, bool active, f
 // on the nearest-neighbour distance is known (the previous outer iteration's closest point): any point that beats or ties
 // the bound lies inside the box.
 template <int TW>
-__device__ __forceinline__ void tile_box_nn1(const GridView& g, bool active, float4 sel, float rad, float& d, int& id) {
+__device__ __forceinline__ void tile_box_nn1(const GridView& g, bool active, float4 sel, float rad, float& d, int& id, float& d2) {
   const int tl = (int)tile_lane<TW>();
   auto consider = [&](float4 p, int) {
     const int i = __float_as_int(p.w);
     const float dd = sqdist3(p, sel.x, sel.y, sel.z);
-    if (dd < d || (dd == d && i < id)) { d = dd; id = i; }
+    if (dd < d || (dd == d && i < id)) { if (id != INT_MAX) d2 = fminf(d2, d); d = dd; id = i; }
+    else if (i != id) d2 = fminf(d2, dd);   // d2: best distance among the other candidates (guard radius of LVO_OPT_ODO_REUSE)
   };
   const int x0 = cell_coord(sel.x - rad, g.inv_cell) - g.org[0], x1 = cell_coord(sel.x + rad, g.inv_cell) - g.org[0];
   const int y0 = cell_coord(sel.y - rad, g.inv_cell) - g.org[1], y1 = cell_coord(sel.y + rad, g.inv_cell) - g.org[1];
@@ -137,14 +185,15 @@ __device__ __forceinline__ void tile_box_nn1(const GridView& g, bool active, flo
 // Shell r >= 2 of a grid, TW/2 rows per step.  Rows (and end cells) whose cell box is farther from the query than the
 // current bound min(best, gate) are skipped: a point `k` cells away along an axis is more than (k - 1) cells away.
 template <int TW>
-__device__ __forceinline__ void tile_shell_nn1(const GridView& g, bool active, float4 sel, int r, float gate, float& d, int& id) {
+__device__ __forceinline__ void tile_shell_nn1(const GridView& g, bool active, float4 sel, int r, float gate, float& d, int& id, float& d2) {
   const int tl = (int)tile_lane<TW>();
   constexpr int H = TW / 2;
   const int cx = cell_coord(sel.x, g.inv_cell) - g.org[0], cy = cell_coord(sel.y, g.inv_cell) - g.org[1], cz = cell_coord(sel.z, g.inv_cell_z) - g.org[2];
   auto consider = [&](float4 p, int) {
     const int i = __float_as_int(p.w);
     const float dd = sqdist3(p, sel.x, sel.y, sel.z);
-    if (dd < d || (dd == d && i < id)) { d = dd; id = i; }
+    if (dd < d || (dd == d && i < id)) { if (id != INT_MAX) d2 = fminf(d2, d); d = dd; id = i; }
+    else if (i != id) d2 = fminf(d2, dd);   // d2: best distance among the other candidates (guard radius of LVO_OPT_ODO_REUSE)
   };
   const float cz_size = 1.0f / g.inv_cell_z;
   const int side = 2 * r + 1, nrows = side * side;
@@ -170,7 +219,11 @@ __device__ __forceinline__ void tile_shell_nn1(const GridView& g, bool active, f
 
 // factor record + correspondence probes of one feature (laserOdometry.cpp:442-462 / :534-557); returns the factor type
 __device__ __forceinline__ int odo_emit(const OdoArgs& a, int lane, int f, int ns, bool corner, bool ok, float4 pt, const float4* C, int closest, float4 pj,
-                                        int same, int other) {
+                                        int same, int other, float4 sel = make_float4(0.f, 0.f, 0.f, 0.f), float4 guard = make_float4(0.f, 0.f, 0.f, 0.f)) {
+  if (a.reuse) {
+    const size_t fi = (size_t)lane * (a.cap_sharp + a.cap_flat) + f;
+    a.ref[fi] = sel; a.guard[fi] = guard;
+  }
   LvoFactor fac;
   fac.type = -1; fac.pad = 0;
   fac.d = distortion_ratio(pt.w, a.distortion);   // s of LidarEdgeFactor / LidarPlaneFactor, :455-459 / :549-553
@@ -238,7 +291,7 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
   __syncthreads();
   const int ns = s.n_sharp, nf = s.n_flat;
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  bool made_c = false, made_p = false;
+  bool made_c = false, made_p = false, certified = false;
   if (f < ns + nf) {
     const bool corner = f < ns;
     const float4* C = corner ? a.corner_last + (size_t)lane * a.cap_lsharp : a.surf_last + (size_t)lane * a.P;
@@ -251,23 +304,34 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
       if (corner) { const int* c = a.corner_corr + (((size_t)lane * a.slots + (a.outer - 1) % a.slots) * a.cap_sharp + f) * 2; pc = c[0]; pB = c[1]; }
       else { const int* c = a.plane_corr + (((size_t)lane * a.slots + (a.outer - 1) % a.slots) * a.cap_flat + (f - ns)) * 3; pc = c[0]; pA = c[1]; pB = c[2]; }
     }
-    float d = FLT_MAX; int id = INT_MAX;
+    const size_t fi = (size_t)lane * (a.cap_sharp + a.cap_flat) + f;
+    certified = a.reuse && a.outer > 0 && odo_certified(a, fi, corner, sel, C, pc, pA, pB);
+    if (certified) {
+      // same three points as in the previous iteration: the factor record stands; carry the row into this iteration's slot
+      if (corner) { int* c = a.corner_corr + (((size_t)lane * a.slots + a.outer % a.slots) * a.cap_sharp + f) * 2; c[0] = pc; c[1] = pB; }
+      else { int* c = a.plane_corr + (((size_t)lane * a.slots + a.outer % a.slots) * a.cap_flat + (f - ns)) * 3; c[0] = pc; c[1] = pA; c[2] = pB; }
+      made_c = corner; made_p = !corner;
+    } else {
+    float d = FLT_MAX, d2c = FLT_MAX; int id = INT_MAX;
     auto near = [&](float4 p) {
       const int i = __float_as_int(p.w);
       const float dd = sqdist3(p, sel.x, sel.y, sel.z);
-      if (dd < d || (dd == d && i < id)) { d = dd; id = i; }
+      if (dd < d || (dd == d && i < id)) { if (id != INT_MAX) d2c = fminf(d2c, d); d = dd; id = i; }
+      else if (i != id) d2c = fminf(d2c, dd);
     };
     const int cx = cell_coord(sel.x, g.inv_cell) - g.org[0], cy = cell_coord(sel.y, g.inv_cell) - g.org[1], cz = cell_coord(sel.z, g.inv_cell_z) - g.org[2];
     // ---- bound on the closest point: the previous iteration's closest point, else the best point of the query's own cell
     if (pc >= 0) { d = sqdist3(C[pc], sel.x, sel.y, sel.z); id = pc; }
     else if (g.dim[0] > 0) { unsigned b, e; row_bounds(g, cz, cy, cx, cx, b, e); scan_range4(g.pts, b, e, near); }
+    d2c = FLT_MAX;   // the second-best distance is taken from the box query below, which sees every point inside the box (the bound itself again too)
     float rad = sqrtf(d) * 1.0001f + 1e-5f;
+    if (a.reuse && rad + LVO_ODO_SLACK < g.cell) rad += LVO_ODO_SLACK;   // a little more than needed: room for the next iterations' certificates
     // (a box query on the 2 m middle grid for bounds between 0.5 and 2 m was tried here: it halves the list handed to the warp-per-feature
     // kernel but one thread then walks a (4 m)^3 box while its warp waits — association time went from 4.1 to 5.1 ms per 128-lane frame)
     bool fast = id != INT_MAX && rad < g.cell && (double)d < 25.0;
     int why = id == INT_MAX ? 0 : (!(rad < g.cell) ? 1 : 2);
     int closest = -1, same = -1, other = -1;
-    float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 pj = make_float4(0.f, 0.f, 0.f, 0.f), guard = make_float4(0.f, 0.f, 0.f, 0.f);
     if (fast) {
       // ---- closest point: box query on the fine grid (every cell that intersects [q - rad, q + rad])
       const int x0 = cell_coord(sel.x - rad, g.inv_cell) - g.org[0], x1 = cell_coord(sel.x + rad, g.inv_cell) - g.org[0];
@@ -289,6 +353,12 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
       // ---- adjacent-ring searches.  Seeds: the previous iteration's points if they still pass the ring filter, else
       // the best points of the +-2 bucket windows.
       Best bA{25.0f, INT_MAX, -1}, bB{25.0f, INT_MAX, -1};
+      float d2A = FLT_MAX, d2B = FLT_MAX;   // best distance among the OTHER eligible candidates of each search (guard radii)
+      auto upd = [&](Best& b, float& d2, const Best& c) {
+        if (c.j == b.j) return;   // the seed met again in its bucket
+        if (c.d < b.d || (c.d == b.d && c.pos < b.pos)) { if (b.j >= 0) d2 = fminf(d2, b.d); b = c; }
+        else d2 = fminf(d2, c.d);
+      };
       auto seed = [&](int pidx, bool same_ring, Best& best) {
         if (pidx < 0 || pidx == closest) return;
         const float4 p = C[pidx];
@@ -311,7 +381,7 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
         const float dd = (p.x - sel.x) * (p.x - sel.x) + (p.y - sel.y) * (p.y - sel.y) + (p.z - sel.z) * (p.z - sel.z);
         if (!(dd < 25.0f)) return;
         const Best c{dd, idx > closest ? (idx - closest) : ((closest - idx) + (1 << 30)), idx};
-        if (dr_cur == 0) bA = best_min(bA, c); else bB = best_min(bB, c);
+        if (dr_cur == 0) upd(bA, d2A, c); else upd(bB, d2B, c);
       };
       // window k = (ring slot r = k >> 1 <-> ring cid - 2 + r, side = k & 1); buckets with |offset| <= skip were scanned before
       auto window = [&](int k, int hA, int hB, int skipA, int skipB, int& lo, int& hi) -> bool {
@@ -335,12 +405,14 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
           if (wA >= 0) sA = wA;
           if (wB >= 0) sB = wB;
         } else {
-          hA = corner ? 0 : (bA.j >= 0 ? az_halfwidth(bA.d, rho) : LVO_AZ_BUCKETS);
-          hB = bB.j >= 0 ? az_halfwidth(bB.d, rho) : LVO_AZ_BUCKETS;
+          // with LVO_OPT_ODO_REUSE the windows reach LVO_ODO_SLACK beyond the best distances: room for the next iterations' certificates
+          hA = corner ? 0 : (bA.j >= 0 ? (a.reuse ? az_halfwidth_slack(bA.d, rho) : az_halfwidth(bA.d, rho)) : LVO_AZ_BUCKETS);
+          hB = bB.j >= 0 ? (a.reuse ? az_halfwidth_slack(bB.d, rho) : az_halfwidth(bB.d, rho)) : LVO_AZ_BUCKETS;
           if (hA > a.fast_h || hB > a.fast_h) {   // a target has no candidate nearby or its window is wide: leave it to the cooperative kernel
             fast = false; why = ((!corner && bA.j < 0) || bB.j < 0) ? 4 : 3; break;
           }
           skipA = corner ? hA : sA; skipB = sB;
+          sA = max(sA, hA); sB = max(sB, hB);   // half-widths scanned completely once this pass is through
         }
         unsigned wb[10], we[10];   // part 0 of every bucket range; fetched together before any candidate
 #pragma unroll
@@ -365,21 +437,48 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
           }
         }
       }
-      if (fast) { same = bA.j; other = bB.j; }
+      if (fast) {
+        same = bA.j; other = bB.j;
+        guard = make_float4(odo_guard_of(d2c, rad), corner ? 0.f : odo_guard_of(d2A, az_region(sA, rho)), odo_guard_of(d2B, az_region(sB, rho)), 0.f);
+      }
     }
     if (fast) {
-      const int type = odo_emit(a, lane, f, ns, corner, true, pt, C, closest, pj, same, other);
+      const int type = odo_emit(a, lane, f, ns, corner, true, pt, C, closest, pj, same, other, sel, guard);
       made_c = corner && type >= 0; made_p = !corner && type >= 0;
     } else {
       a.slow_list[(size_t)lane * (a.cap_sharp + a.cap_flat) + atomicAdd(&a.slow_cnt[lane], 1)] = f;
       atomicAdd(&s.stats.odo_slow[a.outer], 1); atomicAdd(&s.stats.odo_slow_why[why], 1);
     }
+    }   // not certified
   }
   const int nc = __popc(__ballot_sync(0xffffffffu, made_c)), np = __popc(__ballot_sync(0xffffffffu, made_p));
+  const int ncert = __popc(__ballot_sync(0xffffffffu, certified));
   if ((threadIdx.x & 31) == 0) {
     if (nc) atomicAdd(&s.stats.odo_corner_corr[a.outer], nc);
     if (np) atomicAdd(&s.stats.odo_plane_corr[a.outer], np);
+    if (ncert) atomicAdd(&s.stats.odo_certified[a.outer], ncert);
   }
+}
+
+// tile-wide best (d, id) in every lane; a lane whose own best lost folds it into its second-best distance first
+template <int TW>
+__device__ __forceinline__ void tile_best_merge(float& d, int& id, float& d2) {
+  const float dl = d; const int il = id;
+  int key = id;
+  tile_min3<TW>(d, key, id);
+  if (il != id && il != INT_MAX) d2 = fminf(d2, dl);
+}
+template <int TW>
+__device__ __forceinline__ void tile_best_merge(Best& b, float& d2) {
+  const float dl = b.d; const int jl = b.j;
+  tile_min3<TW>(b.d, b.pos, b.j);
+  if (jl != b.j && jl >= 0) d2 = fminf(d2, dl);
+}
+template <int TW>
+__device__ __forceinline__ float tile_min_f(float v) {
+#pragma unroll
+  for (int o = TW / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o, TW));
+  return v;
 }
 
 template <int TW>
@@ -413,7 +512,7 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
   // ---- closest point (laserOdometry.cpp:386 / :470, gate :389 / :473): the 27 cells around the query on the fine grid
   // (0.5 m) settle it when the best squared distance is below cell^2; otherwise the middle grid (2 m), then the coarse
   // grid (8 m, whose 27 cells cover the whole 5 m gate), then coarse shells if the cells had to be enlarged.
-  float d = FLT_MAX; int id = INT_MAX, key;
+  float d = FLT_MAX, d2c = FLT_MAX, region_c = 0.f; int id = INT_MAX;
   // Upper bounds from the previous outer iteration of this frame (same clouds, slightly different pose): the points found
   // then still exist, so their distances to the new query bound the new minima and the searches shrink to a small box /
   // azimuth window.  Results are identical to the unbounded search.
@@ -423,41 +522,51 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
     else { const int* c = a.plane_corr + (((size_t)lane * a.slots + (a.outer - 1) % a.slots) * a.cap_flat + (f - ns)) * 3; pc = c[0]; pA = c[1]; pB = c[2]; }
   }
   bool boxed = false, boxed_mid = false;
+  float rad = 0.f;
   if (pc >= 0) {
     const float dp = sqdist3(C[pc], sel.x, sel.y, sel.z);
-    const float rad = sqrtf(dp) * 1.0001f + 1e-5f;
-    if (rad < gfine.cell) { boxed = true; d = dp; id = pc; }
-    else if (rad < gmid.cell && gmid.dim[0] > 0) { boxed_mid = true; d = dp; id = pc; }   // bound between a fine and a middle cell: box on the 2 m grid
+    rad = sqrtf(dp) * 1.0001f + 1e-5f;
+    if (rad < gfine.cell) { boxed = true; d = dp; id = pc; if (a.reuse && rad + LVO_ODO_SLACK < gfine.cell) rad += LVO_ODO_SLACK; }
+    else if (rad < gmid.cell && gmid.dim[0] > 0) {   // bound between a fine and a middle cell: box on the 2 m grid
+      boxed_mid = true; d = dp; id = pc;
+      if (a.reuse && rad + LVO_ODO_SLACK < gmid.cell) rad += LVO_ODO_SLACK;
+    }
   }
+  // region_c: radius around the query inside which EVERY point of the cloud has been looked at (guard radius of LVO_OPT_ODO_REUSE)
   if (__any_sync(0xffffffffu, boxed)) {
-    tile_box_nn1<TW>(gfine, boxed, sel, sqrtf(d) * 1.0001f + 1e-5f, d, id);
-    key = id; tile_min3<TW>(d, key, id);
+    tile_box_nn1<TW>(gfine, boxed, sel, rad, d, id, d2c);
+    tile_best_merge<TW>(d, id, d2c);
   }
   if (__any_sync(0xffffffffu, boxed_mid)) {
-    tile_box_nn1<TW>(gmid, boxed_mid, sel, sqrtf(d) * 1.0001f + 1e-5f, d, id);
-    key = id; tile_min3<TW>(d, key, id);
+    tile_box_nn1<TW>(gmid, boxed_mid, sel, rad, d, id, d2c);
+    tile_best_merge<TW>(d, id, d2c);
   }
+  if (boxed || boxed_mid) region_c = rad;
   const bool unboxed = have && !boxed && !boxed_mid;
   if (__any_sync(0xffffffffu, unboxed)) {
-    tile_block_nn1<TW>(gfine, unboxed, sel, d, id);
-    key = id; tile_min3<TW>(d, key, id);
+    tile_block_nn1<TW>(gfine, unboxed, sel, d, id, d2c);
+    tile_best_merge<TW>(d, id, d2c);
   }
   bool more = unboxed && !(d < gfine.cell * gfine.cell);
+  if (unboxed && !more) region_c = gfine.cell;   // the 27 fine cells hold every point within one cell edge of the query
   if (__any_sync(0xffffffffu, more)) {
-    tile_block_nn1<TW>(gmid, more, sel, d, id);
-    key = id; tile_min3<TW>(d, key, id);
-    more = more && !(d < gmid.cell * gmid.cell);
-    // beyond the 27 middle cells: shells of the middle grid, pruned by min(best, gate) (the coarse grid is kept only as the
-    // fallback for clouds whose bounding box forced larger middle cells)
+    tile_block_nn1<TW>(gmid, more, sel, d, id, d2c);
+    tile_best_merge<TW>(d, id, d2c);
+    const bool settled = more && d < gmid.cell * gmid.cell;
+    more = more && !settled;
+    if (settled) region_c = gmid.cell;
+    // beyond the 27 middle cells: shells of the middle grid, pruned by min(best, gate)
     const int R = (int)ceilf(5.0f * gmid.inv_cell);
     for (int r = 2; r <= R; ++r) {
       const float bound = (float)(r - 1) * gmid.cell;
       more = more && !(d < bound * bound);
       if (!__any_sync(0xffffffffu, more)) break;
-      tile_shell_nn1<TW>(gmid, more, sel, r, 25.0f, d, id);
-      key = id; tile_min3<TW>(d, key, id);
+      tile_shell_nn1<TW>(gmid, more, sel, r, 25.0f, d, id, d2c);
+      tile_best_merge<TW>(d, id, d2c);
     }
+    if (unboxed && !settled && region_c == 0.f) region_c = sqrtf(d) * 0.999f;   // pruned shells: only the ball of the best distance is certain
   }
+  d2c = tile_min_f<TW>(d2c);
   const bool ok = have && id != INT_MAX && (double)d < 25.0;
   const int closest = ok ? id : 0;
   float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -466,6 +575,12 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
   // ---- adjacent-ring searches on the (ring, azimuth) grid
   const bool needA = !corner;
   Best bA{25.0f, INT_MAX, -1}, bB{25.0f, INT_MAX, -1};
+  float d2A = FLT_MAX, d2B = FLT_MAX;   // per lane: best distance among the other eligible candidates it saw (guard radii)
+  auto upd = [&](Best& b, float& d2, const Best& c) {
+    if (c.j == b.j) return;   // the seed (or the best so far) met again
+    if (c.d < b.d || (c.d == b.d && c.pos < b.pos)) { if (b.j >= 0) d2 = fminf(d2, b.d); b = c; }
+    else d2 = fminf(d2, c.d);
+  };
   const int bq = az_bucket(sel.x, sel.y);
   const float rho = sqrtf(sel.x * sel.x + sel.y * sel.y);
   auto consider = [&](float4 p, int r) {   // range r <-> ring cid - 2 + r
@@ -478,7 +593,7 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
     if (!(dd < 25.0f)) return;
     const int k2 = idx > closest ? (idx - closest) : ((closest - idx) + (1 << 30));
     const Best c{dd, k2, idx};
-    if (dr == 0) bA = best_min(bA, c); else bB = best_min(bB, c);
+    if (dr == 0) upd(bA, d2A, c); else upd(bB, d2B, c);
   };
   const int ring = cid - 2 + tl;   // lanes 0..4 of the tile own rings cid-2 .. cid+2
   const bool ring_ok = ok && tl < 5 && ring >= 0 && ring < LVO_AZ_RINGS && (ring != cid || needA);
@@ -496,15 +611,22 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
   if (needA) seed(pA, true, bA);
   seed(pB, false, bB);
   // phase 1: +-2 buckets, or the window implied by the seed (part 1 only exists when the window wraps)
-  const int h1 = ring == cid ? (bA.j >= 0 ? az_halfwidth(bA.d, rho) : 2) : (bB.j >= 0 ? az_halfwidth(bB.d, rho) : 2);
+  // (bA, bB are the same in every lane of the tile here and after each merge, so every lane can evaluate both searches' windows;
+  // with LVO_OPT_ODO_REUSE they reach LVO_ODO_SLACK beyond the best distances: room for the next iterations' certificates)
+  auto halfw = [&](const Best& b) { return a.reuse ? az_halfwidth_slack(b.d, rho) : az_halfwidth(b.d, rho); };
+  const int h1A = bA.j >= 0 ? halfw(bA) : 2, h1B = bB.j >= 0 ? halfw(bB) : 2;
+  const int h1 = ring == cid ? h1A : h1B;
   for (int part = 0; part < 2; ++part) {
     unsigned b = 0, e = 0;
     if (ring_ok) az_bounds(gaz, ring, bq - h1, bq + h1, part, b, e);
     tile_scan_ranges<TW, 5>(gaz.pts, b, e, consider);
   }
-  tile_min3<TW>(bA.d, bA.pos, bA.j); tile_min3<TW>(bB.d, bB.pos, bB.j);
+  tile_best_merge<TW>(bA, d2A); tile_best_merge<TW>(bB, d2B);
+  int hsA = h1A, hsB = h1B;   // half-widths scanned completely
   {  // phase 2: the rest of the window implied by the best distances so far (or by the 5 m gate)
-    const int h = ring == cid ? (needA ? az_halfwidth(bA.d, rho) : 0) : az_halfwidth(bB.d, rho);
+    const int h2A = needA ? halfw(bA) : 0, h2B = halfw(bB);
+    hsA = max(hsA, h2A); hsB = max(hsB, h2B);
+    const int h = ring == cid ? h2A : h2B;
     const bool whole = 2 * h + 1 >= LVO_AZ_BUCKETS;
     const bool need2 = ring_ok && h > h1 && 2 * h1 + 1 < LVO_AZ_BUCKETS;
     if (__any_sync(0xffffffffu, need2)) {
@@ -517,14 +639,17 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
         }
         tile_scan_ranges<TW, 5>(gaz.pts, b, e, consider);
       }
-      tile_min3<TW>(bA.d, bA.pos, bA.j); tile_min3<TW>(bB.d, bB.pos, bB.j);
+      tile_best_merge<TW>(bA, d2A); tile_best_merge<TW>(bB, d2B);
     }
   }
   const int same = bA.j, other = bB.j;
+  d2A = tile_min_f<TW>(d2A); d2B = tile_min_f<TW>(d2B);
   // ---- factor record (tile leader)
   bool made_c = false, made_p = false;
   if (have && tl == 0) {
-    const int type = odo_emit(a, lane, f, ns, corner, ok, pt, C, closest, pj, same, other);
+    float4 guard = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.reuse && ok) guard = make_float4(odo_guard_of(d2c, region_c), needA ? odo_guard_of(d2A, az_region(hsA, rho)) : 0.f, odo_guard_of(d2B, az_region(hsB, rho)), 0.f);
+    const int type = odo_emit(a, lane, f, ns, corner, ok, pt, C, closest, pj, same, other, sel, guard);
     made_c = corner && type >= 0; made_p = !corner && type >= 0;
   }
   const int nc = __popc(__ballot_sync(0xffffffffu, made_c)), np = __popc(__ballot_sync(0xffffffffu, made_p));

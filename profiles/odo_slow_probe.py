@@ -17,5 +17,5 @@ for k in range(n):
         for lane in range(2):
             s = c.stats(lane)
             print(f"frame {k} lane {lane}: sharp {s.n_sharp} flat {s.n_flat} | slow per outer {list(s.odo_slow)[:10]} | why {list(s.odo_slow_why)} | "
-                  f"corner corr {list(s.odo_corner_corr)[:3]} plane corr {list(s.odo_plane_corr)[:3]} | map knn full {list(s.map_knn_full)[:10]}")
+                  f"corner corr {list(s.odo_corner_corr)[:3]} plane corr {list(s.odo_plane_corr)[:3]} | map knn full {list(s.map_knn_full)[:10]} | odo certified {list(s.odo_certified)[:10]}")
 c.close()

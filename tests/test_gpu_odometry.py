@@ -86,3 +86,41 @@ def test_few_correspondences_warning(lvo_mod, synth):
     assert st_o == 2 and st_g == L.LVO_W_FEW_CORR
     assert np.array_equal(rel_g, rel_o)
     lvo.close()
+
+
+def test_odo_reuse_is_bitwise_identical(lvo_mod, synth):
+    """LVO_OPT_ODO_REUSE (default on): a scan-to-scan feature whose closest / same-ring / adjacent-ring points (laserOdometry.cpp:386-440,
+    :470-532) are certified unchanged by the guard radii of its last full association keeps its factor record in the following outer
+    iterations (:364).  Correspondence rows of ALL ten iterations, counters, LM traces, poses and the maps built from them must equal
+    those of associating every feature every time."""
+    L = lvo_mod
+    mk = dict(lanes=2, max_map_corner=1 << 18, max_map_surf=1 << 19)
+    a, b = L.Lvo(**mk), L.Lvo(**mk)
+    for c, v in ((a, 1), (b, 0)):
+        c.set_option(L.LVO_OPT_GRAPHS, 0)
+        c.set_option(L.LVO_OPT_ODO_REUSE, v)
+        c.set_option(L.LVO_OPT_FIXPOINT_SKIP, 0)   # all ten iterations run: the certificate is exercised nine times per frame
+    arrays = ("odo_corner_corr", "odo_plane_corr", "odo_lm_iters", "odo_final_cost", "map_corner_corr", "map_surf_corr", "map_lm_iters", "map_final_cost")
+    probes = (L.P_ODO_CORNER_CORR, L.P_ODO_PLANE_CORR, L.P_ODO_LM_TRACE, L.P_MAP_CORNER_KNN, L.P_MAP_SURF_KNN)
+    cert = feats = 0
+    for k in range(12):
+        sws = [synth.sweep(64, 0, k)[0], synth.sweep(64, 6, k)[0]]
+        sa, oa, ma = a.step_batch(sws)
+        sb, ob, mb = b.step_batch(sws)
+        assert sa == sb and np.array_equal(oa, ob) and np.array_equal(ma, mb), k
+        for lane in range(2):
+            x, y = a.stats(lane), b.stats(lane)
+            for name in arrays:
+                assert list(getattr(x, name)) == list(getattr(y, name)), (k, lane, name)
+            for what in probes:
+                assert np.array_equal(a.probe(what, lane), b.probe(what, lane)), (k, lane, what)
+            assert list(y.odo_certified) == [0] * 16 and x.odo_certified[0] == 0
+            if k > 0:
+                cert += sum(x.odo_certified[1:10]); feats += 9 * (x.n_sharp + x.n_flat)
+    assert cert > 0.5 * feats, (cert, feats)   # most features are carried over from the second or third iteration on
+    for lane in range(2):
+        for which in (0, 1):
+            pa, ca = a.map_export(lane, which)
+            pb, cb = b.map_export(lane, which)
+            assert np.array_equal(ca, cb) and np.array_equal(pa.view(np.uint32), pb.view(np.uint32))
+    a.close(); b.close()
