@@ -442,6 +442,7 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
   LVO_TRY(dalloc(c, &od.slow_list, (size_t)L * (c->cap_sharp + c->cap_flat))); LVO_TRY(dalloc(c, &od.slow_cnt, (size_t)L));
   { const char* e = getenv("LVO_ODO_REUSE"); od.reuse = e ? atoi(e) : 1; }   // default: correspondences carried across the outer iterations with a certificate
   LVO_TRY(dalloc(c, &od.ref, (size_t)L * (c->cap_sharp + c->cap_flat))); LVO_TRY(dalloc(c, &od.guard, (size_t)L * (c->cap_sharp + c->cap_flat)));
+  LVO_TRY(dalloc(c, &od.sel, (size_t)L * (c->cap_sharp + c->cap_flat)));
   LVO_TRY(dalloc(c, &od.corner_corr, (size_t)L * slots * c->cap_sharp * 2));
   LVO_TRY(dalloc(c, &od.plane_corr, (size_t)L * slots * c->cap_flat * 3));
   const size_t odo_cells = 2 * ((size_t)(1 << 22) + (size_t)LVO_AZ_BUCKETS * LVO_AZ_RINGS + (1 << 19));   // per lane, see k_setup_grid_problems

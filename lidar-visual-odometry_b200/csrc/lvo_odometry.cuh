@@ -42,7 +42,8 @@ struct OdoArgs {
   // LVO_OPT_ODO_REUSE: certified reuse of a feature's correspondence across the outer iterations of a frame (see odo_certified)
   int reuse;
   float4* ref;       // [lanes][cap_sharp + cap_flat] feature position (TransformToStart) at its last full association
-  float4* guard;     // [lanes][cap_sharp + cap_flat] guard radii of that association: x closest point, y same-ring point, z adjacent-ring point
+  float4* guard;     // [lanes][cap_sharp + cap_flat] guard radii of that association: x closest point, y same-ring point, z adjacent-ring point; w != 0: record valid
+  int4* sel;         // [lanes][cap_sharp + cap_flat] what that association chose: x closest, y same-ring, z adjacent-ring point (-1: none inside the 5 m gate)
 };
 
 // ---- certified reuse of a correspondence across outer iterations (LVO_OPT_ODO_REUSE) ---------------------------------------------
@@ -56,8 +57,8 @@ struct OdoArgs {
 // with j unchanged the filters are unchanged.  All three certified: the factor record stands and the feature is skipped.  Margins of
 // 1e-4 relative + 1e-5 m dwarf float rounding and only decide WHETHER the shortcut is taken.
 #define LVO_ODO_SLACK 0.05f   // extra radius (m) scanned around a full association so that the next iterations can be certified
-__device__ __forceinline__ float odo_guard_of(float d2_second, float region) {
-  const float g = fminf(fminf(sqrtf(d2_second), region), 5.0f);   // candidates at or beyond the gate are never ranked: they are >= 5 m away
+__device__ __forceinline__ float odo_guard_of(float d2_other, float region) {
+  const float g = fminf(sqrtf(d2_other), region);
   return fmaxf(g * 0.9999f - 1e-5f, 0.f);
 }
 // radius around the query (horizontal range rho) inside which every point lies in the azimuth window of half-width h buckets
@@ -74,17 +75,23 @@ __device__ __forceinline__ int az_halfwidth_slack(float d2, float rho) {
   const float d = sqrtf(d2) + LVO_ODO_SLACK;
   return az_halfwidth(d * d, rho);
 }
-// true iff the previous iteration's correspondence (pc, pA, pB) of this feature is certified at `sel`
-__device__ __forceinline__ bool odo_certified(const OdoArgs& a, size_t fi, bool corner, float4 sel, const float4* C, int pc, int pA, int pB) {
-  if (pc < 0 || pB < 0 || (!corner && pA < 0)) return false;
-  const float4 g = a.guard[fi], r = a.ref[fi];
+// true iff the choices of this feature's last full association (a.sel) are certified at `sel`: a chosen point is still the strict
+// minimum of its search and inside the gate; a search that found nothing inside the gate still finds nothing.  p receives the choices.
+__device__ __forceinline__ bool odo_certified(const OdoArgs& a, size_t fi, bool corner, float4 sel, const float4* C, int4& p) {
+  const float4 g = a.guard[fi];
+  if (g.w == 0.f) return false;
+  p = a.sel[fi];
+  const float4 r = a.ref[fi];
   const float dx = sel.x - r.x, dy = sel.y - r.y, dz = sel.z - r.z;
   const float delta = sqrtf(dx * dx + dy * dy + dz * dz) * 1.0001f + 1e-5f;
   auto still = [&](int idx, float guard) {
+    if (idx < 0) return guard - delta > 5.001f;   // every eligible point stays outside the gate
     const float dd = sqdist3(C[idx], sel.x, sel.y, sel.z);
     return dd < 25.0f && sqrtf(dd) * 1.0001f + 1e-5f + delta < guard;
   };
-  return still(pc, g.x) && still(pB, g.z) && (corner || still(pA, g.y));
+  if (!still(p.x, g.x)) return false;
+  if (p.x < 0) return true;   // no closest point inside the gate: no factor, as before
+  return still(p.z, g.z) && (corner || still(p.y, g.y));
 }
 
 __global__ void k_odo_begin(OdoArgs a) {
@@ -223,6 +230,7 @@ __device__ __forceinline__ int odo_emit(const OdoArgs& a, int lane, int f, int n
   if (a.reuse) {
     const size_t fi = (size_t)lane * (a.cap_sharp + a.cap_flat) + f;
     a.ref[fi] = sel; a.guard[fi] = guard;
+    a.sel[fi] = make_int4(ok ? closest : -1, ok ? same : -1, ok ? other : -1, 0);
   }
   LvoFactor fac;
   fac.type = -1; fac.pad = 0;
@@ -290,8 +298,41 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
   if (threadIdx.x < 4) gv[threadIdx.x] = grid_view(a.grid, LVO_ODO_GRIDS * lane + threadIdx.x);
   __syncthreads();
   const int ns = s.n_sharp, nf = s.n_flat;
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  bool made_c = false, made_p = false, certified = false;
+  const int f0 = blockIdx.x * blockDim.x + threadIdx.x;
+  int made_c = 0, made_p = 0;
+  bool certified = false;
+  int f = f0;
+  if (a.reuse && a.outer > 0) {
+    // ---- phase A (LVO_OPT_ODO_REUSE), one thread per feature: certificate of the previous iteration's correspondence.  The features
+    // that fail are compacted, so that the searches below run in full warps instead of one lane per warp.
+    __shared__ int s_list[128];
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    bool need = false;
+    if (f0 < ns + nf) {
+      const bool corner = f0 < ns;
+      const float4* C = corner ? a.corner_last + (size_t)lane * a.cap_lsharp : a.surf_last + (size_t)lane * a.P;
+      const float4 pt = corner ? a.sharp[(size_t)lane * a.cap_sharp + f0] : a.flat[(size_t)lane * a.cap_flat + (f0 - ns)];
+      const float4 sel = transform_to_start(s.para_q, s.para_t, pt, a.distortion);
+      int4 p;
+      certified = odo_certified(a, (size_t)lane * (a.cap_sharp + a.cap_flat) + f0, corner, sel, C, p);
+      if (certified) {
+        // same choices as in the last full association: the factor record (or its absence) stands; this iteration's row repeats it
+        const bool valid = p.x >= 0 && p.z >= 0 && (corner || p.y >= 0);
+        if (corner) { int* c = a.corner_corr + (((size_t)lane * a.slots + a.outer % a.slots) * a.cap_sharp + f0) * 2; c[0] = valid ? p.x : -1; c[1] = valid ? p.z : -1; }
+        else { int* c = a.plane_corr + (((size_t)lane * a.slots + a.outer % a.slots) * a.cap_flat + (f0 - ns)) * 3; c[0] = valid ? p.x : -1; c[1] = valid ? p.y : -1; c[2] = valid ? p.z : -1; }
+        if (valid) { if (corner) made_c++; else made_p++; }
+      } else need = true;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    int off = 0;
+    if ((threadIdx.x & 31) == 0 && m) off = atomicAdd(&s_n, __popc(m));
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (need) s_list[off + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = f0;
+    __syncthreads();
+    f = (int)threadIdx.x < s_n ? s_list[threadIdx.x] : ns + nf;
+  }
   if (f < ns + nf) {
     const bool corner = f < ns;
     const float4* C = corner ? a.corner_last + (size_t)lane * a.cap_lsharp : a.surf_last + (size_t)lane * a.P;
@@ -304,14 +345,7 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
       if (corner) { const int* c = a.corner_corr + (((size_t)lane * a.slots + (a.outer - 1) % a.slots) * a.cap_sharp + f) * 2; pc = c[0]; pB = c[1]; }
       else { const int* c = a.plane_corr + (((size_t)lane * a.slots + (a.outer - 1) % a.slots) * a.cap_flat + (f - ns)) * 3; pc = c[0]; pA = c[1]; pB = c[2]; }
     }
-    const size_t fi = (size_t)lane * (a.cap_sharp + a.cap_flat) + f;
-    certified = a.reuse && a.outer > 0 && odo_certified(a, fi, corner, sel, C, pc, pA, pB);
-    if (certified) {
-      // same three points as in the previous iteration: the factor record stands; carry the row into this iteration's slot
-      if (corner) { int* c = a.corner_corr + (((size_t)lane * a.slots + a.outer % a.slots) * a.cap_sharp + f) * 2; c[0] = pc; c[1] = pB; }
-      else { int* c = a.plane_corr + (((size_t)lane * a.slots + a.outer % a.slots) * a.cap_flat + (f - ns)) * 3; c[0] = pc; c[1] = pA; c[2] = pB; }
-      made_c = corner; made_p = !corner;
-    } else {
+    {
     float d = FLT_MAX, d2c = FLT_MAX; int id = INT_MAX;
     auto near = [&](float4 p) {
       const int i = __float_as_int(p.w);
@@ -379,7 +413,7 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
         if (idx == closest) return;
         if ((idx > closest && dr_cur < 0) || (idx < closest && dr_cur > 0)) return;
         const float dd = (p.x - sel.x) * (p.x - sel.x) + (p.y - sel.y) * (p.y - sel.y) + (p.z - sel.z) * (p.z - sel.z);
-        if (!(dd < 25.0f)) return;
+        if (!(dd < 25.0f)) { if (dr_cur == 0) d2A = fminf(d2A, dd); else d2B = fminf(d2B, dd); return; }   // eligible, beyond the gate: only bounds the guard
         const Best c{dd, idx > closest ? (idx - closest) : ((closest - idx) + (1 << 30)), idx};
         if (dr_cur == 0) upd(bA, d2A, c); else upd(bB, d2B, c);
       };
@@ -439,19 +473,19 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
       }
       if (fast) {
         same = bA.j; other = bB.j;
-        guard = make_float4(odo_guard_of(d2c, rad), corner ? 0.f : odo_guard_of(d2A, az_region(sA, rho)), odo_guard_of(d2B, az_region(sB, rho)), 0.f);
+        guard = make_float4(odo_guard_of(d2c, rad), corner ? 0.f : odo_guard_of(d2A, az_region(sA, rho)), odo_guard_of(d2B, az_region(sB, rho)), 1.f);
       }
     }
     if (fast) {
       const int type = odo_emit(a, lane, f, ns, corner, true, pt, C, closest, pj, same, other, sel, guard);
-      made_c = corner && type >= 0; made_p = !corner && type >= 0;
+      if (type >= 0) { if (corner) made_c++; else made_p++; }
     } else {
       a.slow_list[(size_t)lane * (a.cap_sharp + a.cap_flat) + atomicAdd(&a.slow_cnt[lane], 1)] = f;
       atomicAdd(&s.stats.odo_slow[a.outer], 1); atomicAdd(&s.stats.odo_slow_why[why], 1);
     }
-    }   // not certified
+    }
   }
-  const int nc = __popc(__ballot_sync(0xffffffffu, made_c)), np = __popc(__ballot_sync(0xffffffffu, made_p));
+  const int nc = __reduce_add_sync(0xffffffffu, made_c), np = __reduce_add_sync(0xffffffffu, made_p);
   const int ncert = __popc(__ballot_sync(0xffffffffu, certified));
   if ((threadIdx.x & 31) == 0) {
     if (nc) atomicAdd(&s.stats.odo_corner_corr[a.outer], nc);
@@ -556,15 +590,17 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
     more = more && !settled;
     if (settled) region_c = gmid.cell;
     // beyond the 27 middle cells: shells of the middle grid, pruned by min(best, gate)
-    const int R = (int)ceilf(5.0f * gmid.inv_cell);
+    const float gate_r = a.reuse ? 5.0f + LVO_ODO_SLACK : 5.0f;   // with LVO_OPT_ODO_REUSE a little beyond the gate, so that "nothing inside" can be certified later
+    const int R = (int)ceilf(gate_r * gmid.inv_cell);
     for (int r = 2; r <= R; ++r) {
       const float bound = (float)(r - 1) * gmid.cell;
       more = more && !(d < bound * bound);
       if (!__any_sync(0xffffffffu, more)) break;
-      tile_shell_nn1<TW>(gmid, more, sel, r, 25.0f, d, id, d2c);
+      tile_shell_nn1<TW>(gmid, more, sel, r, gate_r * gate_r, d, id, d2c);
       tile_best_merge<TW>(d, id, d2c);
     }
-    if (unboxed && !settled && region_c == 0.f) region_c = sqrtf(d) * 0.999f;   // pruned shells: only the ball of the best distance is certain
+    // pruned shells: only the ball of min(best distance, scanned gate) is certain
+    if (unboxed && !settled && region_c == 0.f) region_c = sqrtf(fminf(d, gate_r * gate_r)) * 0.999f;
   }
   d2c = tile_min_f<TW>(d2c);
   const bool ok = have && id != INT_MAX && (double)d < 25.0;
@@ -590,7 +626,7 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
     // the walk is monotone in the ring id: above `closest` it only meets rings >= cid, below it rings <= cid
     if ((idx > closest && dr < 0) || (idx < closest && dr > 0)) return;
     const float dd = (p.x - sel.x) * (p.x - sel.x) + (p.y - sel.y) * (p.y - sel.y) + (p.z - sel.z) * (p.z - sel.z);
-    if (!(dd < 25.0f)) return;
+    if (!(dd < 25.0f)) { if (dr == 0) d2A = fminf(d2A, dd); else d2B = fminf(d2B, dd); return; }   // eligible, beyond the gate: only bounds the guard
     const int k2 = idx > closest ? (idx - closest) : ((closest - idx) + (1 << 30));
     const Best c{dd, k2, idx};
     if (dr == 0) upd(bA, d2A, c); else upd(bB, d2B, c);
@@ -648,7 +684,11 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
   bool made_c = false, made_p = false;
   if (have && tl == 0) {
     float4 guard = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a.reuse && ok) guard = make_float4(odo_guard_of(d2c, region_c), needA ? odo_guard_of(d2A, az_region(hsA, rho)) : 0.f, odo_guard_of(d2B, az_region(hsB, rho)), 0.f);
+    if (a.reuse) {
+      // ok: the other points are at least min(second best, region) away.  Not ok: the nearest point itself lies beyond the gate (or there is none)
+      if (ok) guard = make_float4(odo_guard_of(d2c, region_c), needA ? odo_guard_of(d2A, az_region(hsA, rho)) : 0.f, odo_guard_of(d2B, az_region(hsB, rho)), 1.f);
+      else guard = make_float4(odo_guard_of(d, region_c), 0.f, 0.f, 1.f);
+    }
     const int type = odo_emit(a, lane, f, ns, corner, ok, pt, C, closest, pj, same, other, sel, guard);
     made_c = corner && type >= 0; made_p = !corner && type >= 0;
   }
