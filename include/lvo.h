@@ -109,8 +109,8 @@ typedef struct lvo_stats {
   /* scan-to-scan features per outer iteration that the thread-per-feature association handed to the warp-per-feature kernel, and why
    * (summed over the iterations of the frame): 0 no bound on the closest point, 1 bound wider than a fine cell, 2 closest point beyond the
    * 5 m gate, 3 an adjacent-ring target exists but its azimuth window is wider than the fast limit, 4 an adjacent-ring target has no
-   * candidate nearby.  Diagnostic only. */
-  int odo_slow[16], odo_slow_why[5];
+   * candidate nearby, 5 too few uncertified features left in a block to keep one thread busy each.  Diagnostic only. */
+  int odo_slow[16], odo_slow_why[6];
   /* LVO_OPT_ODO_REUSE: scan-to-scan features per outer iteration whose correspondence was carried over under the certificate */
   int odo_certified[16];
 } lvo_stats;

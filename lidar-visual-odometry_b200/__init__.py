@@ -53,7 +53,7 @@ class Stats(C.Structure):
                 ("map_corner_from_map", C.c_int), ("map_surf_from_map", C.c_int), ("map_corner_stack", C.c_int), ("map_surf_stack", C.c_int),
                 ("map_corner_corr", C.c_int * 16), ("map_surf_corr", C.c_int * 16), ("map_lm_iters", C.c_int * 16), ("map_final_cost", C.c_double * 16),
                 ("map_corner_total", C.c_int), ("map_surf_total", C.c_int), ("center_cube", C.c_int * 3), ("cen", C.c_int * 3),
-                ("odo_outer_executed", C.c_int), ("map_outer_executed", C.c_int), ("map_knn_full", C.c_int * 16), ("odo_slow", C.c_int * 16), ("odo_slow_why", C.c_int * 5), ("odo_certified", C.c_int * 16)]
+                ("odo_outer_executed", C.c_int), ("map_outer_executed", C.c_int), ("map_knn_full", C.c_int * 16), ("odo_slow", C.c_int * 16), ("odo_slow_why", C.c_int * 6), ("odo_certified", C.c_int * 16)]
 
 
 class Camera(C.Structure):

@@ -56,6 +56,7 @@ struct OdoArgs {
 // (:389 / :473), it is still the strict minimum.  The eligibility of l / m depends only on j and on fixed ring ids and indices, so
 // with j unchanged the filters are unchanged.  All three certified: the factor record stands and the feature is skipped.  Margins of
 // 1e-4 relative + 1e-5 m dwarf float rounding and only decide WHETHER the shortcut is taken.
+#define LVO_ODO_FEW 24       // uncertified features per block of 128 below which they are handed to the warp-per-feature kernel
 #define LVO_ODO_SLACK 0.05f   // extra radius (m) scanned around a full association so that the next iterations can be certified
 __device__ __forceinline__ float odo_guard_of(float d2_other, float region) {
   const float g = fminf(sqrtf(d2_other), region);
@@ -101,7 +102,7 @@ __global__ void k_odo_begin(OdoArgs a) {
   s.odo_status = s.odo_inited ? LVO_OK : LVO_W_FIRST_FRAME;
   s.odo_done = 0; s.stats.odo_outer_executed = 0;
   for (int o = 0; o < LVO_MAX_OUTER; ++o) { s.stats.odo_corner_corr[o] = 0; s.stats.odo_plane_corr[o] = 0; s.stats.odo_lm_iters[o] = 0; s.stats.odo_final_cost[o] = 0; s.stats.odo_slow[o] = 0; s.stats.odo_certified[o] = 0; }
-  for (int k = 0; k < 5; ++k) s.stats.odo_slow_why[k] = 0;
+  for (int k = 0; k < 6; ++k) s.stats.odo_slow_why[k] = 0;
 }
 
 struct Best { float d; int pos; int j; };
@@ -332,6 +333,16 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
     if (need) s_list[off + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = f0;
     __syncthreads();
     f = (int)threadIdx.x < s_n ? s_list[threadIdx.x] : ns + nf;
+    // A handful of features left in this block (typical from the third iteration on): one thread each would walk its searches as a
+    // chain of ~100 dependent loads with nothing else in flight — ~130 us of pure latency per launch.  They go to the warp-per-feature
+    // kernel, which is launched anyway.
+    if (s_n <= LVO_ODO_FEW) {
+      if (f < ns + nf) {
+        a.slow_list[(size_t)lane * (a.cap_sharp + a.cap_flat) + atomicAdd(&a.slow_cnt[lane], 1)] = f;
+        atomicAdd(&s.stats.odo_slow[a.outer], 1); atomicAdd(&s.stats.odo_slow_why[5], 1);
+      }
+      f = ns + nf;
+    }
   }
   if (f < ns + nf) {
     const bool corner = f < ns;
@@ -342,7 +353,10 @@ __global__ void __launch_bounds__(128) k_odo_assoc_fast(OdoArgs a) {
     const float4 sel = transform_to_start(s.para_q, s.para_t, pt, a.distortion);
     int pc = -1, pA = -1, pB = -1;
     if (a.outer > 0) {
-      if (corner) { const int* c = a.corner_corr + (((size_t)lane * a.slots + (a.outer - 1) % a.slots) * a.cap_sharp + f) * 2; pc = c[0]; pB = c[1]; }
+      if (a.reuse) {   // what the last full association chose, also when it produced no factor (any of them is a valid bound)
+        const int4 p = a.sel[(size_t)lane * (a.cap_sharp + a.cap_flat) + f];
+        pc = p.x; pA = p.y; pB = p.z;
+      } else if (corner) { const int* c = a.corner_corr + (((size_t)lane * a.slots + (a.outer - 1) % a.slots) * a.cap_sharp + f) * 2; pc = c[0]; pB = c[1]; }
       else { const int* c = a.plane_corr + (((size_t)lane * a.slots + (a.outer - 1) % a.slots) * a.cap_flat + (f - ns)) * 3; pc = c[0]; pA = c[1]; pB = c[2]; }
     }
     {
@@ -552,7 +566,10 @@ __global__ void __launch_bounds__(256, 4) k_odo_assoc(OdoArgs a) {
   // azimuth window.  Results are identical to the unbounded search.
   int pc = -1, pA = -1, pB = -1;
   if (have && a.outer > 0) {
-    if (corner) { const int* c = a.corner_corr + (((size_t)lane * a.slots + (a.outer - 1) % a.slots) * a.cap_sharp + f) * 2; pc = c[0]; pB = c[1]; }
+    if (a.reuse) {   // what the last full association chose, also when it produced no factor
+      const int4 p = a.sel[(size_t)lane * (a.cap_sharp + a.cap_flat) + f];
+      pc = p.x; pA = p.y; pB = p.z;
+    } else if (corner) { const int* c = a.corner_corr + (((size_t)lane * a.slots + (a.outer - 1) % a.slots) * a.cap_sharp + f) * 2; pc = c[0]; pB = c[1]; }
     else { const int* c = a.plane_corr + (((size_t)lane * a.slots + (a.outer - 1) % a.slots) * a.cap_flat + (f - ns)) * 3; pc = c[0]; pA = c[1]; pB = c[2]; }
   }
   bool boxed = false, boxed_mid = false;
