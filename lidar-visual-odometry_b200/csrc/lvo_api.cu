@@ -342,7 +342,21 @@ int stage_sweeps(lvo_ctx* c, const lvo_cloud_view* sweeps, unsigned char* buf, c
   return LVO_OK;
 }
 
+
+// Every entry point makes the context's device current for its duration (a process may hold contexts on several GPUs and call them
+// from any thread: kernels launched on a context's stream while another device is current fail with "invalid resource handle")
+// and restores the caller's device on return.
+struct LvoDeviceGuard {
+  int prev = -1; bool switched = false;
+  explicit LvoDeviceGuard(const lvo_ctx* c);
+  ~LvoDeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
 }  // namespace
+
+LvoDeviceGuard::LvoDeviceGuard(const lvo_ctx* c) {
+  if (!c) return;
+  if (cudaGetDevice(&prev) == cudaSuccess && prev != c->cfg.device) switched = cudaSetDevice(c->cfg.device) == cudaSuccess;
+}
 
 static void destroy_graphs(lvo_ctx* c) {
   for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) if (c->graph_exec[a][b]) { cudaGraphExecDestroy(c->graph_exec[a][b]); c->graph_exec[a][b] = nullptr; }
@@ -374,6 +388,8 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
   c->lanes = cfg->lanes;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { lvo_set_error(c, "no CUDA device: liblvo has no CPU fallback"); return LVO_E_CUDA; }
+  struct RestoreDevice { int prev = -1; ~RestoreDevice() { if (prev >= 0) cudaSetDevice(prev); } } restore;   // the caller's current device is left as it was
+  cudaGetDevice(&restore.prev);
   LVO_CUDA_OK(c, cudaSetDevice(cfg->device));
   cudaDeviceProp prop;
   LVO_CUDA_OK(c, cudaGetDeviceProperties(&prop, cfg->device));
@@ -514,6 +530,7 @@ int lvo_create(const lvo_config* cfg, lvo_ctx** out) {
 
 int lvo_destroy(lvo_ctx* c) {
   if (!c) return LVO_E_BADARG;
+  LvoDeviceGuard _dev(c);
   if (c->st) cudaStreamSynchronize(c->st);
   for (void* p : c->allocs) cudaFree(p);
   for (void* p : c->pinned) cudaFreeHost(p);
@@ -534,6 +551,7 @@ int lvo_get_stats(const lvo_ctx* c, int lane, lvo_stats* out, size_t bytes) {
 int lvo_lane_status(const lvo_ctx* c, int lane) { return (c && lane >= 0 && lane < c->lanes) ? c->lane_status[lane] : LVO_E_BADARG; }
 size_t lvo_state_bytes(void) { return sizeof(LaneState); }
 int lvo_set_option(lvo_ctx* c, int option, int value) {
+  LvoDeviceGuard _dev(c);
   if (!c) return LVO_E_BADARG;
   if (option == LVO_OPT_GRAPHS) { c->opt_graphs = value; return LVO_OK; }
   if (option == LVO_OPT_STAGE_TIMING) { c->opt_stage_timing = value ? 1 : 0; return LVO_OK; }
@@ -564,6 +582,7 @@ int lvo_set_option(lvo_ctx* c, int option, int value) {
   return LVO_E_BADARG;
 }
 int lvo_set_stream(lvo_ctx* c, void* cuda_stream) {
+  LvoDeviceGuard _dev(c);
   if (!c) return LVO_E_BADARG;
   cudaStreamSynchronize(c->st);
   destroy_graphs(c);
@@ -575,6 +594,7 @@ int lvo_get_timings(const lvo_ctx* c, lvo_timings* out) { if (!c || !out) return
 // ---------------------------------------------------------------------------------------------------------------
 int lvo_extract_features(lvo_ctx* c, lvo_cloud_view sweep, lvo_cloud_out* full, lvo_cloud_out* sharp, lvo_cloud_out* less_sharp, lvo_cloud_out* flat,
                          lvo_cloud_out* less_flat) {
+  LvoDeviceGuard _dev(c);
   if (!c) return LVO_E_BADARG;
   LVO_TRY(check_view(c, sweep, (size_t)c->P, true));
   if (c->pending) { lvo_set_error(c, "lvo_wait has not been called for the last *_async step"); return LVO_E_STATE; }
@@ -604,6 +624,7 @@ int lvo_extract_features(lvo_ctx* c, lvo_cloud_view sweep, lvo_cloud_out* full, 
 
 int lvo_scan_to_scan(lvo_ctx* c, lvo_cloud_view sharp, lvo_cloud_view less_sharp, lvo_cloud_view flat, lvo_cloud_view less_flat, lvo_pose* T_last_curr,
                      lvo_pose* T_w_curr) {
+  LvoDeviceGuard _dev(c);
   if (!c) return LVO_E_BADARG;
   if (c->pending) { lvo_set_error(c, "lvo_wait has not been called for the last *_async step"); return LVO_E_STATE; }
   LVO_TRY(check_view(c, sharp, (size_t)c->cap_sharp)); LVO_TRY(check_view(c, less_sharp, (size_t)c->cap_lsharp));
@@ -632,6 +653,7 @@ int lvo_scan_to_scan(lvo_ctx* c, lvo_cloud_view sharp, lvo_cloud_view less_sharp
 
 int lvo_scan_to_map(lvo_ctx* c, lvo_cloud_view corner_last, lvo_cloud_view surf_last, lvo_cloud_view full_or_null, const lvo_pose* T_wodom_curr,
                     lvo_pose* T_wmap_curr, lvo_cloud_out* registered_or_null) {
+  LvoDeviceGuard _dev(c);
   if (!c || !T_wodom_curr) return LVO_E_BADARG;
   if (c->pending) { lvo_set_error(c, "lvo_wait has not been called for the last *_async step"); return LVO_E_STATE; }
   LVO_TRY(check_view(c, corner_last, (size_t)c->cap_lsharp)); LVO_TRY(check_view(c, surf_last, (size_t)c->P));
@@ -803,6 +825,7 @@ static int check_sweeps(lvo_ctx* c, const lvo_cloud_view* sweeps, int* max_n) {
 }
 
 int lvo_step_batch_async(lvo_ctx* c, const lvo_cloud_view* sweeps) {
+  LvoDeviceGuard _dev(c);
   if (!c || !sweeps) return LVO_E_BADARG;
   if (c->pending) { lvo_set_error(c, "lvo_wait has not been called for the last *_async step"); return LVO_E_STATE; }
   int max_n = 0;
@@ -811,15 +834,18 @@ int lvo_step_batch_async(lvo_ctx* c, const lvo_cloud_view* sweeps) {
   return step_enqueue(c, (int)sweeps[0].stride, (int)sweeps[0].off_xyz, max_n);
 }
 int lvo_wait(lvo_ctx* c, lvo_pose* T_wodom, lvo_pose* T_wmap) {
+  LvoDeviceGuard _dev(c);
   if (!c) return LVO_E_BADARG;
   return step_finish(c, T_wodom, T_wmap);
 }
 int lvo_step_batch(lvo_ctx* c, const lvo_cloud_view* sweeps, lvo_pose* T_wodom, lvo_pose* T_wmap) {
+  LvoDeviceGuard _dev(c);
   LVO_TRY(lvo_step_batch_async(c, sweeps));
   return step_finish(c, T_wodom, T_wmap);
 }
 
 int lvo_step_batch_pipelined(lvo_ctx* c, const lvo_cloud_view* sweeps, const lvo_cloud_view* next, lvo_pose* T_wodom, lvo_pose* T_wmap) {
+  LvoDeviceGuard _dev(c);
   if (!c || !sweeps) return LVO_E_BADARG;
   if (c->pending) { lvo_set_error(c, "lvo_wait has not been called for the last *_async step"); return LVO_E_STATE; }
   if (!c->copy_st) {
@@ -850,6 +876,7 @@ int lvo_step_batch_pipelined(lvo_ctx* c, const lvo_cloud_view* sweeps, const lvo
 }
 
 int lvo_step_batch_dev_async(lvo_ctx* c, const lvo_point* const* d_sweeps, const size_t* n) {
+  LvoDeviceGuard _dev(c);
   if (!c || !d_sweeps || !n) return LVO_E_BADARG;
   if (c->pending) { lvo_set_error(c, "lvo_wait has not been called for the last *_async step"); return LVO_E_STATE; }
   int max_n = 0;
@@ -861,6 +888,7 @@ int lvo_step_batch_dev_async(lvo_ctx* c, const lvo_point* const* d_sweeps, const
   return step_enqueue(c, 16, 0, max_n);
 }
 int lvo_step_batch_dev(lvo_ctx* c, const lvo_point* const* d_sweeps, const size_t* n, lvo_pose* T_wodom, lvo_pose* T_wmap) {
+  LvoDeviceGuard _dev(c);
   LVO_TRY(lvo_step_batch_dev_async(c, d_sweeps, n));
   return step_finish(c, T_wodom, T_wmap);
 }
@@ -868,6 +896,7 @@ int lvo_step_batch_dev(lvo_ctx* c, const lvo_point* const* d_sweeps, const size_
 // ---------------------------------------------------------------------------------------------------------------
 int lvo_map_import(lvo_ctx* c, int lane, const lvo_point* corner, const int* corner_cube, size_t n_corner, const lvo_point* surf, const int* surf_cube,
                    size_t n_surf) {
+  LvoDeviceGuard _dev(c);
   if (!c || lane < 0 || lane >= c->lanes) return LVO_E_BADARG;
   const lvo_point* pts[2] = {corner, surf}; const int* cubes[2] = {corner_cube, surf_cube}; const size_t ns[2] = {n_corner, n_surf};
   LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
@@ -892,6 +921,7 @@ int lvo_map_import(lvo_ctx* c, int lane, const lvo_point* corner, const int* cor
 }
 
 int lvo_map_export(lvo_ctx* c, int lane, int which, lvo_cloud_out* pts, int* cube_out) {
+  LvoDeviceGuard _dev(c);
   if (!c || lane < 0 || lane >= c->lanes || which < 0 || which > 1 || !pts) return LVO_E_BADARG;
   LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
   std::vector<unsigned> start(LVO_NCUBES + 1);
@@ -909,6 +939,7 @@ int lvo_map_export(lvo_ctx* c, int lane, int which, lvo_cloud_out* pts, int* cub
 }
 
 int lvo_map_cloud(lvo_ctx* c, int lane, int which, lvo_cloud_out* pts) {
+  LvoDeviceGuard _dev(c);
   if (!c || lane < 0 || lane >= c->lanes || which < 0 || which > 1 || !pts) return LVO_E_BADARG;
   unsigned* off = c->map.new_cnt;              // [LVO_NCUBES + 1] scratch (rewritten by every mapping frame)
   float4* out = (float4*)c->d_upload;          // >= 4 * max(map_cap) points
@@ -924,6 +955,7 @@ int lvo_map_cloud(lvo_ctx* c, int lane, int which, lvo_cloud_out* pts) {
 }
 
 int lvo_transform_cloud(lvo_ctx* c, lvo_cloud_view in, const lvo_pose* T, int to_end, lvo_cloud_out* out) {
+  LvoDeviceGuard _dev(c);
   if (!c || !out) return LVO_E_BADARG;
   const size_t cap = (size_t)std::max(c->P, std::max(c->map.map_cap[0], c->map.map_cap[1]));
   LVO_TRY(check_view(c, in, cap));
@@ -954,14 +986,17 @@ static int set_pose(lvo_ctx* c, int lane, int what, const lvo_pose* p) {
   LVO_CUDA_OK(c, cudaStreamSynchronize(c->st));
   return LVO_OK;
 }
-int lvo_set_map_correction(lvo_ctx* c, int lane, const lvo_pose* T) { return set_pose(c, lane, 2, T); }
+int lvo_set_map_correction(lvo_ctx* c, int lane, const lvo_pose* T) {
+  LvoDeviceGuard _dev(c); return set_pose(c, lane, 2, T); }
 int lvo_get_map_correction(lvo_ctx* c, int lane, lvo_pose* T) {
+  LvoDeviceGuard _dev(c);
   if (!c || !T || lane < 0 || lane >= c->lanes) return LVO_E_BADARG;
   LVO_TRY(sync_state(c));
   pose_out(T, c->h_ls[lane].q_wmap_wodom, c->h_ls[lane].t_wmap_wodom);
   return LVO_OK;
 }
 int lvo_set_odometry_state(lvo_ctx* c, int lane, const lvo_pose* T_last_curr, const lvo_pose* T_w_curr) {
+  LvoDeviceGuard _dev(c);
   int r = LVO_OK;
   if (T_last_curr) r = set_pose(c, lane, 3, T_last_curr);
   if (r == LVO_OK && T_w_curr) r = set_pose(c, lane, 4, T_w_curr);
@@ -970,6 +1005,7 @@ int lvo_set_odometry_state(lvo_ctx* c, int lane, const lvo_pose* T_last_curr, co
 
 // ---------------------------------------------------------------------------------------------------------------
 int lvo_probe_fetch(lvo_ctx* c, int lane, int what, void* out, size_t cap_bytes, size_t* n_bytes) {
+  LvoDeviceGuard _dev(c);
   if (!c || lane < 0 || lane >= c->lanes) return LVO_E_BADARG;
   LVO_TRY(sync_state(c));
   const LaneState& s = c->h_ls[lane];
@@ -1036,6 +1072,7 @@ int lvo_probe_fetch(lvo_ctx* c, int lane, int what, void* out, size_t cap_bytes,
 
 // ---------------------------------------------------------------------------------------------------------------
 int lvo_voxel_downsample(lvo_ctx* c, lvo_cloud_view in, float leaf, lvo_cloud_out* out) {
+  LvoDeviceGuard _dev(c);
   if (!c || !out || !(leaf > 0.f)) return LVO_E_BADARG;
   LVO_TRY(check_view(c, in, (size_t)c->map.vx.cap_items));
   if (in.n * in.stride > (size_t)std::max(c->P, std::max(c->map.map_cap[0], c->map.map_cap[1])) * 64) return LVO_E_CAPACITY;
@@ -1055,6 +1092,7 @@ int lvo_voxel_downsample(lvo_ctx* c, lvo_cloud_view in, float leaf, lvo_cloud_ou
 }
 
 int lvo_voxel_downsample_dev(lvo_ctx* c, const lvo_point* d_in, size_t n, float leaf, lvo_point* d_out, size_t* n_out, float* ms) {
+  LvoDeviceGuard _dev(c);
   if (!c || !d_in || !d_out || !n_out || !(leaf > 0.f)) return LVO_E_BADARG;
   if (n > (size_t)c->map.vx.cap_items) { lvo_set_error(c, "input cloud exceeds the voxel engine capacity"); return LVO_E_CAPACITY; }
   c->launches = 0;
@@ -1077,6 +1115,7 @@ int lvo_voxel_downsample_dev(lvo_ctx* c, const lvo_point* d_in, size_t n, float 
 }
 
 int lvo_knn(lvo_ctx* c, lvo_cloud_view cloud, lvo_cloud_view queries, int K, float max_sq, int* ind, float* sq) {
+  LvoDeviceGuard _dev(c);
   if (!c || !ind || !sq || (K != 1 && K != 5)) return LVO_E_BADARG;
   LVO_TRY(check_view(c, cloud, (size_t)c->map.map_cap[1])); LVO_TRY(check_view(c, queries, (size_t)c->P));
   c->launches = 0;
@@ -1113,6 +1152,7 @@ __global__ void k_setup_batch_problems(GridProblem* prob, int S, const float4* m
 
 int lvo_depth_associate(lvo_ctx* c, lvo_cloud_view sweep, const lvo_camera* cam, const float* keypoints_uv, size_t n_kp, float* depth_out, int* valid_out,
                         int* nn_out, lvo_cloud_out* depth_cloud_or_null) {
+  LvoDeviceGuard _dev(c);
   if (!c || !cam || (n_kp && (!keypoints_uv || !depth_out || !valid_out))) return LVO_E_BADARG;
   LVO_TRY(check_view(c, sweep, (size_t)c->P));
   if (n_kp > (size_t)c->P) { lvo_set_error(c, "too many keypoints"); return LVO_E_CAPACITY; }
@@ -1160,6 +1200,7 @@ int lvo_depth_associate(lvo_ctx* c, lvo_cloud_view sweep, const lvo_camera* cam,
 
 int lvo_knn5_throughput(lvo_ctx* c, const lvo_point* d_maps, const int* map_counts, const lvo_point* d_queries, const int* query_counts, int S, int reps,
                         int* d_ind_out, float* d_sq_out, float* ms) {
+  LvoDeviceGuard _dev(c);
   if (!c || !d_maps || !map_counts || !d_queries || !query_counts || S < 1 || reps < 1 || !d_ind_out || !d_sq_out || !ms) return LVO_E_BADARG;
   std::vector<unsigned> moff(S + 1, 0), qoff(S + 1, 0);
   int maxm = 1, maxq = 1;
