@@ -552,7 +552,8 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 3) k_lessflat_voxel(Extrac
   extern __shared__ unsigned long long skeys[];  // NT * 17 keys (padded)
   __shared__ float s_red[6][NT / 32];
   __shared__ int s_i[2];
-  __shared__ unsigned s_scan[33];
+  __shared__ unsigned s_scan[64];
+  int ph = 0;   // double-buffer phase of block_flag_rank
   const int lane = blockIdx.y, ring = blockIdx.x;
   const LaneState& s = a.ls[lane];
   const int S = s.scan_start[ring], E = s.scan_end[ring];
@@ -608,7 +609,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 3) k_lessflat_voxel(Extrac
     const int k = base + threadIdx.x;
     const bool c = (k <= E - 1) && label[k] <= 0;
     unsigned tot;
-    const unsigned ex = block_excl_scan(c ? 1u : 0u, s_scan, &tot);
+    const unsigned ex = block_flag_rank(c, s_scan, ph++, &tot);
     if (c) {
       const float4 p = P[k];
       unsigned idx;
@@ -632,7 +633,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 3) k_lessflat_voxel(Extrac
     const int t = base + threadIdx.x;
     const bool head = t < ncand && (t == 0 || cand_idx[t] != cand_idx[t - 1]);
     unsigned tot;
-    const unsigned ex = block_excl_scan(head ? 1u : 0u, s_scan, &tot);
+    const unsigned ex = block_flag_rank(head, s_scan, ph++, &tot);
     if (head) run_pos[carry + (int)ex] = (unsigned short)t;
     carry += (int)tot;
   }
@@ -666,7 +667,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 3) k_lessflat_voxel(Extrac
     bool head = false;
     if (t < nruns) head = (t == 0) || ((skeys[pad16(t)] >> 32) != (skeys[pad16(t - 1)] >> 32));
     unsigned tot;
-    const unsigned ex = block_excl_scan(head ? 1u : 0u, s_scan, &tot);
+    const unsigned ex = block_flag_rank(head, s_scan, ph++, &tot);
     if (head) {
       const unsigned long long v = skeys[pad16(t)] >> 32;
       float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;

@@ -49,6 +49,21 @@ __device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* sm, un
   return r;
 }
 
+// Stable compaction rank of one FLAG per thread over the block, for loops that compact chunk after chunk: rank = number of set flags in
+// lower threads, *total = set flags in the block.  One ballot per warp and ONE barrier per call (block_excl_scan: two shuffle scans and
+// three barriers); `sm` needs 2 * 32 unsigned and `phase` must alternate 0 / 1 between consecutive calls (double buffering).
+__device__ __forceinline__ unsigned block_flag_rank(bool flag, unsigned* sm, int phase, unsigned* total) {
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const unsigned m = __ballot_sync(0xffffffffu, flag);
+  unsigned* cnt = sm + 32 * (phase & 1);
+  if (lane == 0) cnt[w] = __popc(m);
+  __syncthreads();
+  unsigned pre = 0, tot = 0;
+  for (unsigned ww = 0; ww < nw; ++ww) { const unsigned c = cnt[ww]; tot += c; if (ww < w) pre += c; }
+  *total = tot;
+  return pre + __popc(m & ((1u << lane) - 1u));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // exclusive scan, in place, n from device memory
 // ---------------------------------------------------------------------------------------------------------------

@@ -32,3 +32,19 @@ def lvo_mod():
 def synth():
     from oracle_py import Synth
     return Synth()
+
+
+def record_metric(name, value):
+    """Measured quantities of the parity tests (e.g. how many kNN rows differ from the oracle after the poses have drifted apart by
+    rounding) go to gpurun_out/test_metrics.json when that directory exists, so that they can be quoted in profiles/."""
+    import json
+    d = os.path.join(ROOT, "gpurun_out")
+    if not os.path.isdir(d):
+        return
+    p = os.path.join(d, "test_metrics.json")
+    try:
+        cur = json.load(open(p)) if os.path.exists(p) else {}
+    except Exception:
+        cur = {}
+    cur[name] = value
+    json.dump(cur, open(p, "w"), indent=1)

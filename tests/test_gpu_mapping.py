@@ -84,6 +84,8 @@ def test_scan_to_map_from_imported_state(lvo_mod, synth, model, cfg, seq):
         assert (s.map_corner_total, s.map_surf_total) == (len(lvo.map_export(0, 0)[0]), len(lvo.map_export(0, 1)[0]))
         reg_o = info["registered"]
         assert reg_g.shape == reg_o.shape and np.abs(reg_g - reg_o).max() < 1e-3
+    from conftest import record_metric
+    record_metric(f"mapping_knn_and_accept_rows_differing_from_oracle/model{model}_seq{seq}", {"differ": int(flips), "rows": int(rows), "frames": len(frames)})
     assert flips <= 0.002 * max(rows, 1), f"{flips} of {rows} kNN / accept rows differ"
     lvo.close()
 
