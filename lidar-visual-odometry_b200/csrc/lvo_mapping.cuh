@@ -875,7 +875,7 @@ static inline void lvo_launch_mapping(cudaStream_t st, MapArgs a, const SolveArg
     else k_map_fit<<<ga, 128, 0, st>>>(a);
     if (launches) *launches += 1;
     SolveArgs sa = solve_proto;
-    sa.which = 1; sa.outer = o; sa.n_outer = outer_iters; sa.factors = a.factors; sa.factor_cap = a.factor_cap; sa.distort = 0; sa.lane0 = 0;  // LidarEdgeFactor(..., 1.0), :610
+    sa.which = 1; sa.outer = o; sa.n_outer = outer_iters; sa.factors = a.factors; sa.factor_cap = a.factor_cap; sa.distort = 0; sa.lane0 = 0; sa.reset_cnt = nullptr;  // LidarEdgeFactor(..., 1.0), :610
     LVO_MARK(tm, LVO_ST_MAP_SOLVER, st);
     lvo_launch_lm(st, sa, lanes, 16384);
     if (launches) *launches += 2;

@@ -103,6 +103,7 @@ __global__ void k_odo_begin(OdoArgs a) {
   s.odo_done = 0; s.stats.odo_outer_executed = 0;
   for (int o = 0; o < LVO_MAX_OUTER; ++o) { s.stats.odo_corner_corr[o] = 0; s.stats.odo_plane_corr[o] = 0; s.stats.odo_lm_iters[o] = 0; s.stats.odo_final_cost[o] = 0; s.stats.odo_slow[o] = 0; s.stats.odo_certified[o] = 0; }
   for (int k = 0; k < 6; ++k) s.stats.odo_slow_why[k] = 0;
+  a.slow_cnt[lane] = 0;
 }
 
 struct Best { float d; int pos; int j; };
@@ -794,13 +795,12 @@ static inline void lvo_launch_odometry(cudaStream_t st, OdoArgs a, const SolveAr
     for (int o = 0; o < outer_iters; ++o) {
       a.outer = o;
       LVO_MARK(tm, LVO_ST_ODO_ASSOC, st);
-      cudaMemsetAsync(a.slow_cnt + l0, 0, sizeof(int) * nl, st);
-      k_odo_assoc_fast<<<gf, 128, 0, st>>>(a);
+      k_odo_assoc_fast<<<gf, 128, 0, st>>>(a);   // (slow_cnt is zero here: k_odo_begin before the loop, k_lm_solve after every iteration)
       if (launches) *launches += 1;
       if (o == 0) k_odo_assoc<8><<<ga, 256, 0, st>>>(a);   // first iteration: more features lack a nearby candidate
       else k_odo_assoc<32><<<gs, 256, 0, st>>>(a);
       SolveArgs sa = solve_proto;
-      sa.which = 0; sa.outer = o; sa.n_outer = outer_iters; sa.factors = a.factors; sa.factor_cap = a.factor_cap; sa.distort = a.distortion != 0; sa.lane0 = l0;
+      sa.which = 0; sa.outer = o; sa.n_outer = outer_iters; sa.factors = a.factors; sa.factor_cap = a.factor_cap; sa.distort = a.distortion != 0; sa.lane0 = l0; sa.reset_cnt = a.slow_cnt;
       LVO_MARK(tm, LVO_ST_ODO_SOLVER, st);
       lvo_launch_lm(st, sa, nl, nfeat_cap);
       if (launches) *launches += 2;

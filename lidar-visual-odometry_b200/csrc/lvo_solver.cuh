@@ -290,6 +290,7 @@ struct SolveArgs {
   int distort;                // != 0: factors may carry an interpolation ratio s != 1 (scan-to-scan with DISTORTION 1)
   int n_outer;                // outer iterations of the frame (stats slots to fill when the loop is cut short)
   int fixpoint_skip;          // LVO_OPT_FIXPOINT_SKIP
+  int* reset_cnt;             // [lanes] or null: per-lane counter the solve zeroes for the next outer iteration (the scan-to-scan slow-list length)
 };
 
 struct LmShared {
@@ -415,6 +416,7 @@ __global__ void __launch_bounds__(LVO_LM_THREADS, LVO_LM_MINB) k_lm_solve(SolveA
   const bool lead = threadIdx.x == 0;
   const int lane = a.lane0 + blockIdx.x;
   LaneState& s = a.ls[lane];
+  if (a.reset_cnt && threadIdx.x == 0) a.reset_cnt[lane] = 0;   // the association kernels of this iteration are through with it
   if (a.which == 0 ? (s.odo_inited == 0 || s.odo_done != 0) : (s.map_too_small != 0 || s.map_done != 0)) return;
   const int nslots = a.which == 0 ? (s.n_sharp + s.n_flat) : (s.n_stack[0] + s.n_stack[1]);
   const LvoFactor* F = a.factors + (size_t)lane * a.factor_cap;
