@@ -57,7 +57,9 @@ struct OdoArgs {
 // with j unchanged the filters are unchanged.  All three certified: the factor record stands and the feature is skipped.  Margins of
 // 1e-4 relative + 1e-5 m dwarf float rounding and only decide WHETHER the shortcut is taken.
 #define LVO_ODO_FEW 24       // uncertified features per block of 128 below which they are handed to the warp-per-feature kernel
+#ifndef LVO_ODO_SLACK
 #define LVO_ODO_SLACK 0.05f   // extra radius (m) scanned around a full association so that the next iterations can be certified
+#endif
 __device__ __forceinline__ float odo_guard_of(float d2_other, float region) {
   const float g = fminf(sqrtf(d2_other), region);
   return fmaxf(g * 0.9999f - 1e-5f, 0.f);
