@@ -6,7 +6,7 @@
 #   2. `--set full` of the ten 5-NN launches of one frame               -> gpurun_out/<tag>_knn.ncu-rep  + raw CSV
 #   3. `--set full` of the other hot kernels of one frame               -> gpurun_out/<tag>_hot.ncu-rep  + raw CSV
 # usage (under gpurun): profiles/capture_r2.sh <tag>
-tag=${1:-r2f}
+tag=${1:-r2h}
 mkdir -p gpurun_out
 B="python bench.py --lanes 128 --groups 1 --steps 4 --warmup 3 --skip-e2e --no-extras --knn-frames 0 --no-cpu-baseline --no-full-schedule --no-single"
 timeout 300 $B > gpurun_out/${tag}_plain.json 2> gpurun_out/${tag}_plain.err; echo "plain rc=$?"
