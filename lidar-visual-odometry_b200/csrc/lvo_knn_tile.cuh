@@ -26,7 +26,7 @@
 #define LVO_KT_CS (LVO_KT_RUN + 4)
 #define LVO_QSORT_MAX 8192      // queries per (lane, type) that k_map_qsort orders
 #define LVO_KT_BULK_MIN 64      // rows of at least this many points (1 KB) go through cp.async.bulk; shorter ones are loaded by the lanes
-                                // (a bulk copy costs ~0.2 us of the SM's copy unit whatever its size: measured, profiles/r2_knn_tile_notes.md)
+                                // (a bulk copy costs ~0.2 us of the SM's copy unit whatever its size: measured while tuning this kernel)
 #define LVO_KT_MAX_GROUPS 5     // a chunk whose 32 queries fall into more cell rows than this is searched thread-per-query instead
 
 // ---- mbarrier / bulk-copy PTX (sm_90+; SASS: SYNCS.* and UBLKCP) ---------------------------------------------------------------

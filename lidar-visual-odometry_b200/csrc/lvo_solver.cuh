@@ -13,10 +13,11 @@
 //     discarded when a tolerance fires, rejected and invalid steps counted as iterations — A19) run by thread 0 in
 //     double.  The damped 6x6 system is solved from the normal equations (Cholesky) instead of a QR of the stacked
 //     Jacobian: same minimiser, difference O(cond * eps), far below the 1e-4 m / 1e-5 rad pose tolerance.
-// One thread-block CLUSTER (up to 8 CTAs, portable size) per lane runs the WHOLE inner loop (<= max_iters evaluations of all
-// factors) without returning to the host: every CTA reduces its slice of the factors to 28 doubles in its own shared
-// memory, cluster.sync(), CTA 0 adds the 8 partials in rank order through distributed shared memory, its thread 0 takes
-// the trust-region decision and writes the next evaluation point into every CTA's shared memory, cluster.sync().
+// One CTA of LVO_LM_THREADS threads per lane runs the WHOLE inner loop (<= max_iters evaluations of all factors) without returning to
+// the host: the threads stride over the lane's factor slots, 28 doubles are reduced by warp shuffles and then across the warps in rank
+// order through shared memory (bitwise deterministic), thread 0 takes the trust-region decision and publishes the next evaluation
+// point.  (Round 1 spread a lane over a cluster of up to 8 CTAs with DSMEM reductions; two cluster barriers per evaluation cost more
+// than the extra SMs gave once every SM had a lane of its own.)
 // Each LM iteration costs one pass over the factors because cost, J^T W J and J^T r at the candidate are accumulated
 // together (if the step is accepted they are the next iteration's system).
 #pragma once
@@ -106,7 +107,7 @@ __device__ inline bool lsq_qr_5x3(double A[15], double b[5], double y[3]) {
 
 // Cholesky solve of a 6x6 SPD system (A full row-major, destroyed).  false if not positive definite.
 // Fully unrolled and division-free apart from one reciprocal square root per pivot: this runs on ONE thread while the
-// rest of the cluster waits, so its dependent-latency chain is the critical path of every LM iteration.
+// rest of the CTA waits, so its dependent-latency chain is the critical path of every LM iteration.
 __device__ __forceinline__ bool chol6_solve(double A[36], const double b[6], double y[6]) {
   double inv[6];
 #pragma unroll
