@@ -216,9 +216,19 @@ __global__ void k_vx_centroid(VoxelEngine e) {
   }
 }
 
-__global__ void k_vx_copy_cnt(VoxelEngine e) {
+// per-segment output offsets: exclusive scan of seg_out_cnt (at most a few ten thousand segments: one block, one launch)
+__global__ void __launch_bounds__(1024) k_vx_seg_offsets(VoxelEngine e) {
+  __shared__ unsigned sm[33];
   const int nsegs = *e.d_nsegs;
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nsegs; s += gridDim.x * blockDim.x) e.seg_out_start[s] = e.seg_out_cnt[s];
+  unsigned carry = 0;
+  for (int base = 0; base < nsegs; base += blockDim.x) {
+    const int s = base + threadIdx.x;
+    const unsigned v = s < nsegs ? e.seg_out_cnt[s] : 0u;
+    unsigned tot;
+    const unsigned ex = block_excl_scan(v, sm, &tot);
+    if (s < nsegs) e.seg_out_start[s] = carry + ex;
+    carry += tot;
+  }
 }
 
 // n_items_cap / n_segs_cap bound the grids for this invocation (<= engine capacities).
@@ -233,7 +243,6 @@ static inline void lvo_voxel_run(cudaStream_t st, const VoxelEngine& e, int n_it
   k_vx_heads<<<gi, 256, 0, st>>>(e);
   lvo_scan_exclusive(st, e.outpos, e.d_n, n_items_cap, e.d_n_out, e.scan, launches);
   k_vx_centroid<<<gi, 256, 0, st>>>(e);
-  k_vx_copy_cnt<<<gs, 256, 0, st>>>(e);
-  lvo_scan_exclusive(st, e.seg_out_start, e.d_nsegs, n_segs_cap, nullptr, e.scan, launches);
+  k_vx_seg_offsets<<<1, 1024, 0, st>>>(e);
   if (launches) *launches += 7;
 }
